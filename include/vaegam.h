@@ -1,0 +1,277 @@
+/*
+ * vaegam.h — C ABI of libvaegam_sm100.so: the B200 (sm_100a) hot path of VAE-GAM.
+ *
+ * The reference (dannyfa/VAE-GAM) has no FFI: its hot path is Python calling PyTorch
+ * library kernels.  Each entry point below names the reference call site(s) it
+ * replaces (file:line in the reference tree).  The drop-in Python modules in
+ * vae-gam_b200/ (vae_reg_GP.py, gp.py) bind these through ctypes; INTEGRATION.md shows
+ * the binding a reference maintainer would add.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers + sizes; every pointer is DEVICE memory owned by the caller unless
+ *     a parameter is documented as host memory; no allocation, no ownership transfer;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing
+ *     synchronises the host, so every call is CUDA-graph capturable;
+ *   - return 0 on success or a negative VG_E* code; vg_last_error() gives a message
+ *     (thread-local);
+ *   - activations are fp32, channels-last (N, D, H, W, C); weights keep PyTorch's
+ *     layouts (Conv3d: (Cout,Cin,kD,kH,kW); ConvTranspose3d: (Cin,Cout,kD,kH,kW);
+ *     Linear: (out,in)), so checkpoints interchange with the reference byte for byte;
+ *   - BatchNorm3d(track_running_stats=False) is never a kernel of its own: batch
+ *     statistics are reduced per (group, channel) — group = image_index / group_size, so
+ *     the 9 decoder passes keep 9 separate statistics (vae_reg_GP.py:326-343 calls
+ *     decode 9 times) — and the normalisation is folded into the consumer's operand load.
+ */
+#ifndef VAEGAM_H_
+#define VAEGAM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VG_OK 0
+#define VG_EINVAL (-1)  /* bad shape / null pointer / unsupported channel count */
+#define VG_ECUDA (-2)   /* CUDA runtime error; see vg_last_error() */
+#define VG_ENOTPD (-3)  /* reported through a device flag: non-positive-definite pivot */
+
+#define VG_ACT_NONE 0
+#define VG_ACT_RELU 1
+#define VG_ACT_SIGMOID 2
+
+/* library identity / diagnostics */
+int vg_version(void);                 /* 100 * major + minor */
+const char* vg_last_error(void);      /* thread-local, never NULL */
+int vg_sm_count(void);                /* SMs of the current device (148 on B200) */
+long long vg_launch_count(void);      /* kernels launched by this library so far (process-wide) */
+
+/* ------------------------------------------------------------------------------------
+ * 3-D convolution family.  One descriptor covers Conv3d and ConvTranspose3d.
+ * Replaces torch nn.Conv3d / nn.ConvTranspose3d forward + autograd backward at
+ * vae_reg_GP.py:238-242 (conv1..5, layers :189-193) and :260-264 (convt1..5, :211-215).
+ * ---------------------------------------------------------------------------------- */
+typedef struct VgConvDesc {
+  int32_t transposed;      /* 0: Conv3d, 1: ConvTranspose3d */
+  int32_t cin, cout;       /* module in/out channels; each in {1, 8, 16} */
+  int32_t k[3];            /* kernel (kD,kH,kW), each <= 5 */
+  int32_t stride;          /* 1 or 2 (same in all dims) */
+  int32_t pad[3];          /* ConvTranspose3d padding (0 for Conv3d) */
+  int32_t opad[3];         /* ConvTranspose3d output_padding */
+  int32_t in[3];           /* input grid (D,H,W) */
+  int32_t out[3];          /* output grid (D,H,W) — must satisfy the PyTorch size formula */
+  int32_t n;               /* images */
+  int32_t group_size;      /* images per BatchNorm statistics group (n % group_size == 0) */
+  int64_t x_img_stride;    /* floats between consecutive images of x / dx; 0 = dense (D*H*W*cin) */
+  int64_t y_img_stride;    /* floats between consecutive images of y / dy; 0 = dense (D*H*W*cout) */
+} VgConvDesc;
+
+/* y = act(conv(x * in_scale[g,ci] + in_shift[g,ci]) + bias); zero padding is applied
+ * AFTER the affine (it pads the normalised tensor).  in_scale/in_shift: (n/group_size, cin)
+ * or NULL.  out_stats: (n/group_size, cout, 2) doubles, ACCUMULATED with sum(y), sum(y^2)
+ * (caller zeroes) or NULL. */
+int vg_conv_fwd(const VgConvDesc* d, const float* x, const float* w, const float* bias,
+                const float* in_scale, const float* in_shift, float* y, int act,
+                double* out_stats, void* stream);
+
+/* dx = conv^T(dy) w.r.t. the (affine-folded) input.  dy must already be the gradient
+ * w.r.t. the pre-activation.  Epilogue modes:
+ *   mask_act != NULL                : dx *= (mask_act > 0)        (ReLU of the producer)
+ *   bn_x != NULL                    : bn_sums (n/group_size, cin, 2) doubles accumulate
+ *                                     sum(dx), sum(dx * xhat), xhat = bn_x*bn_istd - bn_mistd
+ *                                     (bn_istd, bn_mistd: (groups, cin) = 1/std, mean/std)
+ *   dx == NULL                      : nothing is stored (statistics only; bn1 of conv1). */
+int vg_conv_dgrad(const VgConvDesc* d, const float* dy, const float* w, float* dx,
+                  const float* mask_act, const float* bn_x, const float* bn_istd,
+                  const float* bn_mistd, double* bn_sums, void* stream);
+
+/* dw (PyTorch layout, ACCUMULATED — caller zeroes) and dbias (cout, accumulated) from
+ * x (with the same affine fold as the forward) and dy (gradient w.r.t. pre-activation). */
+int vg_conv_wgrad(const VgConvDesc* d, const float* x, const float* dy, const float* in_scale,
+                  const float* in_shift, float* dw, float* dbias, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Batch-norm helpers (nn.BatchNorm3d(track_running_stats=False), vae_reg_GP.py:194-196,
+ * 216-218; applied at :238,240,242,260,262,264).
+ * ---------------------------------------------------------------------------------- */
+/* stats (groups, c, 2) doubles accumulate sum(x), sum(x^2) over a channels-last tensor of
+ * n images x `spatial` voxels x c channels. */
+int vg_bn_stats(const float* x, int n, int group_size, long long spatial, int c, double* stats,
+                void* stream);
+/* From stats -> fold coefficients, per (group, channel):
+ *   scale = gamma/std, shift = beta - mean*scale, istd = 1/std, mistd = mean/std,
+ *   std = sqrt(var_biased + 1e-5), count = group_size * spatial. */
+int vg_bn_finalize(const double* stats, const float* gamma, const float* beta, int groups, int c,
+                   double count, float* scale, float* shift, float* istd, float* mistd,
+                   void* stream);
+/* dx = scale[g,c] * (dy - m1 - xhat*m2) [* (x > 0) if relu_mask], m1 = sums[g,c,0]/count,
+ * m2 = sums[g,c,1]/count; dgamma[c] += sum_g sums[g,c,1]; dbeta[c] += sum_g sums[g,c,0]
+ * (dgamma/dbeta may be NULL; they are accumulated by one thread block). In-place (dx == dy) ok. */
+int vg_bn_bwd_apply(const float* dy, const float* x, const double* sums, const float* scale,
+                    const float* istd, const float* mistd, int n, int group_size,
+                    long long spatial, int c, double count, int relu_mask, float* dx,
+                    float* dgamma, float* dbeta, void* stream);
+/* (n, c, spatial) <-> (n, spatial, c) */
+int vg_nchw_to_nhwc(const float* src, float* dst, int n, int c, long long spatial, void* stream);
+int vg_nhwc_to_nchw(const float* src, float* dst, int n, int c, long long spatial, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Linear layers (nn.Linear fc1..fc8, vae_reg_GP.py:197-210, used at :244-251, :255-258).
+ * ---------------------------------------------------------------------------------- */
+/* y (m,n) = act(x (m,k) @ w (n,k)^T + bias (n)) */
+int vg_linear_fwd(const float* x, const float* w, const float* bias, float* y, int m, int n,
+                  int k, int act, void* stream);
+/* Given dy (m,n) w.r.t. the layer OUTPUT and, if relu_out != NULL, the saved output y
+ * (gradient is masked by y > 0): dx (m,k) (may be NULL), dw (n,k) and db (n) ACCUMULATED. */
+int vg_linear_bwd(const float* dy, const float* relu_out, const float* x, const float* w,
+                  float* dx, float* dw, float* db, int m, int n, int k, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Latent sample + KL (vae_reg_GP.py:321-325 LowRankMultivariateNormal(mu,u,d).rsample(),
+ * :400 kl_divergence(latent_dist, z_prior); torch lowrank_multivariate_normal.py:214-223,
+ * kl.py:342-372).  heads: (3, b, 32) = [mu | u | log d] (fc41/42/43 outputs, fc43 BEFORE exp).
+ * zcat: (9, b, 41) rows [z | onehot(j)] for the 9 decoder passes (:326-330,339-343).
+ * ---------------------------------------------------------------------------------- */
+int vg_latent_fwd(const float* heads, const float* eps_w, const float* eps_d, int b, float* z,
+                  float* klz, float* d_out, float* zcat, int* jitter_flag, void* stream);
+/* dheads (3,b,32) from dzcat (9,b,41) (summed over the 9 passes) and dklz (b). */
+int vg_latent_bwd(const float* heads, const float* eps_w, const float* eps_d, const float* d_used,
+                  const float* dzcat, const float* dklz, int b, float* dheads, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Gains: linear + sparse-GP posterior, Cholesky sample, HRF FIR, KLs, for all K covariates
+ * in one launch (one warp per covariate GP).  Replaces vae_reg_GP.py:345-378, :266-281,
+ * :283-305 and gp.py:41-65,67-110,113-136.  Internals are fp64.
+ * ---------------------------------------------------------------------------------- */
+typedef struct VgGainParams {       /* device pointers, one entry per covariate (K = 8) */
+  const float* sa[8];               /* (1,1) */
+  const float* logstd[8];           /* (1,1) */
+  const float* qu_m[8];             /* (1,m)   NULL when !has_gp */
+  const float* qu_S[8];             /* (m,m) */
+  const float* logkvar[8];          /* () */
+  const float* logls[8];            /* () */
+  const float* xu[8];               /* (m) inducing locations (constant) */
+  int32_t has_gp[8];                /* vae_reg_GP.py:352 -> {0,1,1,1,1,1,1,0} */
+  int32_t hrf[8];                   /* vae_reg_GP.py:377 -> {neural_covariates,0,...} */
+} VgGainParams;
+typedef struct VgGainGrads {
+  float* sa[8]; float* logstd[8]; float* qu_m[8]; float* qu_S[8]; float* logkvar[8]; float* logls[8];
+} VgGainGrads;
+
+size_t vg_gain_workspace_bytes(int b, int m);
+/* covariates (b,8) fp32; eps (8,b); taps: 15 HRF taps (fp64, device).  Outputs: g (8,b) fp32
+ * (post-HRF), kl_terms (8,2) fp64 = [linear-weight KL, GP KL] per covariate, beta_mean (8,b) and
+ * beta_var (8,b) = diag(beta_cov) for the TensorBoard hook (may be NULL), status (8) int:
+ * 0 ok, else 1-based index of the failed pivot (covariance / qu_S not PD). */
+int vg_gain_fwd(const VgGainParams* p, const float* covariates, const float* eps,
+                const double* taps, int b, int m, float* g, double* kl_terms, float* beta_mean,
+                float* beta_var, int* status, void* workspace, size_t workspace_bytes,
+                void* stream);
+/* dg (8,b): dLoss/dg; kl_scale: gradient weight of the KL terms (gp_kl_scale).  Grads are
+ * ACCUMULATED into the VgGainGrads pointers (fp32). */
+int vg_gain_bwd(const VgGainParams* p, const VgGainGrads* grads, const float* covariates,
+                const float* eps, const double* taps, const float* dg, double kl_scale, int b,
+                int m, void* workspace, size_t workspace_bytes, void* stream);
+/* GP posterior at arbitrary query points (plot_GPs, vae_reg_GP.py:655-666; gp.GP.evaluate_posterior,
+ * gp.py:67-110).  k_var, ls: DEVICE scalars (the reference passes 0-d tensors).  f_bar (nq),
+ * var (nq) = diag(Sigma) (may be NULL); sigma (nq,nq) optional — NULL skips the O(nq^2) matrix —
+ * and then a_ws, an (nq, m) fp64 scratch, is required. */
+int vg_gp_posterior(const float* xu, int m, const float* k_var, const float* ls, const float* qu_m,
+                    const float* qu_S, const float* xq, int nq, float* f_bar, float* var,
+                    float* sigma, double* a_ws, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Fused reconstruction + likelihood + GLM regulariser (vae_reg_GP.py:380, :388-390, :401-405).
+ * maps (9,b,VP): decoder outputs (base, 8 covariate maps), every row padded to
+ * VP = round_up(V,4) floats so rows are 16-byte aligned (V = 70315 is odd); g (8,b); x (b,V)
+ * dense; eps (VP) fp32 copy of the fp64 epsilon parameter (.float() at :402); glm (8,VP) fp32
+ * transposed GLM maps.  One HBM pass; partial sums are reduced deterministically in a second
+ * tiny kernel.  dpre has the (9,b,VP) layout of maps; deps is (VP).
+ * ---------------------------------------------------------------------------------- */
+size_t vg_recon_workspace_bytes(int b, long long v);
+/* logp (b), norms (8,b) = ||g_i D_i[b] - G_i||_2.  Optional cons (8,b,V) and x_rec (b,V)
+ * (R5 side outputs, NULL in training). */
+int vg_recon_loss_fwd(const float* maps, const float* g, const float* x, const float* eps,
+                      const float* glm, int b, long long v, float* logp, float* norms,
+                      float* cons, float* x_rec, void* workspace, size_t workspace_bytes,
+                      void* stream);
+/* Backward of  tot = -mean_b(logp) + lam * b * sum_{i,b} norms  w.r.t. the decoder
+ * PRE-sigmoid activations (dpre = dD * D * (1-D)), g and epsilon:
+ *   dpre (9,b,V), dg (8,b), deps (V, fp32; caller adds into the fp64 grad). */
+int vg_recon_loss_bwd(const float* maps, const float* g, const float* x, const float* eps,
+                      const float* glm, const float* norms, int b, long long v, float lam,
+                      float* dpre, float* dg, float* deps, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Fused Adam over a flat parameter buffer (torch.optim.Adam defaults, vae_reg_GP.py:179,429).
+ * fp32 segment [0,n32) and fp64 segment (epsilon).  step_count: device int64 incremented here.
+ * grad_scale multiplies the gradient (1/world_size after the NCCL sum).
+ * ---------------------------------------------------------------------------------- */
+int vg_adam_step(float* p32, const float* g32, float* m32, float* v32, long long n32, double* p64,
+                 const double* g64, double* m64, double* v64, long long n64, float lr, float beta1,
+                 float beta2, float eps, float grad_scale, long long* step_count, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Whole training step (vae_reg_GP.py:307-413 forward, :427-428 backward) chained on one
+ * stream with no host synchronisation.  See vaegam/step.py for the buffer tables.
+ * ---------------------------------------------------------------------------------- */
+#define VG_NUM_PARAMS 97
+typedef struct VgStepConfig {
+  int32_t b;                 /* minibatch */
+  int32_t m;                 /* inducing points */
+  int32_t neural_covariates; /* HRF on covariate 1 */
+  int32_t want_maps;         /* also emit cons / x_rec (return_latent_rec) */
+  float gp_kl_scale;
+  float glm_reg_scale;
+} VgStepConfig;
+
+size_t vg_step_workspace_bytes(const VgStepConfig* cfg);
+/* params: VG_NUM_PARAMS device pointers in the order of vaegam/step.py:PARAM_ORDER (the
+ * reference's named_parameters() order; epsilon is fp64).  consts: xu (6 pointers, (m)),
+ * glm_t (8,V) fp32, taps (15) fp64.  inputs: x (b,V), covariates (b,8), eps_w (b,1),
+ * eps_d (b,32), eps_g (8,b).  outputs: out_scalars (8) fp64 = [tot, neg_elbo, gp_kl, glm_reg,
+ * mean logp, mean klz, 0, 0]; z (b,32); maps (9,b,VP), VP = round_up(V,4); g (8,b); optional
+ * cons (8,b,V) / x_rec (b,V) dense. */
+typedef struct VgStepIO {
+  const void* params[VG_NUM_PARAMS];
+  void* grads[VG_NUM_PARAMS];          /* backward only; epsilon grad is fp64 */
+  const float* xu[6];
+  const float* glm_t;
+  const double* taps;
+  const float* x;
+  const float* covariates;
+  const float* eps_w;
+  const float* eps_d;
+  const float* eps_g;
+  double* out_scalars;
+  float* z;
+  float* maps;
+  float* g;
+  float* cons;
+  float* x_rec;
+  float* beta_mean;
+  float* beta_var;
+  int32_t* status;                     /* (16) ints: [0..7] gain status, [8] latent jitter flag */
+} VgStepIO;
+
+int vg_step_fwd(const VgStepConfig* cfg, const VgStepIO* io, void* workspace,
+                size_t workspace_bytes, void* stream);
+/* Gradients of out_scalars[0] are ACCUMULATED into io->grads (caller zeroes).  Must follow
+ * vg_step_fwd with the same cfg/io/workspace.  If stream2 != NULL the gain backward runs on
+ * it concurrently (fork/join through events; still capturable). */
+int vg_step_bwd(const VgStepConfig* cfg, const VgStepIO* io, void* workspace,
+                size_t workspace_bytes, void* stream);
+/* Encoder only (VAE.encode, vae_reg_GP.py:236-252): heads (3,b,32) = [mu | u | log d]. */
+int vg_encode_fwd(const VgStepConfig* cfg, const VgStepIO* io, float* heads, void* workspace,
+                  size_t workspace_bytes, void* stream);
+/* Decoder only (VAE.decode, :254-264) for n rows of zcat (n,41) treated as ONE BatchNorm batch. */
+size_t vg_decode_workspace_bytes(int n);
+int vg_decode_fwd(const VgStepIO* io, const float* zcat, int n, float* out, void* workspace,
+                  size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VAEGAM_H_ */

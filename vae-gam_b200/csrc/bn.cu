@@ -1,0 +1,221 @@
+// Batch-statistics BatchNorm helpers (nn.BatchNorm3d(track_running_stats=False),
+// vae_reg_GP.py:194-196,216-218).  The normalisation itself is folded into the consumer
+// convolution's operand load (conv.cu); what remains are the reductions that cannot be
+// produced by a convolution epilogue, the coefficient finalisation, the backward apply
+// and the layout changes at the conv <-> fully-connected seams.
+#include "common.cuh"
+
+namespace vg {
+
+// x: (n, spatial, c) channels-last.  grid = (blocks_per_image, n).
+template <int C>
+__global__ void __launch_bounds__(256)
+bn_stats_kernel(const float* __restrict__ x, long long spatial, int group_size, double* stats) {
+  __shared__ double sred[2 * C];
+  const int tid = threadIdx.x;
+  if (tid < 2 * C) sred[tid] = 0.0;
+  __syncthreads();
+  const int n = blockIdx.y;
+  const long long total = spatial * C;           // floats in this image
+  const float* xi = x + (size_t)n * total;
+  float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+  // each thread walks float4 lanes; with C in {1,8,16} and 256 threads the channel of a
+  // lane is fixed per thread when the stride (in floats) is a multiple of C.
+  if constexpr (C % 4 == 0) {
+    const long long nv = total / 4;
+    const long long stride = (long long)gridDim.x * blockDim.x;   // multiple of C/4 (256 % 4 == 0)
+    for (long long i = (long long)blockIdx.x * blockDim.x + tid; i < nv; i += stride) {
+      float4 v = ldg_stream(reinterpret_cast<const float4*>(xi) + i);
+      s1[0] += v.x; s1[1] += v.y; s1[2] += v.z; s1[3] += v.w;
+      s2[0] = fmaf(v.x, v.x, s2[0]); s2[1] = fmaf(v.y, v.y, s2[1]);
+      s2[2] = fmaf(v.z, v.z, s2[2]); s2[3] = fmaf(v.w, v.w, s2[3]);
+    }
+    const int c0 = (int)((((long long)blockIdx.x * blockDim.x + tid) * 4) % C);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      atomicAdd(&sred[2 * (c0 + j)], (double)s1[j]);
+      atomicAdd(&sred[2 * (c0 + j) + 1], (double)s2[j]);
+    }
+  } else {  // C == 1
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + tid; i < total; i += stride) {
+      const float v = __ldg(xi + i);
+      s1[0] += v;
+      s2[0] = fmaf(v, v, s2[0]);
+    }
+    const float a = warp_sum(s1[0]), b = warp_sum(s2[0]);
+    if ((tid & 31) == 0) {
+      atomicAdd(&sred[0], (double)a);
+      atomicAdd(&sred[1], (double)b);
+    }
+  }
+  __syncthreads();
+  if (tid < 2 * C) atomicAdd(stats + (size_t)(n / group_size) * 2 * C + tid, sred[tid]);
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, int groups, int c, double count,
+                                   float* scale, float* shift, float* istd, float* mistd) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= groups * c) return;
+  const int ch = i % c;
+  const double mean = stats[2 * i] / count;
+  double var = stats[2 * i + 1] / count - mean * mean;   // biased variance
+  if (var < 0) var = 0;
+  const double is = 1.0 / sqrt(var + 1e-5);
+  const double sc = (double)gamma[ch] * is;
+  scale[i] = (float)sc;
+  shift[i] = (float)((double)beta[ch] - mean * sc);
+  if (istd) istd[i] = (float)is;
+  if (mistd) mistd[i] = (float)(mean * is);
+}
+
+// dx = scale * (dy - m1 - xhat*m2) [* (x>0)];  one float4 (or scalar) per thread.
+template <int C>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                    const double* __restrict__ sums, const float* __restrict__ scale,
+                    const float* __restrict__ istd, const float* __restrict__ mistd, int group_size,
+                    long long spatial, double count, int relu_mask, float* dx) {
+  const int n = blockIdx.y;
+  const int grp = n / group_size;
+  const long long total = spatial * C;
+  const size_t base = (size_t)n * total;
+  constexpr int W = (C % 4 == 0) ? 4 : 1;
+  const long long nv = total / W;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+    float d[4], xv[4], o[4];
+    if constexpr (W == 4) {
+      float4 a = ldg_stream(reinterpret_cast<const float4*>(dy + base) + i);
+      float4 b = ldg_stream(reinterpret_cast<const float4*>(x + base) + i);
+      d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w;
+      xv[0] = b.x; xv[1] = b.y; xv[2] = b.z; xv[3] = b.w;
+    } else {
+      d[0] = dy[base + i];
+      xv[0] = x[base + i];
+    }
+    const int c0 = (int)((i * W) % C);
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      const int gc = grp * C + c0 + j;
+      const float m1 = (float)(sums[2 * gc] / count);
+      const float m2 = (float)(sums[2 * gc + 1] / count);
+      const float xh = fmaf(xv[j], istd[gc], -mistd[gc]);
+      float r = scale[gc] * (d[j] - m1 - xh * m2);
+      if (relu_mask && !(xv[j] > 0.f)) r = 0.f;
+      o[j] = r;
+    }
+    if constexpr (W == 4)
+      reinterpret_cast<float4*>(dx + base)[i] = make_float4(o[0], o[1], o[2], o[3]);
+    else
+      dx[base + i] = o[0];
+  }
+}
+
+__global__ void bn_param_grad_kernel(const double* __restrict__ sums, int groups, int c, float* dgamma,
+                                     float* dbeta) {
+  const int ch = threadIdx.x;
+  if (ch >= c) return;
+  double a = 0, b = 0;
+  for (int g = 0; g < groups; ++g) {
+    b += sums[2 * (g * c + ch)];
+    a += sums[2 * (g * c + ch) + 1];
+  }
+  if (dgamma) dgamma[ch] += (float)a;
+  if (dbeta) dbeta[ch] += (float)b;
+}
+
+// (n, c, spatial) -> (n, spatial, c) through a 32x33 shared tile
+__global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
+  // per image: src is (rows, cols), dst is (cols, rows)
+  __shared__ float tile[32][33];
+  const size_t img = (size_t)blockIdx.z * rows * cols;
+  int c = blockIdx.x * 32 + threadIdx.x;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int r = blockIdx.y * 32 + j;
+    if (r < rows && c < cols) tile[j][threadIdx.x] = src[img + (size_t)r * cols + c];
+  }
+  __syncthreads();
+  int r2 = blockIdx.y * 32 + threadIdx.x;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int c2 = blockIdx.x * 32 + j;
+    if (r2 < rows && c2 < cols) dst[img + (size_t)c2 * rows + r2] = tile[threadIdx.x][j];
+  }
+}
+
+static int transpose(const float* src, float* dst, int n, int rows, int cols, cudaStream_t st) {
+  dim3 grid(cdiv(cols, 32), cdiv(rows, 32), n), block(32, 8);
+  transpose_kernel<<<grid, block, 0, st>>>(src, dst, rows, cols);
+  VG_LAUNCH_CHECK();
+  return VG_OK;
+}
+
+}  // namespace vg
+
+using namespace vg;
+
+extern "C" int vg_bn_stats(const float* x, int n, int group_size, long long spatial, int c, double* stats,
+                           void* stream) {
+  VG_CHECK_ARG(x && stats && n > 0 && group_size > 0 && n % group_size == 0, "bad arguments");
+  long long per_img = spatial * c;
+  int bx = (int)((per_img / 4 + 255) / 256);
+  int cap = (4 * vg_sm_count() + n - 1) / n;
+  if (cap < 1) cap = 1;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  dim3 grid(bx, n);
+  if (c == 1) bn_stats_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(x, spatial, group_size, stats);
+  else if (c == 8) bn_stats_kernel<8><<<grid, 256, 0, as_stream(stream)>>>(x, spatial, group_size, stats);
+  else if (c == 16) bn_stats_kernel<16><<<grid, 256, 0, as_stream(stream)>>>(x, spatial, group_size, stats);
+  else { set_error("vg_bn_stats: channels must be 1, 8 or 16 (got %d)", c); return VG_EINVAL; }
+  VG_LAUNCH_CHECK();
+  return VG_OK;
+}
+
+extern "C" int vg_bn_finalize(const double* stats, const float* gamma, const float* beta, int groups, int c,
+                              double count, float* scale, float* shift, float* istd, float* mistd,
+                              void* stream) {
+  VG_CHECK_ARG(stats && gamma && beta && scale && shift && groups > 0 && c > 0, "bad arguments");
+  bn_finalize_kernel<<<cdiv(groups * c, 128), 128, 0, as_stream(stream)>>>(stats, gamma, beta, groups, c, count,
+                                                                           scale, shift, istd, mistd);
+  VG_LAUNCH_CHECK();
+  return VG_OK;
+}
+
+extern "C" int vg_bn_bwd_apply(const float* dy, const float* x, const double* sums, const float* scale,
+                               const float* istd, const float* mistd, int n, int group_size,
+                               long long spatial, int c, double count, int relu_mask, float* dx,
+                               float* dgamma, float* dbeta, void* stream) {
+  VG_CHECK_ARG(x && sums && n > 0 && group_size > 0 && n % group_size == 0, "bad arguments");
+  cudaStream_t st = as_stream(stream);
+  if (dx) {
+    VG_CHECK_ARG(dy && scale && istd && mistd, "null coefficient");
+    long long per_img = spatial * c;
+    int bx = (int)((per_img / 4 + 255) / 256);
+    int cap = (8 * vg_sm_count() + n - 1) / n;
+    if (cap < 1) cap = 1;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    dim3 grid(bx, n);
+    if (c == 1) bn_bwd_apply_kernel<1><<<grid, 256, 0, st>>>(dy, x, sums, scale, istd, mistd, group_size, spatial, count, relu_mask, dx);
+    else if (c == 8) bn_bwd_apply_kernel<8><<<grid, 256, 0, st>>>(dy, x, sums, scale, istd, mistd, group_size, spatial, count, relu_mask, dx);
+    else if (c == 16) bn_bwd_apply_kernel<16><<<grid, 256, 0, st>>>(dy, x, sums, scale, istd, mistd, group_size, spatial, count, relu_mask, dx);
+    else { set_error("vg_bn_bwd_apply: channels must be 1, 8 or 16 (got %d)", c); return VG_EINVAL; }
+    VG_LAUNCH_CHECK();
+  }
+  if (dgamma || dbeta) {
+    bn_param_grad_kernel<<<1, 32, 0, st>>>(sums, n / group_size, c, dgamma, dbeta);
+    VG_LAUNCH_CHECK();
+  }
+  return VG_OK;
+}
+
+extern "C" int vg_nchw_to_nhwc(const float* src, float* dst, int n, int c, long long spatial, void* stream) {
+  VG_CHECK_ARG(src && dst && n > 0 && c > 0 && spatial > 0, "bad arguments");
+  return transpose(src, dst, n, c, (int)spatial, as_stream(stream));
+}
+extern "C" int vg_nhwc_to_nchw(const float* src, float* dst, int n, int c, long long spatial, void* stream) {
+  VG_CHECK_ARG(src && dst && n > 0 && c > 0 && spatial > 0, "bad arguments");
+  return transpose(src, dst, n, (int)spatial, c, as_stream(stream));
+}

@@ -1,0 +1,545 @@
+// fp32 direct 3-D convolution family for sm_100a: one "tap-list gather" formulation serves
+// Conv3d / ConvTranspose3d forward, both data gradients and both weight gradients.
+//
+//   out[n, q*sout + r, co] = epi( sum_t sum_ci pro(in[n, q*sin + off_t, ci]) * W[t][ci][co] )
+//
+// * Conv3d forward  (vae_reg_GP.py:238-242): sin = stride, taps = all kernel offsets.
+// * ConvTranspose3d forward (vae_reg_GP.py:260-264): gather form of SURVEY Appendix B; a
+//   stride-2 layer is split into its 8 output-parity phases, each a stride-1 gather over the
+//   taps whose parity matches (sout = 2, r = phase).
+// * data gradients are the same two forms with the channel roles of W swapped.
+// * weight gradients correlate the (affine-folded) input with dy over the same geometry.
+// Layout: activations channels-last (N,D,H,W,C) so one voxel's channels are one or more
+// 128-bit loads and a warp's loads are contiguous; weights are read straight from the
+// PyTorch layouts through (tap, ci, co) strides and staged once per CTA in shared memory.
+// BatchNorm (batch statistics, per image group) never runs as its own pass: `pro` applies
+// scale/shift to in-range taps only (zero padding pads the NORMALISED tensor) and `epi`
+// accumulates the next layer's statistics, or the BatchNorm-backward sums.
+#include "common.cuh"
+
+namespace vg {
+
+constexpr int kMaxTaps = 48;
+
+struct Tap {
+  int8_t dd, dh, dw, pad_;
+  int32_t widx;
+};
+
+struct Geom {
+  int N, group_size;
+  int inD, inH, inW;
+  int outD, outH, outW;
+  int qD, qH, qW;
+  int sin, sout;
+  int rD, rH, rW;
+  int ntaps, check;
+  int wst_t, wst_ci, wst_co;
+  long long in_img, out_img;   // floats between images of the tensor read / written
+  Tap taps[kMaxTaps];
+};
+
+struct GatherArgs {
+  const float* in;
+  const float* w;
+  const float* bias;      // (COUT) or null
+  const float* in_scale;  // (groups, CIN) or null
+  const float* in_shift;
+  float* out;             // null: statistics only
+  int act;
+  double* stats;          // (groups, COUT, 2): sum y, sum y^2   (forward)
+  const float* aux;       // saved tensor at the output positions (backward)
+  int aux_mode;           // 0 none, 1 relu mask, 2 batch-norm backward sums
+  const float* aux_istd;  // (groups, COUT)
+  const float* aux_mistd;
+  double* aux_sums;       // (groups, COUT, 2): sum dy, sum dy*xhat
+};
+
+template <int C>
+__device__ __forceinline__ void load_vec(const float* __restrict__ p, float (&v)[C]) {
+  if constexpr (C % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < C / 4; ++i) {
+      float4 t = __ldg(reinterpret_cast<const float4*>(p) + i);
+      v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < C; ++i) v[i] = __ldg(p + i);
+  }
+}
+template <int C>
+__device__ __forceinline__ void store_vec(float* __restrict__ p, const float (&v)[C]) {
+  if constexpr (C % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < C / 4; ++i)
+      reinterpret_cast<float4*>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < C; ++i) p[i] = v[i];
+  }
+}
+
+template <int CIN, int COUT, int VT>
+__global__ void __launch_bounds__(256)
+gather_kernel(const __grid_constant__ Geom g, const GatherArgs a) {
+  extern __shared__ float sw[];  // [ntaps][CIN][COUT]
+  __shared__ double sred[2 * COUT];
+  const int tid = threadIdx.x;
+  {
+    const int per_tap = CIN * COUT;
+    const int nw = g.ntaps * per_tap;
+    for (int i = tid; i < nw; i += blockDim.x) {
+      int t = i / per_tap, rem = i - t * per_tap;
+      int ci = rem / COUT, co = rem - ci * COUT;
+      sw[i] = __ldg(a.w + (size_t)g.taps[t].widx * g.wst_t + (size_t)ci * g.wst_ci + (size_t)co * g.wst_co);
+    }
+    if (tid < 2 * COUT) sred[tid] = 0.0;
+  }
+  __syncthreads();
+
+  const int n = blockIdx.y;
+  const int grp = n / g.group_size;
+  const int nWc = (g.qW + VT - 1) / VT;
+  const int items = g.qD * g.qH * nWc;
+  const int item = blockIdx.x * blockDim.x + tid;
+  const bool active = item < items;
+  const int qw0 = (item % nWc) * VT;
+  const int qh = (item / nWc) % g.qH;
+  const int qd = item / (nWc * g.qH);
+
+  float acc[VT][COUT];
+#pragma unroll
+  for (int v = 0; v < VT; ++v)
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) acc[v][c] = 0.f;
+
+  if (active) {
+    float sc[CIN], sh[CIN];
+    const bool affine = a.in_scale != nullptr;
+    if (affine) {
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) {
+        sc[c] = __ldg(a.in_scale + grp * CIN + c);
+        sh[c] = __ldg(a.in_shift + grp * CIN + c);
+      }
+    }
+    const float* in_n = a.in + (size_t)n * g.in_img;
+    for (int t = 0; t < g.ntaps; ++t) {
+      const Tap tp = g.taps[t];
+      const int id = qd * g.sin + tp.dd;
+      const int ih = qh * g.sin + tp.dh;
+      if (g.check && (id < 0 || id >= g.inD || ih < 0 || ih >= g.inH)) continue;
+      const size_t row = ((size_t)id * g.inH + ih) * g.inW;
+      float xv[VT][CIN];
+#pragma unroll
+      for (int v = 0; v < VT; ++v) {
+        const int iw = (qw0 + v) * g.sin + tp.dw;
+        const bool ok = (qw0 + v < g.qW) && (!g.check || (iw >= 0 && iw < g.inW));
+        if (ok) {
+          load_vec<CIN>(in_n + (row + iw) * CIN, xv[v]);
+          if (affine) {
+#pragma unroll
+            for (int c = 0; c < CIN; ++c) xv[v][c] = fmaf(xv[v][c], sc[c], sh[c]);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < CIN; ++c) xv[v][c] = 0.f;
+        }
+      }
+      const float* wt = sw + t * (CIN * COUT);
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci) {
+        float wr[COUT];
+        if constexpr (COUT % 4 == 0) {
+#pragma unroll
+          for (int i = 0; i < COUT / 4; ++i) {
+            float4 q4 = reinterpret_cast<const float4*>(wt + ci * COUT)[i];
+            wr[4 * i] = q4.x; wr[4 * i + 1] = q4.y; wr[4 * i + 2] = q4.z; wr[4 * i + 3] = q4.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < COUT; ++i) wr[i] = wt[ci * COUT + i];
+        }
+#pragma unroll
+        for (int v = 0; v < VT; ++v)
+#pragma unroll
+          for (int co = 0; co < COUT; ++co) acc[v][co] = fmaf(xv[v][ci], wr[co], acc[v][co]);
+      }
+    }
+  }
+
+  // ---- epilogue
+  const bool want_stats = a.stats != nullptr;
+  const bool want_bn = a.aux_mode == 2;
+  float s1[COUT], s2[COUT];
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) s1[c] = s2[c] = 0.f;
+  if (active) {
+    float bias[COUT];
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) bias[c] = a.bias ? __ldg(a.bias + c) : 0.f;
+    float istd[COUT], mistd[COUT];
+    if (want_bn) {
+#pragma unroll
+      for (int c = 0; c < COUT; ++c) {
+        istd[c] = __ldg(a.aux_istd + grp * COUT + c);
+        mistd[c] = __ldg(a.aux_mistd + grp * COUT + c);
+      }
+    }
+    const int od = qd * g.sout + g.rD, oh = qh * g.sout + g.rH;
+#pragma unroll
+    for (int v = 0; v < VT; ++v) {
+      if (qw0 + v >= g.qW) continue;
+      const int ow = (qw0 + v) * g.sout + g.rW;
+      const size_t o = (size_t)n * g.out_img + (((size_t)od * g.outH + oh) * g.outW + ow) * COUT;
+      float y[COUT];
+#pragma unroll
+      for (int c = 0; c < COUT; ++c) {
+        float t = acc[v][c] + bias[c];
+        if (a.act == VG_ACT_RELU) t = fmaxf(t, 0.f);
+        else if (a.act == VG_ACT_SIGMOID) t = 1.f / (1.f + __expf(-t));
+        y[c] = t;
+      }
+      if (a.aux_mode != 0) {
+        float ax[COUT];
+        load_vec<COUT>(a.aux + o, ax);
+        if (a.aux_mode == 1) {
+#pragma unroll
+          for (int c = 0; c < COUT; ++c) y[c] = ax[c] > 0.f ? y[c] : 0.f;
+        } else {
+#pragma unroll
+          for (int c = 0; c < COUT; ++c) {
+            const float xh = fmaf(ax[c], istd[c], -mistd[c]);
+            s1[c] += y[c];
+            s2[c] = fmaf(y[c], xh, s2[c]);
+          }
+        }
+      }
+      if (want_stats) {
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) {
+          s1[c] += y[c];
+          s2[c] = fmaf(y[c], y[c], s2[c]);
+        }
+      }
+      if (a.out) store_vec<COUT>(a.out + o, y);
+    }
+  }
+  if (want_stats || want_bn) {
+    const int lane = tid & 31;
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) {
+      const float r1 = warp_sum(s1[c]);
+      const float r2 = warp_sum(s2[c]);
+      if (lane == 0) {
+        atomicAdd(&sred[2 * c], (double)r1);
+        atomicAdd(&sred[2 * c + 1], (double)r2);
+      }
+    }
+    __syncthreads();
+    if (tid < 2 * COUT) {
+      double* dst = want_stats ? a.stats : a.aux_sums;
+      atomicAdd(dst + (size_t)grp * COUT * 2 + tid, sred[tid]);
+    }
+  }
+}
+
+// Weight gradient: one warp per (tap, co-slice); lanes stride over voxels of a chunk.
+template <int CIN, int COT>
+__global__ void __launch_bounds__(256)
+wgrad_kernel(const __grid_constant__ Geom g, const float* __restrict__ in,
+             const float* __restrict__ dout, const float* __restrict__ in_scale,
+             const float* __restrict__ in_shift, float* dw, float* dbias, int cout_full,
+             int co_splits, long long chunk_items) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slot = blockIdx.y * (blockDim.x >> 5) + warp;
+  const int tap = slot / co_splits;
+  const int co0 = (slot - tap * co_splits) * COT;
+  const bool do_bias = (tap == 0) && dbias != nullptr;
+  const bool do_w = tap < g.ntaps;
+  if (!do_bias && !do_w) return;
+  Tap tp = g.taps[do_w ? tap : 0];
+
+  float acc[CIN][COT];
+  float bs[COT];
+#pragma unroll
+  for (int i = 0; i < CIN; ++i)
+#pragma unroll
+    for (int j = 0; j < COT; ++j) acc[i][j] = 0.f;
+#pragma unroll
+  for (int j = 0; j < COT; ++j) bs[j] = 0.f;
+
+  const long long per_img = (long long)g.qD * g.qH * g.qW;
+  const long long total = per_img * g.N;
+  const long long beg = (long long)blockIdx.x * chunk_items;
+  const long long end = min(total, beg + chunk_items);
+  const bool affine = in_scale != nullptr;
+  for (long long it = beg + lane; it < end; it += 32) {
+    const int n = (int)(it / per_img);
+    int rem = (int)(it - (long long)n * per_img);
+    const int qw = rem % g.qW; rem /= g.qW;
+    const int qh = rem % g.qH;
+    const int qd = rem / g.qH;
+    const int od = qd * g.sout + g.rD, oh = qh * g.sout + g.rH, ow = qw * g.sout + g.rW;
+    const size_t o = (size_t)n * g.out_img + (((size_t)od * g.outH + oh) * g.outW + ow) * cout_full + co0;
+    float dy[COT];
+    load_vec<COT>(dout + o, dy);
+    if (do_bias) {
+#pragma unroll
+      for (int j = 0; j < COT; ++j) bs[j] += dy[j];
+    }
+    if (!do_w) continue;
+    const int id = qd * g.sin + tp.dd, ih = qh * g.sin + tp.dh, iw = qw * g.sin + tp.dw;
+    if (g.check && (id < 0 || id >= g.inD || ih < 0 || ih >= g.inH || iw < 0 || iw >= g.inW)) continue;
+    float xv[CIN];
+    load_vec<CIN>(in + (size_t)n * g.in_img + (((size_t)id * g.inH + ih) * g.inW + iw) * CIN, xv);
+    if (affine) {
+      const int grp = n / g.group_size;
+#pragma unroll
+      for (int c = 0; c < CIN; ++c)
+        xv[c] = fmaf(xv[c], __ldg(in_scale + grp * CIN + c), __ldg(in_shift + grp * CIN + c));
+    }
+#pragma unroll
+    for (int i = 0; i < CIN; ++i)
+#pragma unroll
+      for (int j = 0; j < COT; ++j) acc[i][j] = fmaf(xv[i], dy[j], acc[i][j]);
+  }
+  if (do_w) {
+#pragma unroll
+    for (int i = 0; i < CIN; ++i)
+#pragma unroll
+      for (int j = 0; j < COT; ++j) {
+        const float r = warp_sum(acc[i][j]);
+        if (lane == ((i * COT + j) & 31))
+          atomicAdd(dw + (size_t)tp.widx * g.wst_t + (size_t)i * g.wst_ci + (size_t)(co0 + j) * g.wst_co, r);
+      }
+  }
+  if (do_bias) {
+#pragma unroll
+    for (int j = 0; j < COT; ++j) {
+      const float r = warp_sum(bs[j]);
+      if (lane == j) atomicAdd(dbias + co0 + j, r);
+    }
+  }
+}
+
+// --------------------------------------------------------------------------- geometry
+static int check_desc(const VgConvDesc* d) {
+  VG_CHECK_ARG(d != nullptr, "null descriptor");
+  VG_CHECK_ARG(d->stride == 1 || d->stride == 2, "stride must be 1 or 2");
+  VG_CHECK_ARG(d->n > 0 && d->group_size > 0 && d->n % d->group_size == 0, "n % group_size != 0");
+  for (int i = 0; i < 3; ++i) {
+    VG_CHECK_ARG(d->k[i] >= 1 && d->k[i] <= 5, "kernel extent must be 1..5");
+    int expect = d->transposed
+                     ? (d->in[i] - 1) * d->stride - 2 * d->pad[i] + d->k[i] + d->opad[i]
+                     : (d->in[i] - d->k[i]) / d->stride + 1;
+    VG_CHECK_ARG(expect == d->out[i], "output size does not match the PyTorch formula");
+    VG_CHECK_ARG(d->transposed || d->pad[i] == 0, "Conv3d padding is not supported (reference uses none)");
+  }
+  return VG_OK;
+}
+
+// kind 0 reads x and writes y; kind 1 reads dy and writes dx
+static void set_img_strides(const VgConvDesc* d, int kind, Geom& g) {
+  const long long xs = d->x_img_stride ? d->x_img_stride : (long long)d->in[0] * d->in[1] * d->in[2] * d->cin;
+  const long long ys = d->y_img_stride ? d->y_img_stride : (long long)d->out[0] * d->out[1] * d->out[2] * d->cout;
+  g.in_img = kind == 0 ? xs : ys;
+  g.out_img = kind == 0 ? ys : xs;
+}
+
+static inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+// kind 0: module forward; kind 1: data gradient.  Returns number of phase geometries.
+static int build_geoms(const VgConvDesc* d, int kind, Geom* out /* up to 8 */) {
+  const int K = d->k[0] * d->k[1] * d->k[2];
+  const int s = d->stride;
+  int ng = 0;
+  const bool gather_plain = (kind == 0 && !d->transposed) || (kind == 1 && d->transposed);
+  Geom base{};
+  base.N = d->n;
+  base.group_size = d->group_size;
+  // weight strides for (tap, ci_eff, co_eff)
+  if (!d->transposed) {  // w[co][ci][K]
+    if (kind == 0) { base.wst_ci = K; base.wst_co = d->cin * K; }
+    else           { base.wst_ci = d->cin * K; base.wst_co = K; }   // ci_eff = co, co_eff = ci
+  } else {               // w[ci][co][K]
+    if (kind == 0) { base.wst_ci = d->cout * K; base.wst_co = K; }
+    else           { base.wst_ci = K; base.wst_co = d->cout * K; }  // ci_eff = co, co_eff = ci
+  }
+  base.wst_t = 1;
+  if (gather_plain) {
+    // q runs over the SMALL grid; input index = q*s + (k - p)
+    Geom g = base;
+    const int* small = d->transposed ? d->in : d->out;   // output of this gather
+    const int* large = d->transposed ? d->out : d->in;   // tensor being read
+    g.inD = large[0]; g.inH = large[1]; g.inW = large[2];
+    g.outD = small[0]; g.outH = small[1]; g.outW = small[2];
+    g.qD = small[0]; g.qH = small[1]; g.qW = small[2];
+    g.sin = s; g.sout = 1; g.rD = g.rH = g.rW = 0;
+    g.check = d->transposed ? 1 : 0;
+    set_img_strides(d, kind, g);
+    int t = 0;
+    for (int a = 0; a < d->k[0]; ++a)
+      for (int b = 0; b < d->k[1]; ++b)
+        for (int c = 0; c < d->k[2]; ++c) {
+          g.taps[t].dd = (int8_t)(a - d->pad[0]);
+          g.taps[t].dh = (int8_t)(b - d->pad[1]);
+          g.taps[t].dw = (int8_t)(c - d->pad[2]);
+          g.taps[t].widx = (a * d->k[1] + b) * d->k[2] + c;
+          ++t;
+        }
+    g.ntaps = t;
+    out[ng++] = g;
+  } else {
+    // q runs over one parity phase of the LARGE grid; input index = q + (r + p - k)/s
+    const int* small = d->transposed ? d->in : d->out;   // tensor being read
+    const int* large = d->transposed ? d->out : d->in;   // output of this gather
+    for (int r0 = 0; r0 < s; ++r0)
+      for (int r1 = 0; r1 < s; ++r1)
+        for (int r2 = 0; r2 < s; ++r2) {
+          const int r[3] = {r0, r1, r2};
+          Geom g = base;
+          g.inD = small[0]; g.inH = small[1]; g.inW = small[2];
+          g.outD = large[0]; g.outH = large[1]; g.outW = large[2];
+          g.sin = 1; g.sout = s; g.rD = r0; g.rH = r1; g.rW = r2;
+          g.check = 1;
+          set_img_strides(d, kind, g);
+          int q[3];
+          bool empty = false;
+          for (int i = 0; i < 3; ++i) {
+            q[i] = large[i] > r[i] ? (large[i] - r[i] + s - 1) / s : 0;
+            if (q[i] == 0) empty = true;
+          }
+          if (empty) continue;
+          g.qD = q[0]; g.qH = q[1]; g.qW = q[2];
+          int t = 0;
+          for (int a = 0; a < d->k[0]; ++a) {
+            if (((r0 + d->pad[0] - a) % s + s) % s != 0) continue;
+            for (int b = 0; b < d->k[1]; ++b) {
+              if (((r1 + d->pad[1] - b) % s + s) % s != 0) continue;
+              for (int c = 0; c < d->k[2]; ++c) {
+                if (((r2 + d->pad[2] - c) % s + s) % s != 0) continue;
+                g.taps[t].dd = (int8_t)floordiv(r0 + d->pad[0] - a, s);
+                g.taps[t].dh = (int8_t)floordiv(r1 + d->pad[1] - b, s);
+                g.taps[t].dw = (int8_t)floordiv(r2 + d->pad[2] - c, s);
+                g.taps[t].widx = (a * d->k[1] + b) * d->k[2] + c;
+                ++t;
+              }
+            }
+          }
+          g.ntaps = t;
+          out[ng++] = g;
+        }
+  }
+  return ng;
+}
+
+template <int CIN, int COUT, int VT>
+static int launch_gather_t(const Geom& g, const GatherArgs& a, cudaStream_t st) {
+  const int nWc = (g.qW + VT - 1) / VT;
+  const long long items = (long long)g.qD * g.qH * nWc;
+  int threads = items >= 256 ? 256 : (int)((items + 31) / 32 * 32);
+  if (threads < 32) threads = 32;
+  dim3 grid(cdiv(items, threads), g.N);
+  const size_t smem = (size_t)g.ntaps * CIN * COUT * sizeof(float);
+  gather_kernel<CIN, COUT, VT><<<grid, threads, smem, st>>>(g, a);
+  VG_LAUNCH_CHECK();
+  return VG_OK;
+}
+
+static int launch_gather(int cin, int cout, const Geom& g, const GatherArgs& a, cudaStream_t st) {
+  if (cin == 1 && cout == 8) return launch_gather_t<1, 8, 4>(g, a, st);
+  if (cin == 8 && cout == 1) return launch_gather_t<8, 1, 4>(g, a, st);
+  if (cin == 8 && cout == 8) return launch_gather_t<8, 8, 4>(g, a, st);
+  if (cin == 8 && cout == 16) return launch_gather_t<8, 16, 4>(g, a, st);
+  if (cin == 16 && cout == 8) return launch_gather_t<16, 8, 4>(g, a, st);
+  if (cin == 16 && cout == 16) return launch_gather_t<16, 16, 2>(g, a, st);
+  if (cin == 1 && cout == 1) return launch_gather_t<1, 1, 4>(g, a, st);
+  if (cin == 1 && cout == 16) return launch_gather_t<1, 16, 4>(g, a, st);
+  if (cin == 16 && cout == 1) return launch_gather_t<16, 1, 4>(g, a, st);
+  set_error("unsupported channel pair (%d,%d): channels must be in {1,8,16}", cin, cout);
+  return VG_EINVAL;
+}
+
+template <int CIN, int COT>
+static int launch_wgrad_t(const Geom& g, int cout_full, const float* in, const float* dy,
+                          const float* sc, const float* sh, float* dw, float* dbias, cudaStream_t st) {
+  const int co_splits = cout_full / COT;
+  const int slots = (g.ntaps > 0 ? g.ntaps : 1) * co_splits;
+  const int wpb = 8;
+  const int gy = cdiv(slots, wpb);
+  const long long total = (long long)g.N * g.qD * g.qH * g.qW;
+  int sms = vg_sm_count();
+  long long want_chunks = (long long)sms * 4 / gy;
+  if (want_chunks < 1) want_chunks = 1;
+  long long chunk = (total + want_chunks - 1) / want_chunks;
+  if (chunk < 256) chunk = 256;
+  chunk = (chunk + 31) / 32 * 32;
+  dim3 grid(cdiv(total, chunk), gy);
+  wgrad_kernel<CIN, COT><<<grid, wpb * 32, 0, st>>>(g, in, dy, sc, sh, dw, dbias, cout_full, co_splits, chunk);
+  VG_LAUNCH_CHECK();
+  return VG_OK;
+}
+
+static int launch_wgrad(int cin, int cout, const Geom& g, const float* in, const float* dy, const float* sc,
+                        const float* sh, float* dw, float* dbias, cudaStream_t st) {
+  if (cin == 1 && cout == 8) return launch_wgrad_t<1, 8>(g, 8, in, dy, sc, sh, dw, dbias, st);
+  if (cin == 8 && cout == 1) return launch_wgrad_t<8, 1>(g, 1, in, dy, sc, sh, dw, dbias, st);
+  if (cin == 8 && cout == 8) return launch_wgrad_t<8, 8>(g, 8, in, dy, sc, sh, dw, dbias, st);
+  if (cin == 8 && cout == 16) return launch_wgrad_t<8, 8>(g, 16, in, dy, sc, sh, dw, dbias, st);
+  if (cin == 16 && cout == 8) return launch_wgrad_t<16, 8>(g, 8, in, dy, sc, sh, dw, dbias, st);
+  if (cin == 16 && cout == 16) return launch_wgrad_t<16, 8>(g, 16, in, dy, sc, sh, dw, dbias, st);
+  if (cin == 1 && cout == 1) return launch_wgrad_t<1, 1>(g, 1, in, dy, sc, sh, dw, dbias, st);
+  if (cin == 1 && cout == 16) return launch_wgrad_t<1, 8>(g, 16, in, dy, sc, sh, dw, dbias, st);
+  if (cin == 16 && cout == 1) return launch_wgrad_t<16, 1>(g, 1, in, dy, sc, sh, dw, dbias, st);
+  set_error("unsupported channel pair (%d,%d): channels must be in {1,8,16}", cin, cout);
+  return VG_EINVAL;
+}
+
+}  // namespace vg
+
+using namespace vg;
+
+extern "C" int vg_conv_fwd(const VgConvDesc* d, const float* x, const float* w, const float* bias,
+                           const float* in_scale, const float* in_shift, float* y, int act,
+                           double* out_stats, void* stream) {
+  VG_TRY(check_desc(d));
+  VG_CHECK_ARG(x && w && y, "null tensor");
+  Geom gs[8];
+  const int ng = build_geoms(d, 0, gs);
+  GatherArgs a{};
+  a.in = x; a.w = w; a.bias = bias; a.in_scale = in_scale; a.in_shift = in_shift;
+  a.out = y; a.act = act; a.stats = out_stats;
+  for (int i = 0; i < ng; ++i) VG_TRY(launch_gather(d->cin, d->cout, gs[i], a, as_stream(stream)));
+  return VG_OK;
+}
+
+extern "C" int vg_conv_dgrad(const VgConvDesc* d, const float* dy, const float* w, float* dx,
+                             const float* mask_act, const float* bn_x, const float* bn_istd,
+                             const float* bn_mistd, double* bn_sums, void* stream) {
+  VG_TRY(check_desc(d));
+  VG_CHECK_ARG(dy && w, "null tensor");
+  VG_CHECK_ARG(!(mask_act && bn_x), "mask_act and bn_x are exclusive");
+  VG_CHECK_ARG(!bn_x || (bn_istd && bn_mistd && bn_sums), "bn_x needs istd/mistd/sums");
+  Geom gs[8];
+  const int ng = build_geoms(d, 1, gs);
+  GatherArgs a{};
+  a.in = dy; a.w = w; a.out = dx; a.act = VG_ACT_NONE;
+  if (mask_act) { a.aux = mask_act; a.aux_mode = 1; }
+  if (bn_x) { a.aux = bn_x; a.aux_mode = 2; a.aux_istd = bn_istd; a.aux_mistd = bn_mistd; a.aux_sums = bn_sums; }
+  // the gather reads dy (cout channels) and produces cin channels
+  for (int i = 0; i < ng; ++i) VG_TRY(launch_gather(d->cout, d->cin, gs[i], a, as_stream(stream)));
+  return VG_OK;
+}
+
+extern "C" int vg_conv_wgrad(const VgConvDesc* d, const float* x, const float* dy, const float* in_scale,
+                             const float* in_shift, float* dw, float* dbias, void* stream) {
+  VG_TRY(check_desc(d));
+  VG_CHECK_ARG(x && dy && dw, "null tensor");
+  Geom gs[8];
+  const int ng = build_geoms(d, 0, gs);
+  for (int i = 0; i < ng; ++i)
+    VG_TRY(launch_wgrad(d->cin, d->cout, gs[i], x, dy, in_scale, in_shift, dw, dbias, as_stream(stream)));
+  return VG_OK;
+}
