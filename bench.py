@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""Headline benchmark: VAE-GAM training volumes/s (fwd + bwd + Adam step) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            # native sm_100a path (this repo)
+    python bench.py --impl reference --steps K --warmup W    # the reference's algorithm on the host CPUs
+
+Workload (BASELINE.json configs[1]): multi-subject synthetic checkerboard cohort, 14 subjects x 98
+volumes of 41x49x35 (1372 volumes), batch 32, default num_inducing_pts=6 / gp_kl_scale=10, HRF on.
+One "step" = one minibatch through forward, backward and the Adam update.  Every rank trains on
+its own 14-subject cohort (weak scaling); gradients are all-reduced with NCCL.
+
+Prints ONE JSON line (rank 0).  `value` = volumes/s with the cohort resident in HBM; `e2e` = the same
+through the public API (`VAE.forward` / `loss.backward()` / `optimizer.step()`) with the batch copied
+from pinned host memory and the loss read back every step.  `roofline` describes the dominant
+operation, timed live with CUDA events on the launching stream (vg_profile_*); `kernels` lists
+every operation's share.  `cpu_baseline` is the oracle port of the reference step
+(oracle/ref_port.py, PyTorch fp32 CPU kernels, all host threads) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "vae-gam_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+V = 41 * 49 * 35
+BATCH = 32
+N_SUBJECTS = 14
+WORKLOAD = "configs[1]: multi-subject synthetic checkerboard, 14 subj x 98 vol (41x49x35), B=32, m=6, gp_kl_scale=10"
+
+# algorithmic work per operation and per image: (flops, bytes) for one image of the
+# layer's batch; conv bytes = fp32 input + output tensors, flops = 2*M*N*K
+_CONV = {  # name: (cin, cout, taps, out voxels, in voxels)
+    "conv1": (1, 8, 27, 60489, 70315), "conv2": (8, 8, 27, 6992, 60489), "conv3": (8, 16, 27, 4998, 6992),
+    "conv4": (16, 16, 27, 480, 4998), "conv5": (16, 16, 27, 192, 480),
+    "convt1": (16, 16, 27, 560, 240), "convt2": (16, 16, 27, 4704, 560), "convt3": (16, 8, 27, 6624, 4704),
+    "convt4": (8, 8, 45, 60489, 6624), "convt5": (8, 1, 27, 70315, 60489),
+}
+
+
+def conv_work(name):
+    """(flops, bytes) per image for one pass (fwd, dgrad or wgrad) of a conv layer."""
+    cin, cout, taps, vo, vi = _CONV[name]
+    if name.startswith("convt"):          # gather form: MACs = input voxels * taps * cin * cout
+        flops = 2.0 * vi * taps * cin * cout
+    else:
+        flops = 2.0 * vo * taps * cin * cout
+    return flops, 4.0 * (vi * cin + vo * cout)
+
+
+def op_work(op, B):
+    """Algorithmic (flops, bytes) of one recorded operation at minibatch B; None if not modelled."""
+    layer, _, kind = op.partition(".")
+    if layer in _CONV:
+        n = B if layer.startswith("conv") and not layer.startswith("convt") else 9 * B
+        f, b = conv_work(layer)
+        return f * n, b * n
+    if op == "recon_loss.fwd":
+        return 30.0 * B * V, 4.0 * (10 * B * V + 9 * V)
+    if op == "recon_loss.bwd":
+        return 60.0 * B * V, 4.0 * (19 * B * V + 10 * V)
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_cohort_tensors(rank, device):
+    from vaegam import synthetic as syn
+    coh = syn.make_cohort(N_SUBJECTS, "checker", seed=rank)
+    return coh, coh.volumes().to(device), torch.from_numpy(coh.covariates()).to(device), \
+        torch.from_numpy(coh.subject_index()).to(device)
+
+
+def build_model(workdir, seed=1):
+    import vae_reg_GP
+    from vaegam import synthetic as syn
+    tr, te, glm, _ = syn.write_experiment(workdir, n_subjects=2, config="checker", glm="uniform")
+    torch.manual_seed(seed)
+    model = vae_reg_GP.VAE(save_dir=workdir, glm_maps=glm, csv_files=[tr, te])
+    model.writer = vae_reg_GP._NullWriter()
+    return model
+
+
+def cpu_baseline(steps=3, warmup=1, threads=None):
+    """The oracle port of the reference training step on the host CPUs (volumes/s)."""
+    import tempfile
+    from oracle import ref_port as rp
+    from vaegam import synthetic as syn
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    work = tempfile.mkdtemp(prefix="cpu_base_")
+    model = build_model_cpu(work)
+    P = rp.cast_params(rp.params_from_module(model), torch.float32, requires_grad=True)
+    coh = syn.make_cohort(1, "checker", seed=0)
+    x = coh.volumes(rows=range(BATCH)).float()
+    cov = torch.from_numpy(coh.covariates()[:BATCH])
+    st = {}
+    times = []
+    for i in range(warmup + steps):
+        noise = rp.draw_noise(BATCH, seed=100 + i)
+        t0 = time.perf_counter()
+        rp.training_step_cpu(P, st, x, cov, noise)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return BATCH / float(np.mean(times)), threads, float(np.mean(times))
+
+
+def build_model_cpu(workdir):
+    import vae_reg_GP
+    from vaegam import synthetic as syn
+    tr, te, glm, _ = syn.write_experiment(workdir, n_subjects=2, config="checker", glm="uniform")
+    torch.manual_seed(1)
+    m = vae_reg_GP.VAE(save_dir=workdir, glm_maps=glm, csv_files=[tr, te], device_name="cpu")
+    return m
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's own algorithm on the host cores (oracle port; the Python
+    reference itself cannot travel to the GPU box).  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    t_start = time.time()
+    val, threads, sec = cpu_baseline(steps=max(1, args.steps), warmup=max(0, args.warmup))
+    line = {
+        "impl": "reference", "metric": "training volumes/sec (fwd+bwd+step)", "value": val, "unit": "volumes/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch": BATCH},
+        "cpu_baseline": {"value": val, "unit": "volumes/s", "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} steps of B={BATCH} (oracle/ref_port.py: torch fp32 CPU conv/BN/linear "
+                                   f"+ closed forms, autograd backward, Adam)"},
+        "e2e": {"value": val, "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.time() - t_start,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import tempfile
+    import torch.distributed as dist
+    from vaegam import dp, native
+    rank, world, local = dp.init_from_env()
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    B = args.batch
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    tf_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = "measured" if peaks else "fallback"
+
+    work = tempfile.mkdtemp(prefix=f"bench_r{rank}_")
+    model = build_model(work)
+    coh, vols, covs, sidx = make_cohort_tensors(rank, device)
+    n_items = vols.shape[0]
+    reducer = dp.GradientAllReduce(model._flat, model.optimizer)
+    reducer.broadcast_parameters()
+    perm = torch.randperm(n_items, generator=torch.Generator().manual_seed(rank)).to(device)
+    n_batches = n_items // B
+
+    def batch_idx(i):
+        j = i % n_batches
+        return perm[j * B:(j + 1) * B]
+
+    def resident_step(i):
+        idx = batch_idx(i)
+        return dp.train_step(model, reducer, sidx[idx], covs[idx], vols[idx])
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput
+    for i in range(args.warmup):
+        resident_step(i)
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = native.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        resident_step(args.warmup + i)
+    e1.record()
+    sync_all()
+    launches = native.launch_count() - n0
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    model.check_status()
+
+    # ---------------- end to end through the public API, host buffers
+    hx = torch.empty(B, 41, 49, 35).pin_memory()
+    hc = torch.empty(B, 8).pin_memory()
+    hi = torch.empty(B, dtype=torch.int64).pin_memory()
+    host_vol = vols.cpu()
+    host_cov, host_idx = covs.cpu(), sidx.cpu()
+    perm_h = perm.cpu()
+
+    def e2e_step(i):
+        j = i % n_batches
+        idx = perm_h[j * B:(j + 1) * B]
+        hx.copy_(host_vol[idx]); hc.copy_(host_cov[idx]); hi.copy_(host_idx[idx])     # loader output (host)
+        x = hx.to(device, non_blocking=True)
+        c = hc.to(device, non_blocking=True)
+        ii = hi.to(device, non_blocking=True)
+        loss = model.forward(ii, c, x, 'train', train_mode=False)
+        val = loss.item()                                                          # D2H, as train_epoch does
+        model.optimizer.zero_grad()
+        loss.backward()
+        reducer()
+        model.optimizer.step()
+        return val
+
+    for i in range(2):
+        e2e_step(i)
+    sync_all()
+    k2 = max(3, min(args.steps, 20))
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(k2):
+        e2e_step(2 + i)
+    f1.record()
+    sync_all()
+    e2e_ms = f0.elapsed_time(f1)   # device clock; the loop is host-synchronous (loss.item())
+
+    # ---------------- max over ranks
+    t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(t[0]), float(t[1])
+
+    # ---------------- live per-operation timing (separate pass, same steps)
+    kernels, roof = {}, None
+    if not args.no_profile and rank == 0:
+        native.profile(True)
+        ksteps = 3
+        for i in range(ksteps):          # local steps only: the other ranks are not in this pass
+            idx = batch_idx(i)
+            loss = model.forward(sidx[idx], covs[idx], vols[idx], 'train', train_mode=False)
+            model.optimizer.zero_grad()
+            loss.backward()
+            model.optimizer.step()
+        torch.cuda.synchronize()
+        rec = native.profile_collect()
+        native.profile(False)
+        total = sum(sum(v) for v in rec.values())
+        rows = []
+        for op, v in rec.items():
+            per_step = sum(v) / ksteps
+            w = op_work(op, B)
+            row = {"op": op, "ms_per_step": round(per_step, 4), "share": round(sum(v) / total, 4)}
+            if w:
+                row["gflops"] = round(w[0] / (per_step * 1e-3) / 1e9, 1)
+                row["gbs"] = round(w[1] / (per_step * 1e-3) / 1e9, 1)
+            rows.append(row)
+        rows.sort(key=lambda r: -r["ms_per_step"])
+        kernels = {"ops": rows[:16], "profiled_ms_per_step": round(total / ksteps, 3)}
+        top = next((r for r in rows if "gbs" in r), None)
+        if top:
+            w = op_work(top["op"], B)
+            roof = {"kernel": top["op"], "bound": "hbm", "achieved": top["gbs"], "peak": hbm_peak, "unit": "GB/s",
+                    "frac": round(top["gbs"] / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes": w[1], "ms": top["ms_per_step"], "share_of_step": top["share"],
+                    "tensor_frac": round(top["gflops"] / 1e3 / tf_peak, 5)}
+        rl = [r for r in rows if r["op"].startswith("recon_loss")]
+        kernels["fused_loss"] = [{"op": r["op"], "gbs": r.get("gbs"), "frac_hbm": round(r.get("gbs", 0) / hbm_peak, 4)} for r in rl]
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+        return
+    total_vols = args.steps * B * world
+    value = total_vols / (ms * 1e-3)
+    line = {
+        "metric": "training volumes/sec (fwd+bwd+step)", "value": value, "unit": "volumes/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world,
+                   "parallelism": f"dp{world} (one minibatch per rank, NCCL grad all-reduce)",
+                   "l2": "inputs cycle through a 386 MB HBM-resident cohort and the step's 1.8 GB activation "
+                         "working set, both larger than the 126 MB L2",
+                   "gain_stage": "fp64", "conv": "fp32 CUDA-core direct convolution"},
+        "clocks": clocks, "gpu_launches": int(launches),
+        "e2e": {"value": k2 * B * world / (e2e_ms * 1e-3), "unit": "volumes/s",
+                "h2d_bytes_per_step": int(B * V * 4 + B * 8 * 4 + B * 8), "d2h_bytes_per_step": 4,
+                "steps": k2, "api": "VAE.forward + loss.item() + loss.backward() + optimizer.step()"},
+        "roofline": roof, "kernels": kernels,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        val, threads, sec = cpu_baseline(steps=3, warmup=1)
+        line["cpu_baseline"] = {"value": val, "unit": "volumes/s", "cores": threads, "kind": "port",
+                                "sample": f"3 steps of B={BATCH} after 1 warm-up ({sec:.2f} s/step)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+
+
+if __name__ == "__main__":
+    main()

@@ -46,6 +46,12 @@ int vg_version(void);                 /* 100 * major + minor */
 const char* vg_last_error(void);      /* thread-local, never NULL */
 int vg_sm_count(void);                /* SMs of the current device (148 on B200) */
 long long vg_launch_count(void);      /* kernels launched by this library so far (process-wide) */
+/* Per-operation timing of the whole-step entry points with CUDA events on the launching stream
+ * (bench.py's live roofline).  enable(1) clears and starts recording, enable(0) stops;
+ * collect() waits for the recorded events and writes "name<TAB>ms\n" lines into buf (host memory),
+ * returning the number of records.  Not for use inside CUDA-graph capture. */
+int vg_profile_enable(int on);
+long long vg_profile_collect(char* buf, size_t cap);
 
 /* ------------------------------------------------------------------------------------
  * 3-D convolution family.  One descriptor covers Conv3d and ConvTranspose3d.

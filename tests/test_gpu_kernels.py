@@ -1,0 +1,463 @@
+"""Per-kernel parity through the C ABI (ctypes) on a real GPU.
+
+Dense layers are compared with PyTorch's own fp32 operators (TF32 disabled) on the same
+device — those ARE the reference's implementation of these layers.  The closed-
+form stages (latent, gains, fused loss) are compared with the CPU oracle in fp64.
+Tolerances: fp32 kernels 1e-5 relative (north star "fp32 check mode"); fp64 gain stage 1e-6.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+LAYERS = {
+    # name: (transposed, cin, cout, k, stride, in, pad, opad)  — vae_reg_GP.py:189-193, 211-215
+    "conv1": (0, 1, 8, (3, 3, 3), 1, (41, 49, 35), (0, 0, 0), (0, 0, 0)),
+    "conv2": (0, 8, 8, (3, 3, 3), 2, (39, 47, 33), (0, 0, 0), (0, 0, 0)),
+    "conv3": (0, 8, 16, (3, 3, 3), 1, (19, 23, 16), (0, 0, 0), (0, 0, 0)),
+    "conv4": (0, 16, 16, (3, 3, 3), 2, (17, 21, 14), (0, 0, 0), (0, 0, 0)),
+    "conv5": (0, 16, 16, (3, 3, 3), 1, (8, 10, 6), (0, 0, 0), (0, 0, 0)),
+    "convt1": (1, 16, 16, (3, 3, 3), 1, (6, 8, 5), (0, 0, 0), (0, 0, 0)),
+    "convt2": (1, 16, 16, (3, 3, 3), 2, (8, 10, 7), (1, 0, 1), (1, 0, 1)),
+    "convt3": (1, 16, 8, (3, 3, 3), 1, (16, 21, 14), (0, 0, 0), (0, 0, 0)),
+    "convt4": (1, 8, 8, (5, 3, 3), 2, (18, 23, 16), (0, 0, 0), (0, 0, 0)),
+    "convt5": (1, 8, 1, (3, 3, 3), 1, (39, 47, 33), (0, 0, 0), (0, 0, 0)),
+    # small irregular shapes: ragged extents, every parity phase exercised
+    "tiny_conv_s2": (0, 8, 16, (3, 3, 3), 2, (6, 7, 9), (0, 0, 0), (0, 0, 0)),
+    "tiny_convt_s2": (1, 16, 8, (5, 3, 3), 2, (3, 4, 2), (1, 0, 1), (1, 0, 1)),
+}
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from vaegam import native
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return native.load()
+
+
+def nat():
+    from vaegam import native
+    return native
+
+
+def to_cl(t):      # (N,C,D,H,W) -> (N,D,H,W,C) contiguous
+    return t.permute(0, 2, 3, 4, 1).contiguous()
+
+
+def from_cl(t):    # (N,D,H,W,C) -> (N,C,D,H,W)
+    return t.permute(0, 4, 1, 2, 3).contiguous()
+
+
+def torch_layer(spec, x, w, b):
+    tr, cin, cout, k, s, in_, pad, opad = spec
+    if tr:
+        return F.conv_transpose3d(x, w, b, stride=s, padding=pad, output_padding=opad)
+    return F.conv3d(x, w, b, stride=s)
+
+
+@pytest.mark.parametrize("name", list(LAYERS))
+def test_conv_forward_dgrad_wgrad(lib, name):
+    native = nat()
+    spec = LAYERS[name]
+    tr, cin, cout, k, s, in_, pad, opad = spec
+    N, group = 4, 2
+    dev = "cuda"
+    gen = torch.Generator(device=dev).manual_seed(sum(map(ord, name)))
+    x = torch.randn(N, cin, *in_, device=dev, generator=gen)
+    wshape = (cin, cout, *k) if tr else (cout, cin, *k)
+    w = torch.randn(*wshape, device=dev, generator=gen) * 0.2
+    b = torch.randn(cout, device=dev, generator=gen)
+    scale = torch.rand(N // group, cin, device=dev, generator=gen) + 0.5
+    shift = torch.randn(N // group, cin, device=dev, generator=gen)
+    d = native.conv_desc(tr, cin, cout, k, s, in_, N, group, pad, opad)
+    out_shape = tuple(d.out)
+
+    # reference: affine per (group, channel), then the torch operator, ReLU
+    xa = (x * scale.repeat_interleave(group, 0)[:, :, None, None, None]
+          + shift.repeat_interleave(group, 0)[:, :, None, None, None]).requires_grad_(True)
+    wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    pre = torch_layer(spec, xa, wr, br)
+    y_ref = torch.relu(pre)
+
+    x_cl = to_cl(x)
+    y = torch.empty(N, *out_shape, cout, device=dev)
+    stats = torch.zeros(N // group, cout, 2, dtype=torch.float64, device=dev)
+    st = native.stream_ptr()
+    native.check(lib.vg_conv_fwd(C.byref(d), native.ptr(x_cl), native.ptr(w), native.ptr(b), native.ptr(scale),
+                                 native.ptr(shift), native.ptr(y), native.ACT_RELU, native.ptr(stats), st))
+    torch.cuda.synchronize()
+    assert rel_err(from_cl(y).cpu(), y_ref.detach().cpu()) < 1e-5
+    ref_stats = torch.stack([y_ref.detach().double().reshape(N // group, group, cout, -1).sum((1, 3)),
+                             (y_ref.detach().double() ** 2).reshape(N // group, group, cout, -1).sum((1, 3))], -1)
+    assert rel_err(stats.cpu(), ref_stats.cpu()) < 1e-5
+
+    # backward: dy w.r.t. the pre-activation
+    dy = torch.randn_like(pre)
+    pre.backward(dy)
+    dy_cl = to_cl(dy)
+    dx = torch.empty_like(x_cl)
+    native.check(lib.vg_conv_dgrad(C.byref(d), native.ptr(dy_cl), native.ptr(w), native.ptr(dx), None, None, None,
+                                   None, None, st))
+    dw = torch.zeros_like(w)
+    db = torch.zeros_like(b)
+    native.check(lib.vg_conv_wgrad(C.byref(d), native.ptr(x_cl), native.ptr(dy_cl), native.ptr(scale),
+                                   native.ptr(shift), native.ptr(dw), native.ptr(db), st))
+    torch.cuda.synchronize()
+    assert rel_err(from_cl(dx).cpu(), xa.grad.cpu()) < 1e-5          # gradient w.r.t. the affine-folded input
+    assert rel_err(dw.cpu(), wr.grad.cpu()) < 2e-5
+    assert rel_err(db.cpu(), br.grad.cpu()) < 2e-5
+
+    # dgrad epilogues: ReLU mask and BatchNorm-backward sums
+    act = torch.randn(N, cin, *in_, device=dev, generator=gen)
+    act_cl = to_cl(act)
+    dxm = torch.empty_like(x_cl)
+    native.check(lib.vg_conv_dgrad(C.byref(d), native.ptr(dy_cl), native.ptr(w), native.ptr(dxm), native.ptr(act_cl),
+                                   None, None, None, None, st))
+    istd = torch.rand(N // group, cin, device=dev, generator=gen) + 0.5
+    mistd = torch.randn(N // group, cin, device=dev, generator=gen)
+    sums = torch.zeros(N // group, cin, 2, dtype=torch.float64, device=dev)
+    dxb = torch.empty_like(x_cl)
+    native.check(lib.vg_conv_dgrad(C.byref(d), native.ptr(dy_cl), native.ptr(w), native.ptr(dxb), None,
+                                   native.ptr(act_cl), native.ptr(istd), native.ptr(mistd), native.ptr(sums), st))
+    torch.cuda.synchronize()
+    gx = xa.grad
+    assert rel_err(from_cl(dxm).cpu(), (gx * (act > 0)).cpu()) < 1e-5
+    assert rel_err(from_cl(dxb).cpu(), gx.cpu()) < 1e-5
+    xh = act * istd.repeat_interleave(group, 0)[:, :, None, None, None] - mistd.repeat_interleave(group, 0)[:, :, None, None, None]
+    ref_sums = torch.stack([gx.double().reshape(N // group, group, cin, -1).sum((1, 3)),
+                            (gx.double() * xh.double()).reshape(N // group, group, cin, -1).sum((1, 3))], -1)
+    assert rel_err(sums.cpu(), ref_sums.cpu()) < 2e-5
+
+
+def test_conv_rejects_bad_descriptor(lib):
+    native = nat()
+    d = native.conv_desc(0, 8, 8, (3, 3, 3), 1, (5, 5, 5), 2, 1)
+    d.out[0] = 7   # violates the size formula
+    t = torch.zeros(8, device="cuda")
+    rc = lib.vg_conv_fwd(C.byref(d), native.ptr(t), native.ptr(t), None, None, None, native.ptr(t), 0, None,
+                         native.stream_ptr())
+    assert rc == -1 and b"output size" in lib.vg_last_error()
+    d2 = native.conv_desc(0, 3, 8, (3, 3, 3), 1, (5, 5, 5), 2, 1)   # unsupported channel count
+    rc = lib.vg_conv_fwd(C.byref(d2), native.ptr(t), native.ptr(t), None, None, None, native.ptr(t), 0, None,
+                         native.stream_ptr())
+    assert rc == -1
+
+
+@pytest.mark.parametrize("c,spatial", [(1, 70315), (8, 6992), (16, 240)])
+def test_batchnorm_helpers(lib, c, spatial):
+    """stats -> finalize -> folded affine == F.batch_norm(training=True); backward apply == autograd."""
+    native = nat()
+    dev = "cuda"
+    N, group = 6, 3
+    G = N // group
+    gen = torch.Generator(device=dev).manual_seed(c)
+    x = torch.relu(torch.randn(N, spatial, c, device=dev, generator=gen) + 0.3)
+    gamma = torch.rand(c, device=dev, generator=gen) + 0.5
+    beta = torch.randn(c, device=dev, generator=gen)
+    stats = torch.zeros(G, c, 2, dtype=torch.float64, device=dev)
+    st = native.stream_ptr()
+    native.check(lib.vg_bn_stats(native.ptr(x), N, group, spatial, c, native.ptr(stats), st))
+    coef = [torch.empty(G, c, device=dev) for _ in range(4)]
+    count = float(group * spatial)
+    native.check(lib.vg_bn_finalize(native.ptr(stats), native.ptr(gamma), native.ptr(beta), G, c, count,
+                                    *[native.ptr(t) for t in coef], st))
+    scale, shift, istd, mistd = coef
+    xr = x.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    ys = []
+    for g in range(G):   # one F.batch_norm call per group, channels-first view
+        xg = xr[g * group:(g + 1) * group].permute(0, 2, 1)
+        ys.append(F.batch_norm(xg, None, None, gr, br, True, 0.0, 1e-5).permute(0, 2, 1))
+    y_ref = torch.cat(ys)
+    y = x.reshape(G, group, spatial, c) * scale[:, None, None, :] + shift[:, None, None, :]
+    torch.cuda.synchronize()
+    assert rel_err(y.reshape(N, spatial, c).cpu(), y_ref.detach().cpu()) < 1e-5
+    dy = torch.randn_like(y_ref)
+    y_ref.backward(dy)
+    xh = x.reshape(G, group, spatial, c) * istd[:, None, None, :] - mistd[:, None, None, :]
+    sums = torch.stack([dy.double().reshape(G, group, spatial, c).sum((1, 2)),
+                        (dy.double().reshape(G, group, spatial, c) * xh.double()).sum((1, 2))], -1).contiguous()
+    dx = torch.empty_like(x)
+    dgamma, dbeta = torch.zeros(c, device=dev), torch.zeros(c, device=dev)
+    native.check(lib.vg_bn_bwd_apply(native.ptr(dy), native.ptr(x), native.ptr(sums), native.ptr(scale),
+                                     native.ptr(istd), native.ptr(mistd), N, group, spatial, c, count, 0,
+                                     native.ptr(dx), native.ptr(dgamma), native.ptr(dbeta), st))
+    torch.cuda.synchronize()
+    assert rel_err(dx.cpu(), xr.grad.cpu()) < 2e-5
+    assert rel_err(dgamma.cpu(), gr.grad.cpu()) < 2e-5
+    assert rel_err(dbeta.cpu(), br.grad.cpu()) < 2e-5
+    # relu-masked variant
+    dxm = torch.empty_like(x)
+    native.check(lib.vg_bn_bwd_apply(native.ptr(dy), native.ptr(x), native.ptr(sums), native.ptr(scale),
+                                     native.ptr(istd), native.ptr(mistd), N, group, spatial, c, count, 1,
+                                     native.ptr(dxm), None, None, st))
+    torch.cuda.synchronize()
+    assert rel_err(dxm.cpu(), (xr.grad * (x > 0)).cpu()) < 2e-5
+
+
+def test_layout_transposes(lib):
+    native = nat()
+    x = torch.randn(5, 16, 240, device="cuda")
+    y = torch.empty(5, 240, 16, device="cuda")
+    native.check(lib.vg_nchw_to_nhwc(native.ptr(x), native.ptr(y), 5, 16, 240, native.stream_ptr()))
+    z = torch.empty_like(x)
+    native.check(lib.vg_nhwc_to_nchw(native.ptr(y), native.ptr(z), 5, 16, 240, native.stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.equal(y, x.permute(0, 2, 1).contiguous()) and torch.equal(z, x)
+
+
+@pytest.mark.parametrize("m,n,k", [(2, 200, 3072), (32, 50, 100), (288, 3840, 200), (1, 32, 50), (36, 50, 41)])
+def test_linear_forward_backward(lib, m, n, k):
+    native = nat()
+    dev = "cuda"
+    gen = torch.Generator(device=dev).manual_seed(m + n + k)
+    x = torch.randn(m, k, device=dev, generator=gen)
+    w = torch.randn(n, k, device=dev, generator=gen) * 0.1
+    b = torch.randn(n, device=dev, generator=gen)
+    y = torch.empty(m, n, device=dev)
+    st = native.stream_ptr()
+    native.check(lib.vg_linear_fwd(native.ptr(x), native.ptr(w), native.ptr(b), native.ptr(y), m, n, k,
+                                   native.ACT_RELU, st))
+    xr, wr, br = (t.clone().requires_grad_(True) for t in (x, w, b))
+    y_ref = torch.relu(F.linear(xr, wr, br))
+    torch.cuda.synchronize()
+    assert rel_err(y.cpu(), y_ref.detach().cpu()) < 1e-5
+    dy = torch.randn_like(y)
+    y_ref.backward(dy)
+    dx = torch.empty_like(x)
+    dw, db = torch.zeros_like(w), torch.zeros_like(b)
+    native.check(lib.vg_linear_bwd(native.ptr(dy), native.ptr(y), native.ptr(x), native.ptr(w), native.ptr(dx),
+                                   native.ptr(dw), native.ptr(db), m, n, k, st))
+    torch.cuda.synchronize()
+    assert rel_err(dx.cpu(), xr.grad.cpu()) < 1e-5
+    assert rel_err(dw.cpu(), wr.grad.cpu()) < 1e-5
+    assert rel_err(db.cpu(), br.grad.cpu()) < 1e-5
+
+
+@pytest.mark.parametrize("B,small_d", [(1, False), (4, False), (32, True), (70, False)])
+def test_latent_sample_kl(lib, B, small_d):
+    native = nat()
+    from oracle import ref_port as rp
+    dev = "cuda"
+    gen = torch.Generator().manual_seed(B)
+    heads = torch.randn(3, B, 32, generator=gen) * 0.5
+    if small_d:
+        heads[2, 0, 0] = -20.0     # d < 1e-6 somewhere -> every d gets + 1e-6 (vae_reg_GP.py:321-323)
+    eps_w, eps_d = torch.randn(B, 1, generator=gen), torch.randn(B, 32, generator=gen)
+    hd = heads.double().requires_grad_(True)
+    z_ref, klz_ref, d_ref = rp.latent_sample_kl(hd[0], hd[1], torch.exp(hd[2]), eps_w.double(), eps_d.double())
+    hg, ew, ed = heads.to(dev), eps_w.to(dev), eps_d.to(dev)
+    z = torch.empty(B, 32, device=dev); klz = torch.empty(B, device=dev); dd = torch.empty(B, 32, device=dev)
+    zcat = torch.empty(9, B, 41, device=dev); flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    st = native.stream_ptr()
+    native.check(lib.vg_latent_fwd(native.ptr(hg), native.ptr(ew), native.ptr(ed), B, native.ptr(z), native.ptr(klz),
+                                   native.ptr(dd), native.ptr(zcat), native.ptr(flag), st))
+    torch.cuda.synchronize()
+    assert int(flag) == int(small_d)
+    assert rel_err(z.cpu(), z_ref.detach()) < 1e-6
+    assert rel_err(klz.cpu(), klz_ref.detach()) < 1e-5
+    assert torch.equal(zcat[:, :, :32], z.expand(9, B, 32))
+    assert torch.equal(zcat[:, :, 32:], torch.eye(9, device=dev)[:, None, :].expand(9, B, 9))
+    dzcat = torch.randn(9, B, 41, generator=gen)
+    dklz = torch.rand(B, generator=gen)
+    (z_ref * dzcat[:, :, :32].double().sum(0)).sum().add((klz_ref * dklz.double()).sum()).backward()
+    dheads = torch.empty(3, B, 32, device=dev)
+    native.check(lib.vg_latent_bwd(native.ptr(hg), native.ptr(ew), native.ptr(ed), native.ptr(dd),
+                                   native.ptr(dzcat.to(dev)), native.ptr(dklz.to(dev)), B, native.ptr(dheads), st))
+    torch.cuda.synchronize()
+    assert rel_err(dheads.cpu(), hd.grad) < 2e-5
+
+
+def _gain_setup(B, m, seed):
+    from oracle import ref_port as rp
+    gen = torch.Generator().manual_seed(seed)
+    cov = torch.randn(B, 8, generator=gen) * 1.2
+    eps = torch.randn(8, B, generator=gen)
+    P = {}
+    for i, key in enumerate(rp.GP_KEYS):
+        P["sa_" + key] = torch.normal(1, 1, size=(1, 1), generator=gen)
+        P["logstd_" + key] = torch.normal(0, 1, size=(1, 1), generator=gen) * 0.5
+        if rp.has_gp(i + 1):
+            P["qu_m_" + key] = torch.randn(1, m, generator=gen)
+            S = torch.randn(m, m, generator=gen) * 0.3
+            P["qu_S_" + key] = (2 * torch.eye(m) + S @ S.T).float()
+            P["logkvar_" + key] = torch.tensor(0.1 * i)
+            P["logls_" + key] = torch.tensor(-0.2 + 0.1 * i)
+            P["xu_" + key] = torch.linspace(-3.3, 3.4, m)
+    return cov, eps, P
+
+
+@pytest.mark.parametrize("B,m,neural", [(2, 6, True), (32, 6, True), (32, 6, False), (7, 4, True), (128, 6, True)])
+def test_gain_stage(lib, B, m, neural):
+    """vg_gain_fwd/bwd vs the fp64 oracle with autograd (G1-G7)."""
+    native = nat()
+    from oracle import ref_port as rp
+    dev = "cuda"
+    cov, eps, P = _gain_setup(B, m, 100 + B + m)
+    Pd = {k: v.double().clone().requires_grad_(not k.startswith("xu_")) for k, v in P.items()}
+    g_ref, kl_ref, aux = rp.gains(Pd, cov.double(), eps.double(), neural)
+    dg = torch.randn(8, B, generator=torch.Generator().manual_seed(5))
+    kl_scale = 10.0
+    ((g_ref * dg.double()).sum() + kl_scale * kl_ref).backward()
+
+    Pg = {k: v.to(dev).contiguous() for k, v in P.items()}
+    Gg = {k: torch.zeros_like(v) for k, v in Pg.items()}
+    gp, gg = native.VgGainParams(), native.VgGainGrads()
+    for i, key in enumerate(rp.GP_KEYS):
+        gp.sa[i], gp.logstd[i] = native.ptr(Pg["sa_" + key]), native.ptr(Pg["logstd_" + key])
+        gg.sa[i], gg.logstd[i] = native.ptr(Gg["sa_" + key]), native.ptr(Gg["logstd_" + key])
+        gp.hrf[i] = int(neural and i == 0)
+        if rp.has_gp(i + 1):
+            gp.has_gp[i] = 1
+            for f, pk in (("qu_m", "qu_m_"), ("qu_S", "qu_S_"), ("logkvar", "logkvar_"), ("logls", "logls_")):
+                getattr(gp, f)[i] = native.ptr(Pg[pk + key])
+                getattr(gg, f)[i] = native.ptr(Gg[pk + key])
+            gp.xu[i] = native.ptr(Pg["xu_" + key])
+    taps = rp.hrf_taps().to(dev)
+    covg, epsg = cov.to(dev), eps.to(dev)
+    g = torch.empty(8, B, device=dev); kl = torch.zeros(8, 2, dtype=torch.float64, device=dev)
+    bm = torch.empty(8, B, device=dev); bv = torch.empty(8, B, device=dev)
+    status = torch.zeros(8, dtype=torch.int32, device=dev)
+    nbytes = int(lib.vg_gain_workspace_bytes(B, m))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    st = native.stream_ptr()
+    native.check(lib.vg_gain_fwd(C.byref(gp), native.ptr(covg), native.ptr(epsg), native.ptr(taps), B, m, native.ptr(g),
+                                 native.ptr(kl), native.ptr(bm), native.ptr(bv), native.ptr(status), native.ptr(ws),
+                                 nbytes, st))
+    native.check(lib.vg_gain_bwd(C.byref(gp), C.byref(gg), native.ptr(covg), native.ptr(epsg), native.ptr(taps),
+                                 native.ptr(dg.to(dev)), kl_scale, B, m, native.ptr(ws), nbytes, st))
+    torch.cuda.synchronize()
+    assert status.abs().sum().item() == 0
+    assert np.abs(g.cpu().numpy() - g_ref.detach().numpy()).max() < 2e-6 * max(1.0, float(g_ref.abs().max()))
+    assert abs(float(kl.sum()) - float(kl_ref)) < 1e-9 * max(1.0, abs(float(kl_ref)))
+    assert np.abs(bm.cpu().numpy() - aux["mean"].detach().numpy()).max() < 2e-6 * max(1.0, float(aux["mean"].abs().max()))
+    diag = torch.diagonal(aux["cov"], dim1=1, dim2=2).detach()
+    assert rel_err(bv.cpu(), diag) < 1e-6
+    for k, v in Gg.items():
+        if k.startswith("xu_"):
+            continue
+        ref = Pd[k].grad
+        if k.startswith("logkvar"):   # tiny by cancellation: absolute tolerance relative to the other GP grads
+            assert abs(float(v.cpu()) - float(ref)) < 1e-5 * max(1.0, float(Pd["qu_m_" + k[8:]].grad.abs().max()))
+        else:
+            assert rel_err(v.cpu(), ref) < 5e-6, k
+
+
+def test_gain_reports_non_pd(lib):
+    native = nat()
+    from oracle import ref_port as rp
+    dev = "cuda"
+    B, m = 4, 6
+    cov, eps, P = _gain_setup(B, m, 3)
+    P["qu_S_x"] = -torch.eye(m)            # not positive definite -> status, no NaN trap / crash
+    Pg = {k: v.to(dev).contiguous() for k, v in P.items()}
+    gp = native.VgGainParams()
+    for i, key in enumerate(rp.GP_KEYS):
+        gp.sa[i], gp.logstd[i] = native.ptr(Pg["sa_" + key]), native.ptr(Pg["logstd_" + key])
+        if rp.has_gp(i + 1):
+            gp.has_gp[i] = 1
+            gp.qu_m[i], gp.qu_S[i] = native.ptr(Pg["qu_m_" + key]), native.ptr(Pg["qu_S_" + key])
+            gp.logkvar[i], gp.logls[i], gp.xu[i] = native.ptr(Pg["logkvar_" + key]), native.ptr(Pg["logls_" + key]), native.ptr(Pg["xu_" + key])
+    g = torch.empty(8, B, device=dev); kl = torch.zeros(8, 2, dtype=torch.float64, device=dev)
+    status = torch.zeros(8, dtype=torch.int32, device=dev)
+    nbytes = int(lib.vg_gain_workspace_bytes(B, m)); ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    native.check(lib.vg_gain_fwd(C.byref(gp), native.ptr(cov.to(dev)), native.ptr(eps.to(dev)),
+                                 native.ptr(rp.hrf_taps().to(dev)), B, m, native.ptr(g), native.ptr(kl), None, None,
+                                 native.ptr(status), native.ptr(ws), nbytes, native.stream_ptr()))
+    torch.cuda.synchronize()
+    assert status[1].item() != 0 and status[0].item() == 0
+
+
+@pytest.mark.parametrize("B", [1, 2, 5, 32])
+def test_fused_recon_loss(lib, B):
+    """vg_recon_loss_fwd/bwd vs the fp64 oracle (R1-R4 and the fused-pass gradients)."""
+    native = nat()
+    from oracle import ref_port as rp
+    dev = "cuda"
+    V, VP = native.V, native.VP
+    gen = torch.Generator().manual_seed(40 + B)
+    maps = torch.rand(9, B, V, generator=gen) * 0.98 + 0.01
+    pre = torch.log(maps / (1 - maps)).double().requires_grad_(True)          # pre-sigmoid
+    g = (torch.randn(8, B, generator=gen)).double().requires_grad_(True)
+    x = torch.rand(B, V, generator=gen)
+    eps = (torch.randn(V, generator=gen) * 0.3 - 2.0).double().requires_grad_(True)
+    glm = torch.rand(V, 8, generator=gen)
+    lam = 0.7
+    rl = rp.recon_loss(torch.sigmoid(pre), g, x.double(), eps, glm.double(), lam)
+    tot = -rl["logp"].mean() + lam * rl["glm_reg"]
+    tot.backward()
+
+    mp = torch.zeros(9, B, VP, device=dev); mp[:, :, :V] = maps.to(dev)
+    mp[:, :, V:] = float("nan")                                                 # padding must never leak
+    ep = torch.zeros(VP, device=dev); ep[:V] = eps.detach().float().to(dev)
+    gl = torch.zeros(8, VP, device=dev); gl[:, :V] = glm.t().to(dev)
+    gd, xd = g.detach().float().to(dev).contiguous(), x.to(dev)
+    logp = torch.empty(B, device=dev); norms = torch.empty(8, B, device=dev)
+    cons = torch.empty(8, B, V, device=dev); xrec = torch.empty(B, V, device=dev)
+    nbytes = int(lib.vg_recon_workspace_bytes(B, V)); ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    st = native.stream_ptr()
+    native.check(lib.vg_recon_loss_fwd(native.ptr(mp), native.ptr(gd), native.ptr(xd), native.ptr(ep), native.ptr(gl), B,
+                                       V, native.ptr(logp), native.ptr(norms), native.ptr(cons), native.ptr(xrec),
+                                       native.ptr(ws), nbytes, st))
+    dpre = torch.zeros(9, B, VP, device=dev); dg = torch.empty(8, B, device=dev); deps = torch.empty(VP, device=dev)
+    native.check(lib.vg_recon_loss_bwd(native.ptr(mp), native.ptr(gd), native.ptr(xd), native.ptr(ep), native.ptr(gl),
+                                       native.ptr(norms), B, V, lam, native.ptr(dpre), native.ptr(dg), native.ptr(deps),
+                                       native.ptr(ws), nbytes, st))
+    torch.cuda.synchronize()
+    assert rel_err(logp.cpu(), rl["logp"].detach()) < 2e-6
+    assert rel_err(norms.cpu(), rl["glm_norms"].detach()) < 2e-6
+    assert rel_err(cons.cpu(), rl["cons"].detach()) < 1e-6
+    assert rel_err(xrec.cpu(), rl["x_rec"].detach()) < 1e-6
+    assert rel_err(dpre[:, :, :V].cpu(), pre.grad) < 2e-5
+    assert rel_err(dg.cpu(), g.grad) < 2e-5
+    assert rel_err(deps[:V].cpu(), eps.grad) < 2e-5
+
+
+def test_fused_adam_matches_torch(lib):
+    native = nat()
+    dev = "cuda"
+    gen = torch.Generator(device=dev).manual_seed(0)
+    p32 = torch.randn(10007, device=dev, generator=gen); p64 = torch.randn(501, device=dev, dtype=torch.float64, generator=gen)
+    r32, r64 = p32.clone().requires_grad_(True), p64.clone().requires_grad_(True)
+    opt = torch.optim.Adam([r32, r64], lr=1e-3)
+    m32, v32 = torch.zeros_like(p32), torch.zeros_like(p32)
+    m64, v64 = torch.zeros_like(p64), torch.zeros_like(p64)
+    step = torch.zeros(1, dtype=torch.int64, device=dev)
+    for it in range(5):
+        g32 = torch.randn(10007, device=dev, generator=gen); g64 = torch.randn(501, device=dev, dtype=torch.float64, generator=gen)
+        r32.grad, r64.grad = g32.clone(), g64.clone()
+        opt.step()
+        native.check(lib.vg_adam_step(native.ptr(p32), native.ptr(g32), native.ptr(m32), native.ptr(v32), p32.numel(),
+                                      native.ptr(p64), native.ptr(g64), native.ptr(m64), native.ptr(v64), p64.numel(),
+                                      1e-3, 0.9, 0.999, 1e-8, 1.0, native.ptr(step), native.stream_ptr()))
+    torch.cuda.synchronize()
+    assert int(step) == 5
+    assert rel_err(p32.cpu(), r32.detach().cpu()) < 1e-6
+    assert rel_err(p64.cpu(), r64.detach().cpu()) < 1e-12
+
+
+def test_gp_posterior_matches_oracle(lib):
+    import gp as gpmod
+    from oracle import ref_port as rp
+    dev = "cuda"
+    m, nq = 6, 300
+    gen = torch.Generator().manual_seed(9)
+    xu = torch.linspace(-3, 3, m); qm = torch.randn(1, m, generator=gen)
+    S = torch.randn(m, m, generator=gen) * 0.3; qs = 2 * torch.eye(m) + S @ S.T
+    kv, ls = torch.tensor(1.1), torch.tensor(2.3)
+    xq = torch.randn(nq, generator=gen) * 1.5
+    f_ref, s_ref = rp.gp_posterior(xu.double(), kv.double(), ls.double(), qm.double().reshape(-1), qs.double(), xq.double())
+    reg = gpmod.GP(xu.to(dev), kv.to(dev), ls.to(dev), qm.to(dev), qs.to(dev))
+    f, s = reg.evaluate_posterior(xq.to(dev))
+    f2, var = reg.evaluate_posterior_diag(xq.to(dev))
+    assert rel_err(f.cpu(), f_ref) < 1e-6 and rel_err(s.cpu(), s_ref) < 1e-6
+    assert rel_err(var.cpu(), torch.diagonal(s_ref)) < 1e-6 and torch.equal(f, f2)
+    kl = reg.compute_GP_kl(m)
+    assert abs(float(kl) - float(rp.gp_kl(qm.double().reshape(-1), qs.double()))) < 1e-5

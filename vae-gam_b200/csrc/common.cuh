@@ -11,6 +11,19 @@ namespace vg {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 
+// Optional per-operation timing with CUDA events on the launching stream (vg_profile_*).
+// A scope costs nothing unless profiling was enabled.
+bool profiling();
+void prof_begin(const char* name, cudaStream_t st);
+void prof_end(cudaStream_t st);
+struct ProfScope {
+  cudaStream_t st;
+  bool on;
+  ProfScope(const char* name, cudaStream_t s) : st(s), on(profiling()) { if (on) prof_begin(name, st); }
+  ~ProfScope() { if (on) prof_end(st); }
+};
+#define VG_PROF(name, st) vg::ProfScope prof_scope_##__LINE__(name, st)
+
 #define VG_CHECK_ARG(cond, msg)                                        \
   do {                                                                 \
     if (!(cond)) {                                                     \

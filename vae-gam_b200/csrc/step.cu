@@ -219,26 +219,60 @@ static int finalize_bn(const BnBuf& bn, const float* gamma, const float* beta, i
 
 // ---- forward pieces ----------------------------------------------------------------
 static int run_encoder(const VgStepIO* io, const EncWs& e, int B, cudaStream_t st) {
+  { VG_PROF("bn_stats", st);
   VG_TRY(vg_bn_stats(io->x, B, B, V, 1, e.bn1.stats, st));
+  }
+  { VG_PROF("bn1.bn_finalize", st);
   VG_TRY(finalize_bn(e.bn1, PF(BN1), PF(BN1 + 1), 1, 1, (double)B * V, st));
+  }
   VgConvDesc d1 = make_desc(kConv[0], B, B), d2 = make_desc(kConv[1], B, B), d3 = make_desc(kConv[2], B, B),
              d4 = make_desc(kConv[3], B, B), d5 = make_desc(kConv[4], B, B);
+  { VG_PROF("conv1.fwd", st);
   VG_TRY(vg_conv_fwd(&d1, io->x, PF(CONV1), PF(CONV1 + 1), e.bn1.scale, e.bn1.shift, e.a1, VG_ACT_RELU, nullptr, st));
+  }
+  { VG_PROF("conv2.fwd", st);
   VG_TRY(vg_conv_fwd(&d2, e.a1, PF(CONV2), PF(CONV2 + 1), nullptr, nullptr, e.a2, VG_ACT_RELU, e.bn3.stats, st));
+  }
+  { VG_PROF("bn3.bn_finalize", st);
   VG_TRY(finalize_bn(e.bn3, PF(BN3), PF(BN3 + 1), 1, 8, (double)B * vol(kConv[1].out), st));
+  }
+  { VG_PROF("conv3.fwd", st);
   VG_TRY(vg_conv_fwd(&d3, e.a2, PF(CONV3), PF(CONV3 + 1), e.bn3.scale, e.bn3.shift, e.a3, VG_ACT_RELU, nullptr, st));
+  }
+  { VG_PROF("conv4.fwd", st);
   VG_TRY(vg_conv_fwd(&d4, e.a3, PF(CONV4), PF(CONV4 + 1), nullptr, nullptr, e.a4, VG_ACT_RELU, e.bn5.stats, st));
+  }
+  { VG_PROF("bn5.bn_finalize", st);
   VG_TRY(finalize_bn(e.bn5, PF(BN5), PF(BN5 + 1), 1, 16, (double)B * vol(kConv[3].out), st));
+  }
+  { VG_PROF("conv5.fwd", st);
   VG_TRY(vg_conv_fwd(&d5, e.a4, PF(CONV5), PF(CONV5 + 1), e.bn5.scale, e.bn5.shift, e.a5, VG_ACT_RELU, nullptr, st));
+  }
+  { VG_PROF("layout", st);
   VG_TRY(vg_nhwc_to_nchw(e.a5, e.a5f, B, 16, 192, st));   // h.view(-1, 3072) is channel-major
   VG_TRY(vg_linear_fwd(e.a5f, PF(FC1), PF(FC1 + 1), e.h1, B, 200, 3072, VG_ACT_RELU, st));
+  }
+  { VG_PROF("fc2.fwd", st);
   VG_TRY(vg_linear_fwd(e.h1, PF(FC2), PF(FC2 + 1), e.h2, B, 100, 200, VG_ACT_RELU, st));
+  }
+  { VG_PROF("fc31.fwd", st);
   VG_TRY(vg_linear_fwd(e.h2, PF(FC31), PF(FC31 + 1), e.h31, B, 50, 100, VG_ACT_RELU, st));
+  }
+  { VG_PROF("fc32.fwd", st);
   VG_TRY(vg_linear_fwd(e.h2, PF(FC32), PF(FC32 + 1), e.h32, B, 50, 100, VG_ACT_RELU, st));
+  }
+  { VG_PROF("fc33.fwd", st);
   VG_TRY(vg_linear_fwd(e.h2, PF(FC33), PF(FC33 + 1), e.h33, B, 50, 100, VG_ACT_RELU, st));
+  }
+  { VG_PROF("fc41.fwd", st);
   VG_TRY(vg_linear_fwd(e.h31, PF(FC41), PF(FC41 + 1), e.heads, B, L, 50, VG_ACT_NONE, st));
+  }
+  { VG_PROF("fc42.fwd", st);
   VG_TRY(vg_linear_fwd(e.h32, PF(FC42), PF(FC42 + 1), e.heads + (size_t)B * L, B, L, 50, VG_ACT_NONE, st));
+  }
+  { VG_PROF("fc43.fwd", st);
   VG_TRY(vg_linear_fwd(e.h33, PF(FC43), PF(FC43 + 1), e.heads + (size_t)2 * B * L, B, L, 50, VG_ACT_NONE, st));
+  }
   return VG_OK;
 }
 
@@ -246,23 +280,49 @@ static int run_encoder(const VgStepIO* io, const EncWs& e, int B, cudaStream_t s
 static int run_decoder(const VgStepIO* io, const DecWs& d, const float* zcat, int nd, int group, float* out,
                        long long out_stride, cudaStream_t st) {
   const int groups = nd / group;
+  { VG_PROF("fc5.fwd", st);
   VG_TRY(vg_linear_fwd(zcat, PF(FC5), PF(FC5 + 1), d.f5, nd, 50, ZD, VG_ACT_RELU, st));
+  }
+  { VG_PROF("fc6.fwd", st);
   VG_TRY(vg_linear_fwd(d.f5, PF(FC6), PF(FC6 + 1), d.f6, nd, 100, 50, VG_ACT_RELU, st));
+  }
+  { VG_PROF("fc7.fwd", st);
   VG_TRY(vg_linear_fwd(d.f6, PF(FC7), PF(FC7 + 1), d.f7, nd, 200, 100, VG_ACT_RELU, st));
+  }
+  { VG_PROF("fc8.fwd", st);
   VG_TRY(vg_linear_fwd(d.f7, PF(FC8), PF(FC8 + 1), d.f8, nd, 3840, 200, VG_ACT_RELU, st));
+  }
+  { VG_PROF("layout", st);
   VG_TRY(vg_nchw_to_nhwc(d.f8, d.t0, nd, 16, 240, st));   // view(-1,16,6,8,5) -> channels-last
   VG_TRY(vg_bn_stats(d.t0, nd, group, 240, 16, d.bnt1.stats, st));
+  }
+  { VG_PROF("bnt1.bn_finalize", st);
   VG_TRY(finalize_bn(d.bnt1, PF(BNT1), PF(BNT1 + 1), groups, 16, (double)group * 240, st));
+  }
   VgConvDesc c1 = make_desc(kConvT[0], nd, group), c2 = make_desc(kConvT[1], nd, group),
              c3 = make_desc(kConvT[2], nd, group), c4 = make_desc(kConvT[3], nd, group),
              c5 = make_desc(kConvT[4], nd, group, 0, out_stride);
+  { VG_PROF("convt1.fwd", st);
   VG_TRY(vg_conv_fwd(&c1, d.t0, PF(CONVT1), PF(CONVT1 + 1), d.bnt1.scale, d.bnt1.shift, d.t1, VG_ACT_RELU, nullptr, st));
+  }
+  { VG_PROF("convt2.fwd", st);
   VG_TRY(vg_conv_fwd(&c2, d.t1, PF(CONVT2), PF(CONVT2 + 1), nullptr, nullptr, d.t2, VG_ACT_RELU, d.bnt3.stats, st));
+  }
+  { VG_PROF("bnt3.bn_finalize", st);
   VG_TRY(finalize_bn(d.bnt3, PF(BNT3), PF(BNT3 + 1), groups, 16, (double)group * vol(kConvT[1].out), st));
+  }
+  { VG_PROF("convt3.fwd", st);
   VG_TRY(vg_conv_fwd(&c3, d.t2, PF(CONVT3), PF(CONVT3 + 1), d.bnt3.scale, d.bnt3.shift, d.t3, VG_ACT_RELU, nullptr, st));
+  }
+  { VG_PROF("convt4.fwd", st);
   VG_TRY(vg_conv_fwd(&c4, d.t3, PF(CONVT4), PF(CONVT4 + 1), nullptr, nullptr, d.t4, VG_ACT_RELU, d.bnt5.stats, st));
+  }
+  { VG_PROF("bnt5.bn_finalize", st);
   VG_TRY(finalize_bn(d.bnt5, PF(BNT5), PF(BNT5 + 1), groups, 8, (double)group * vol(kConvT[3].out), st));
+  }
+  { VG_PROF("convt5.fwd", st);
   VG_TRY(vg_conv_fwd(&c5, d.t4, PF(CONVT5), PF(CONVT5 + 1), d.bnt5.scale, d.bnt5.shift, out, VG_ACT_SIGMOID, nullptr, st));
+  }
   return VG_OK;
 }
 
@@ -319,16 +379,22 @@ extern "C" int vg_step_fwd(const VgStepConfig* cfg, const VgStepIO* io, void* wo
   cast_eps_kernel<<<cdiv(VP, 256), 256, 0, st>>>(reinterpret_cast<const double*>(io->params[EPSILON]), w.eps32);
   VG_LAUNCH_CHECK();
   VG_TRY(run_encoder(io, w.e, B, st));
+  { VG_PROF("latent.fwd", st);
   VG_TRY(vg_latent_fwd(w.e.heads, io->eps_w, io->eps_d, B, io->z, w.klz, w.d_used, w.zcat,
                        io->status ? io->status + 8 : nullptr, st));
+  }
   VG_TRY(run_decoder(io, w.d, w.zcat, NDEC * B, B, io->maps, VP, st));
   VgGainParams gp;
   fill_gain_params(cfg, io, gp, nullptr);
+  { VG_PROF("gain.fwd", st);
   VG_TRY(vg_gain_fwd(&gp, io->covariates, io->eps_g, io->taps, B, cfg->m, io->g, w.kl_terms, io->beta_mean,
                      io->beta_var, io->status, w.gain_ws, w.gain_ws_bytes, st));
+  }
+  { VG_PROF("recon_loss.fwd", st);
   VG_TRY(vg_recon_loss_fwd(io->maps, io->g, io->x, w.eps32, io->glm_t, B, V, w.logp, w.norms,
                            cfg->want_maps ? io->cons : nullptr, cfg->want_maps ? io->x_rec : nullptr, w.recon_ws,
                            w.recon_ws_bytes, st));
+  }
   scalars_kernel<<<1, 32, 0, st>>>(w.logp, w.klz, w.norms, w.kl_terms, B, cfg->gp_kl_scale, cfg->glm_reg_scale,
                                    io->out_scalars);
   VG_LAUNCH_CHECK();
@@ -348,85 +414,169 @@ extern "C" int vg_step_bwd(const VgStepConfig* cfg, const VgStepIO* io, void* wo
   const DecWs& d = w.d;
 
   // ---- objective
+  { VG_PROF("recon_loss.bwd", st);
   VG_TRY(vg_recon_loss_bwd(io->maps, io->g, io->x, w.eps32, io->glm_t, w.norms, B, V, cfg->glm_reg_scale, w.dpre5,
                            w.dg, w.deps32, w.recon_ws, w.recon_ws_bytes, st));
+  }
   add_eps_grad_kernel<<<cdiv(V, 256), 256, 0, st>>>(w.deps32, reinterpret_cast<double*>(io->grads[EPSILON]));
   VG_LAUNCH_CHECK();
   VgGainParams gp; VgGainGrads gg;
   fill_gain_params(cfg, io, gp, &gg);
+  { VG_PROF("gain.bwd", st);
   VG_TRY(vg_gain_bwd(&gp, &gg, io->covariates, io->eps_g, io->taps, w.dg, (double)cfg->gp_kl_scale, B, cfg->m,
                      w.gain_ws, w.gain_ws_bytes, st));
+  }
 
   // ---- decoder (9B images, groups of B)
   VgConvDesc c1 = make_desc(kConvT[0], nd, B), c2 = make_desc(kConvT[1], nd, B), c3 = make_desc(kConvT[2], nd, B),
              c4 = make_desc(kConvT[3], nd, B), c5 = make_desc(kConvT[4], nd, B, 0, VP);
+  { VG_PROF("convt5.wgrad", st);
   VG_TRY(vg_conv_wgrad(&c5, d.t4, w.dpre5, d.bnt5.scale, d.bnt5.shift, GF(CONVT5), GF(CONVT5 + 1), st));
+  }
+  { VG_PROF("convt5.dgrad", st);
   VG_TRY(vg_conv_dgrad(&c5, w.dpre5, PF(CONVT5), w.d_t4, nullptr, d.t4, d.bnt5.istd, d.bnt5.mistd, d.bnt5.sums, st));
+  }
+  { VG_PROF("bnt5.bn_bwd", st);
   VG_TRY(vg_bn_bwd_apply(w.d_t4, d.t4, d.bnt5.sums, d.bnt5.scale, d.bnt5.istd, d.bnt5.mistd, nd, B,
                          vol(kConvT[3].out), 8, (double)B * vol(kConvT[3].out), 1, w.d_t4, GF(BNT5), GF(BNT5 + 1), st));
+  }
+  { VG_PROF("convt4.wgrad", st);
   VG_TRY(vg_conv_wgrad(&c4, d.t3, w.d_t4, nullptr, nullptr, GF(CONVT4), GF(CONVT4 + 1), st));
+  }
+  { VG_PROF("convt4.dgrad", st);
   VG_TRY(vg_conv_dgrad(&c4, w.d_t4, PF(CONVT4), w.d_t3, d.t3, nullptr, nullptr, nullptr, nullptr, st));
+  }
+  { VG_PROF("convt3.wgrad", st);
   VG_TRY(vg_conv_wgrad(&c3, d.t2, w.d_t3, d.bnt3.scale, d.bnt3.shift, GF(CONVT3), GF(CONVT3 + 1), st));
+  }
+  { VG_PROF("convt3.dgrad", st);
   VG_TRY(vg_conv_dgrad(&c3, w.d_t3, PF(CONVT3), w.d_t2, nullptr, d.t2, d.bnt3.istd, d.bnt3.mistd, d.bnt3.sums, st));
+  }
+  { VG_PROF("bnt3.bn_bwd", st);
   VG_TRY(vg_bn_bwd_apply(w.d_t2, d.t2, d.bnt3.sums, d.bnt3.scale, d.bnt3.istd, d.bnt3.mistd, nd, B,
                          vol(kConvT[1].out), 16, (double)B * vol(kConvT[1].out), 1, w.d_t2, GF(BNT3), GF(BNT3 + 1), st));
+  }
+  { VG_PROF("convt2.wgrad", st);
   VG_TRY(vg_conv_wgrad(&c2, d.t1, w.d_t2, nullptr, nullptr, GF(CONVT2), GF(CONVT2 + 1), st));
+  }
+  { VG_PROF("convt2.dgrad", st);
   VG_TRY(vg_conv_dgrad(&c2, w.d_t2, PF(CONVT2), w.d_t1, d.t1, nullptr, nullptr, nullptr, nullptr, st));
+  }
+  { VG_PROF("convt1.wgrad", st);
   VG_TRY(vg_conv_wgrad(&c1, d.t0, w.d_t1, d.bnt1.scale, d.bnt1.shift, GF(CONVT1), GF(CONVT1 + 1), st));
+  }
+  { VG_PROF("convt1.dgrad", st);
   VG_TRY(vg_conv_dgrad(&c1, w.d_t1, PF(CONVT1), w.d_t0, nullptr, d.t0, d.bnt1.istd, d.bnt1.mistd, d.bnt1.sums, st));
+  }
+  { VG_PROF("bnt1.bn_bwd", st);
   VG_TRY(vg_bn_bwd_apply(w.d_t0, d.t0, d.bnt1.sums, d.bnt1.scale, d.bnt1.istd, d.bnt1.mistd, nd, B, 240, 16,
                          (double)B * 240, 1, w.d_t0, GF(BNT1), GF(BNT1 + 1), st));
+  }
+  { VG_PROF("layout", st);
   VG_TRY(vg_nhwc_to_nchw(w.d_t0, w.d_f8, nd, 16, 240, st));     // gradient w.r.t. fc8 pre-activation
   VG_TRY(vg_linear_bwd(w.d_f8, nullptr, d.f7, PF(FC8), w.d_f7, GF(FC8), GF(FC8 + 1), nd, 3840, 200, st));
+  }
+  { VG_PROF("fc7.bwd", st);
   VG_TRY(vg_linear_bwd(w.d_f7, d.f7, d.f6, PF(FC7), w.d_f6, GF(FC7), GF(FC7 + 1), nd, 200, 100, st));
+  }
+  { VG_PROF("fc6.bwd", st);
   VG_TRY(vg_linear_bwd(w.d_f6, d.f6, d.f5, PF(FC6), w.d_f5, GF(FC6), GF(FC6 + 1), nd, 100, 50, st));
+  }
+  { VG_PROF("fc5.bwd", st);
   VG_TRY(vg_linear_bwd(w.d_f5, d.f5, w.zcat, PF(FC5), w.d_zcat, GF(FC5), GF(FC5 + 1), nd, 50, ZD, st));
+  }
 
   // ---- latent
   fill_kernel<<<cdiv(B, 128), 128, 0, st>>>(w.dklz, B, 1.f / (float)B);   // tot = -mean(logp - klz)
   VG_LAUNCH_CHECK();
+  { VG_PROF("latent.bwd", st);
   VG_TRY(vg_latent_bwd(e.heads, io->eps_w, io->eps_d, w.d_used, w.d_zcat, w.dklz, B, w.dheads, st));
+  }
 
   // ---- encoder
   float* d_h31 = w.d_h3;
   float* d_h32 = w.d_h3 + (size_t)B * 50;
   float* d_h33 = w.d_h3 + (size_t)2 * B * 50;
+  { VG_PROF("fc41.bwd", st);
   VG_TRY(vg_linear_bwd(w.dheads, nullptr, e.h31, PF(FC41), d_h31, GF(FC41), GF(FC41 + 1), B, L, 50, st));
+  }
+  { VG_PROF("fc42.bwd", st);
   VG_TRY(vg_linear_bwd(w.dheads + (size_t)B * L, nullptr, e.h32, PF(FC42), d_h32, GF(FC42), GF(FC42 + 1), B, L, 50, st));
+  }
+  { VG_PROF("fc43.bwd", st);
   VG_TRY(vg_linear_bwd(w.dheads + (size_t)2 * B * L, nullptr, e.h33, PF(FC43), d_h33, GF(FC43), GF(FC43 + 1), B, L, 50, st));
+  }
   // three branches fan into h2: reuse d_f5.. scratch?  keep explicit temporaries in d_a5f (B*3072 >= 3*B*100)
   float* t31 = w.d_a5f;
   float* t32 = w.d_a5f + (size_t)B * 100;
   float* t33 = w.d_a5f + (size_t)2 * B * 100;
+  { VG_PROF("fc31.bwd", st);
   VG_TRY(vg_linear_bwd(d_h31, e.h31, e.h2, PF(FC31), t31, GF(FC31), GF(FC31 + 1), B, 50, 100, st));
+  }
+  { VG_PROF("fc32.bwd", st);
   VG_TRY(vg_linear_bwd(d_h32, e.h32, e.h2, PF(FC32), t32, GF(FC32), GF(FC32 + 1), B, 50, 100, st));
+  }
+  { VG_PROF("fc33.bwd", st);
   VG_TRY(vg_linear_bwd(d_h33, e.h33, e.h2, PF(FC33), t33, GF(FC33), GF(FC33 + 1), B, 50, 100, st));
+  }
   add3_kernel<<<cdiv(B * 100, 256), 256, 0, st>>>(w.d_h2, t31, t32, t33, B * 100);
   VG_LAUNCH_CHECK();
+  { VG_PROF("fc2.bwd", st);
   VG_TRY(vg_linear_bwd(w.d_h2, e.h2, e.h1, PF(FC2), w.d_h1, GF(FC2), GF(FC2 + 1), B, 100, 200, st));
+  }
+  { VG_PROF("fc1.bwd", st);
   VG_TRY(vg_linear_bwd(w.d_h1, e.h1, e.a5f, PF(FC1), w.d_a5f, GF(FC1), GF(FC1 + 1), B, 200, 3072, st));
+  }
+  { VG_PROF("layout", st);
   VG_TRY(vg_nchw_to_nhwc(w.d_a5f, w.d_a5, B, 16, 192, st));
+  }
   relu_mask_kernel<<<cdiv((long long)B * 3072, 256), 256, 0, st>>>(w.d_a5, e.a5, (long long)B * 3072);
   VG_LAUNCH_CHECK();
   VgConvDesc d1 = make_desc(kConv[0], B, B), d2 = make_desc(kConv[1], B, B), d3 = make_desc(kConv[2], B, B),
              d4 = make_desc(kConv[3], B, B), d5 = make_desc(kConv[4], B, B);
+  { VG_PROF("conv5.wgrad", st);
   VG_TRY(vg_conv_wgrad(&d5, e.a4, w.d_a5, e.bn5.scale, e.bn5.shift, GF(CONV5), GF(CONV5 + 1), st));
+  }
+  { VG_PROF("conv5.dgrad", st);
   VG_TRY(vg_conv_dgrad(&d5, w.d_a5, PF(CONV5), w.d_a4, nullptr, e.a4, e.bn5.istd, e.bn5.mistd, e.bn5.sums, st));
+  }
+  { VG_PROF("bn5.bn_bwd", st);
   VG_TRY(vg_bn_bwd_apply(w.d_a4, e.a4, e.bn5.sums, e.bn5.scale, e.bn5.istd, e.bn5.mistd, B, B, vol(kConv[3].out), 16,
                          (double)B * vol(kConv[3].out), 1, w.d_a4, GF(BN5), GF(BN5 + 1), st));
+  }
+  { VG_PROF("conv4.wgrad", st);
   VG_TRY(vg_conv_wgrad(&d4, e.a3, w.d_a4, nullptr, nullptr, GF(CONV4), GF(CONV4 + 1), st));
+  }
+  { VG_PROF("conv4.dgrad", st);
   VG_TRY(vg_conv_dgrad(&d4, w.d_a4, PF(CONV4), w.d_a3, e.a3, nullptr, nullptr, nullptr, nullptr, st));
+  }
+  { VG_PROF("conv3.wgrad", st);
   VG_TRY(vg_conv_wgrad(&d3, e.a2, w.d_a3, e.bn3.scale, e.bn3.shift, GF(CONV3), GF(CONV3 + 1), st));
+  }
+  { VG_PROF("conv3.dgrad", st);
   VG_TRY(vg_conv_dgrad(&d3, w.d_a3, PF(CONV3), w.d_a2, nullptr, e.a2, e.bn3.istd, e.bn3.mistd, e.bn3.sums, st));
+  }
+  { VG_PROF("bn3.bn_bwd", st);
   VG_TRY(vg_bn_bwd_apply(w.d_a2, e.a2, e.bn3.sums, e.bn3.scale, e.bn3.istd, e.bn3.mistd, B, B, vol(kConv[1].out), 8,
                          (double)B * vol(kConv[1].out), 1, w.d_a2, GF(BN3), GF(BN3 + 1), st));
+  }
+  { VG_PROF("conv2.wgrad", st);
   VG_TRY(vg_conv_wgrad(&d2, e.a1, w.d_a2, nullptr, nullptr, GF(CONV2), GF(CONV2 + 1), st));
+  }
+  { VG_PROF("conv2.dgrad", st);
   VG_TRY(vg_conv_dgrad(&d2, w.d_a2, PF(CONV2), w.d_a1, e.a1, nullptr, nullptr, nullptr, nullptr, st));
+  }
+  { VG_PROF("conv1.wgrad", st);
   VG_TRY(vg_conv_wgrad(&d1, io->x, w.d_a1, e.bn1.scale, e.bn1.shift, GF(CONV1), GF(CONV1 + 1), st));
+  }
   // bn1 sits on the network input: only its affine parameters need a gradient
+  { VG_PROF("conv1.dgrad", st);
   VG_TRY(vg_conv_dgrad(&d1, w.d_a1, PF(CONV1), nullptr, nullptr, io->x, e.bn1.istd, e.bn1.mistd, e.bn1.sums, st));
+  }
+  { VG_PROF("bn1.bn_bwd", st);
   VG_TRY(vg_bn_bwd_apply(nullptr, io->x, e.bn1.sums, nullptr, nullptr, nullptr, B, B, V, 1, (double)B * V, 0, nullptr,
                          GF(BN1), GF(BN1 + 1), st));
+  }
   return VG_OK;
 }
 

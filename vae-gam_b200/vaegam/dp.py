@@ -1,0 +1,102 @@
+"""Data-parallel training over minibatches: one process per GPU, NCCL over
+NVLink/NVSwitch.  The independent unit is a MINIBATCH (BatchNorm statistics, the HRF filter
+over the batch index and the B x B gain covariance couple the volumes of a batch), so each
+rank runs the full step on its own batch, BatchNorm is not synchronised, and the only
+exchange is the gradient all-reduce: 6.5 MB per step (1 494 109 fp32 + 70 315 fp64) taken
+straight from the flat gradient buffers — no bucketing copies.
+
+N-GPU DP with local batch B equals the AVERAGE of N independent reference steps of batch B
+(the objective is not a per-sample mean: glm_reg ~ B * sum_b, GP KL is per batch).
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend: str | None = None):
+    """Join the process group described by RANK / WORLD_SIZE / MASTER_* (torchrun)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend)
+    return rank, world, local
+
+
+def shard_indices(n_items: int, rank: int, world: int, epoch: int = 0, shuffle: bool = True, seed: int = 0):
+    """Disjoint, equally sized shards of range(n_items) (DistributedSampler-style, drop tail)."""
+    g = torch.Generator().manual_seed(seed + epoch)
+    perm = torch.randperm(n_items, generator=g) if shuffle else torch.arange(n_items)
+    per = n_items // world
+    return perm[rank * per:(rank + 1) * per]
+
+
+class GradientAllReduce:
+    """Sum-all-reduce of the flat gradient buffers; the 1/world factor is folded into the fused
+    Adam kernel (`grad_scale`).  With `overlap=True` the reduce runs on a side stream so the
+    caller can keep enqueueing work (the optimizer step waits on it)."""
+
+    def __init__(self, flat, optimizer=None, group=None, overlap: bool = True):
+        self.flat = flat
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.optimizer = optimizer
+        if optimizer is not None:
+            optimizer.grad_scale = 1.0 / self.world
+        self.cuda = flat.grad32.is_cuda
+        self.stream = torch.cuda.Stream() if (self.cuda and overlap) else None
+        self._pending = None
+
+    def broadcast_parameters(self, src: int = 0):
+        if self.world == 1:
+            return
+        dist.broadcast(self.flat.flat32, src, group=self.group)
+        dist.broadcast(self.flat.flat64, src, group=self.group)
+
+    def start(self):
+        if self.world == 1:
+            return
+        bufs = (self.flat.grad32, self.flat.grad64)
+        if self.stream is None:
+            for b in bufs:
+                dist.all_reduce(b, group=self.group)
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        self.stream.wait_event(ev)
+        with torch.cuda.stream(self.stream):
+            for b in bufs:
+                dist.all_reduce(b, group=self.group)
+            done = torch.cuda.Event()
+            done.record()
+        self._pending = done
+
+    def finish(self):
+        if self._pending is not None:
+            torch.cuda.current_stream().wait_event(self._pending)
+            self._pending = None
+
+    def __call__(self):
+        self.start()
+        self.finish()
+
+
+def train_step(model, reducer: GradientAllReduce, ids, covariates, x, noise=None):
+    """forward + backward + gradient all-reduce + fused Adam; returns the local loss tensor."""
+    loss = model.forward(ids, covariates, x, 'train', train_mode=False, _noise=noise)
+    model.optimizer.zero_grad()
+    loss.backward()
+    reducer()
+    model.optimizer.step()
+    return loss
