@@ -216,8 +216,8 @@ int vg_recon_loss_bwd(const float* maps, const float* g, const float* x, const f
  * grad_scale multiplies the gradient (1/world_size after the NCCL sum).
  * ---------------------------------------------------------------------------------- */
 int vg_adam_step(float* p32, const float* g32, float* m32, float* v32, long long n32, double* p64,
-                 const double* g64, double* m64, double* v64, long long n64, float lr, float beta1,
-                 float beta2, float eps, float grad_scale, long long* step_count, void* stream);
+                 const double* g64, double* m64, double* v64, long long n64, double lr, double beta1,
+                 double beta2, double eps, double grad_scale, long long* step_count, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Whole training step (vae_reg_GP.py:307-413 forward, :427-428 backward) chained on one

@@ -46,9 +46,13 @@ def load_reference():
     finally:
         sys.path.remove(_SHIMS)
         sys.path.remove(REFERENCE_DIR)
-    # park them under private names so the drop-in modules can be imported later
+    # park them under private names so the drop-in modules can be imported later, and drop the
+    # stubs from sys.modules (the reference modules keep their own references to them)
     for name in ("vae_reg_GP", "gp", "utils"):
         sys.modules["_reference_" + name] = sys.modules.pop(name)
+    for name, mod in list(sys.modules.items()):
+        if getattr(mod, "__file__", None) and str(mod.__file__).startswith(_SHIMS):
+            del sys.modules[name]
 
     if not torch.cuda.is_available():
         def _striped_matrix_cpu(n):

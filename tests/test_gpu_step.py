@@ -60,7 +60,7 @@ def test_step_matches_oracle_and_golden(case):
     for n, p in model.named_parameters():
         assert p.grad is not None, n
         ref = Pd[n].grad
-        err = float((p.grad.double().cpu() - ref).norm() / (ref.norm() + 1e-6 * gmax))
+        err = float((p.grad.double().cpu() - ref).norm() / (ref.norm() + 1e-5 * gmax))
         tol = 5e-3 if n.startswith(("logkvar", "logls")) else 2e-3
         assert err < tol, (n, err)
     # ---- vs the reference's golden vectors (forward quantities that do not depend on its GP noise)
@@ -115,12 +115,18 @@ def test_properties_at_baseline_batch():
     sc1 = model._last.scalars.clone()
     t1.backward()
     g1 = model._flat.grad32.clone()
+    model.optimizer.zero_grad()
     t2 = model.forward(ii, cs, xs, 'train', train_mode=False, _noise=noise)
     sc2 = model._last.scalars.clone()
     t2.backward()
     g2 = model._flat.grad32.clone()
     assert torch.equal(sc1, sc2)                                  # forward is bitwise deterministic
     assert rel_err(g1.cpu(), g2.cpu()) < 1e-5                     # backward uses float atomics: ulp-level only
+    # without zero_grad, gradients ACCUMULATE like any autograd leaf (.grad aliases the flat buffer)
+    t3 = model.forward(ii, cs, xs, 'train', train_mode=False, _noise=noise)
+    (0.5 * t3).backward()
+    assert rel_err(model.fc1.weight.grad.cpu(), (1.5 * g2[model._flat.slices["fc1.weight"][1]:][:200 * 3072]).view(200, 3072).cpu()) < 1e-5
+    model.optimizer.zero_grad()
     s = sc1.cpu().numpy()
     assert abs(s[0] - (s[1] + rc["gp_kl_scale"] * s[2] + rc["glm_reg_scale"] * s[3])) < 1e-6 * abs(s[0])
     # linearity of the objective in the scales (vae_reg_GP.py:410)

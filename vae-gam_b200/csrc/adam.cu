@@ -10,16 +10,17 @@ namespace vg {
 template <typename T>
 __global__ void __launch_bounds__(256)
 adam_kernel(T* __restrict__ p, const T* __restrict__ g, T* __restrict__ m, T* __restrict__ v, long long n,
-            float lr, float b1, float b2, float eps, float gscale, const long long* step_count) {
+            double lr, double b1, double b2, double eps, double gscale, const long long* step_count) {
   const long long t = *step_count + 1;
-  const double bc1 = 1.0 - pow((double)b1, (double)t);
-  const double bc2 = 1.0 - pow((double)b2, (double)t);
-  const T step_size = (T)((double)lr / bc1);
+  const double bc1 = 1.0 - pow(b1, (double)t);
+  const double bc2 = 1.0 - pow(b2, (double)t);
+  const T step_size = (T)(lr / bc1);
   const T inv_sqrt_bc2 = (T)(1.0 / sqrt(bc2));
+  const T c1 = (T)(1.0 - b1), c2 = (T)(1.0 - b2);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const T gi = g[i] * (T)gscale;
-    const T mi = (T)b1 * m[i] + (T)(1.f - b1) * gi;
-    const T vi = (T)b2 * v[i] + (T)(1.f - b2) * gi * gi;
+    const T mi = m[i] + c1 * (gi - m[i]);            // lerp, as torch does
+    const T vi = (T)b2 * v[i] + c2 * gi * gi;
     m[i] = mi;
     v[i] = vi;
     const T denom = sqrt(vi) * inv_sqrt_bc2 + (T)eps;
@@ -34,8 +35,8 @@ __global__ void bump_kernel(long long* c) { *c += 1; }
 using namespace vg;
 
 extern "C" int vg_adam_step(float* p32, const float* g32, float* m32, float* v32, long long n32, double* p64,
-                            const double* g64, double* m64, double* v64, long long n64, float lr, float beta1,
-                            float beta2, float eps, float grad_scale, long long* step_count, void* stream) {
+                            const double* g64, double* m64, double* v64, long long n64, double lr, double beta1,
+                            double beta2, double eps, double grad_scale, long long* step_count, void* stream) {
   VG_CHECK_ARG(step_count, "null step counter");
   cudaStream_t st = as_stream(stream);
   if (n32 > 0) {

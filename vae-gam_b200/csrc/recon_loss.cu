@@ -184,7 +184,12 @@ recon_bwd_kernel(const ReconArgs a, const float* __restrict__ norms, float lam, 
       for (int l = 0; l < 4; ++l) xs[l] = (v0 + l < a.v) ? __ldg(a.x + (size_t)row * a.v + v0 + l) : 0.f;
       float mm[NMAP][4];
 #pragma unroll
-      for (int j = 0; j < NMAP; ++j) { mm[j][0] = m4[j].x; mm[j][1] = m4[j].y; mm[j][2] = m4[j].z; mm[j][3] = m4[j].w; }
+      for (int j = 0; j < NMAP; ++j) {
+        mm[j][0] = m4[j].x; mm[j][1] = m4[j].y; mm[j][2] = m4[j].z; mm[j][3] = m4[j].w;
+#pragma unroll
+        for (int l = 0; l < 4; ++l)
+          if (!(v0 + l < a.v)) mm[j][l] = 0.f;      // row padding may hold anything (even NaN)
+      }
       float xr[4] = {mm[0][0], mm[0][1], mm[0][2], mm[0][3]};
 #pragma unroll
       for (int i = 0; i < KCOV; ++i)

@@ -92,7 +92,7 @@ SIGNATURES = {
     "vg_recon_workspace_bytes": (_SZ, [_I, _LL]),
     "vg_recon_loss_fwd": (_I, [_P, _P, _P, _P, _P, _I, _LL, _P, _P, _P, _P, _P, _SZ, _P]),
     "vg_recon_loss_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _LL, _F, _P, _P, _P, _P, _SZ, _P]),
-    "vg_adam_step": (_I, [_P, _P, _P, _P, _LL, _P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _P, _P]),
+    "vg_adam_step": (_I, [_P, _P, _P, _P, _LL, _P, _P, _P, _P, _LL, _D, _D, _D, _D, _D, _P, _P]),
     "vg_step_workspace_bytes": (_SZ, [C.POINTER(VgStepConfig)]),
     "vg_step_fwd": (_I, [C.POINTER(VgStepConfig), C.POINTER(VgStepIO), _P, _SZ, _P]),
     "vg_step_bwd": (_I, [C.POINTER(VgStepConfig), C.POINTER(VgStepIO), _P, _SZ, _P]),

@@ -247,12 +247,30 @@ class _StepFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         engine, sb = ctx.engine, ctx.sb
-        engine.backward(sb)
         flat = engine.flat
+        # Normal training (`optimizer.zero_grad(); loss.backward()`): every .grad is None and autograd
+        # simply adopts the views returned below — no copies.  If the caller kept gradients from an
+        # earlier backward (accumulation), those ALIAS the flat buffer this call is about to
+        # overwrite, so the new gradient is produced in a scratch copy and autograd adds it.
+        first = flat.params[0]
+        accumulating = first.grad is not None and first.grad.data_ptr() == flat.grad_view(flat.names[0]).data_ptr()
+        if accumulating:
+            keep32, keep64 = flat.grad32.clone(), flat.grad64.clone()
+        engine.backward(sb)
         go = grad_out.reshape(())
         flat.grad32.mul_(go.to(torch.float32))
         flat.grad64.mul_(go.to(torch.float64))
-        grads = tuple(flat.grad_view(n) for n in flat.names)
+        if accumulating:
+            new32, new64 = flat.grad32.clone(), flat.grad64.clone()
+            flat.grad32.copy_(keep32)
+            flat.grad64.copy_(keep64)
+            grads = []
+            for n, p in zip(flat.names, flat.params):
+                dt, off, k = flat.slices[n]
+                grads.append((new32 if dt == torch.float32 else new64)[off:off + k].view(p.shape))
+            grads = tuple(grads)
+        else:
+            grads = tuple(flat.grad_view(n) for n in flat.names)
         return (None, None, None, None, None, None) + grads
 
 
