@@ -245,85 +245,6 @@ gather_kernel(const __grid_constant__ Geom g, const GatherArgs a) {
   }
 }
 
-// Weight gradient: one warp per (tap, co-slice); lanes stride over voxels of a chunk.
-template <int CIN, int COT>
-__global__ void __launch_bounds__(256)
-wgrad_kernel(const __grid_constant__ Geom g, const float* __restrict__ in,
-             const float* __restrict__ dout, const float* __restrict__ in_scale,
-             const float* __restrict__ in_shift, float* dw, float* dbias, int cout_full,
-             int co_splits, long long chunk_items) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int slot = blockIdx.y * (blockDim.x >> 5) + warp;
-  const int tap = slot / co_splits;
-  const int co0 = (slot - tap * co_splits) * COT;
-  const bool do_bias = (tap == 0) && dbias != nullptr;
-  const bool do_w = tap < g.ntaps;
-  if (!do_bias && !do_w) return;
-  Tap tp = g.taps[do_w ? tap : 0];
-
-  float acc[CIN][COT];
-  float bs[COT];
-#pragma unroll
-  for (int i = 0; i < CIN; ++i)
-#pragma unroll
-    for (int j = 0; j < COT; ++j) acc[i][j] = 0.f;
-#pragma unroll
-  for (int j = 0; j < COT; ++j) bs[j] = 0.f;
-
-  const long long per_img = (long long)g.qD * g.qH * g.qW;
-  const long long total = per_img * g.N;
-  const long long beg = (long long)blockIdx.x * chunk_items;
-  const long long end = min(total, beg + chunk_items);
-  const bool affine = in_scale != nullptr;
-  for (long long it = beg + lane; it < end; it += 32) {
-    const int n = (int)(it / per_img);
-    int rem = (int)(it - (long long)n * per_img);
-    const int qw = rem % g.qW; rem /= g.qW;
-    const int qh = rem % g.qH;
-    const int qd = rem / g.qH;
-    const int od = qd * g.sout + g.rD, oh = qh * g.sout + g.rH, ow = qw * g.sout + g.rW;
-    const size_t o = (size_t)n * g.out_img + (((size_t)od * g.outH + oh) * g.outW + ow) * cout_full + co0;
-    float dy[COT];
-    load_vec<COT>(dout + o, dy);
-    if (do_bias) {
-#pragma unroll
-      for (int j = 0; j < COT; ++j) bs[j] += dy[j];
-    }
-    if (!do_w) continue;
-    const int id = qd * g.sin + tp.dd, ih = qh * g.sin + tp.dh, iw = qw * g.sin + tp.dw;
-    if (g.check && (id < 0 || id >= g.inD || ih < 0 || ih >= g.inH || iw < 0 || iw >= g.inW)) continue;
-    float xv[CIN];
-    load_vec<CIN>(in + (size_t)n * g.in_img + (((size_t)id * g.inH + ih) * g.inW + iw) * CIN, xv);
-    if (affine) {
-      const int grp = n / g.group_size;
-#pragma unroll
-      for (int c = 0; c < CIN; ++c)
-        xv[c] = fmaf(xv[c], __ldg(in_scale + grp * CIN + c), __ldg(in_shift + grp * CIN + c));
-    }
-#pragma unroll
-    for (int i = 0; i < CIN; ++i)
-#pragma unroll
-      for (int j = 0; j < COT; ++j) acc[i][j] = fmaf(xv[i], dy[j], acc[i][j]);
-  }
-  if (do_w) {
-#pragma unroll
-    for (int i = 0; i < CIN; ++i)
-#pragma unroll
-      for (int j = 0; j < COT; ++j) {
-        const float r = warp_sum(acc[i][j]);
-        if (lane == ((i * COT + j) & 31))
-          atomicAdd(dw + (size_t)tp.widx * g.wst_t + (size_t)i * g.wst_ci + (size_t)(co0 + j) * g.wst_co, r);
-      }
-  }
-  if (do_bias) {
-#pragma unroll
-    for (int j = 0; j < COT; ++j) {
-      const float r = warp_sum(bs[j]);
-      if (lane == j) atomicAdd(dbias + co0 + j, r);
-    }
-  }
-}
-
 // --------------------------------------------------------------------------- geometry
 static int check_desc(const VgConvDesc* d) {
   VG_CHECK_ARG(d != nullptr, "null descriptor");
@@ -462,41 +383,6 @@ static int launch_gather(int cin, int cout, const Geom& g, const GatherArgs& a, 
   return VG_EINVAL;
 }
 
-template <int CIN, int COT>
-static int launch_wgrad_t(const Geom& g, int cout_full, const float* in, const float* dy,
-                          const float* sc, const float* sh, float* dw, float* dbias, cudaStream_t st) {
-  const int co_splits = cout_full / COT;
-  const int slots = (g.ntaps > 0 ? g.ntaps : 1) * co_splits;
-  const int wpb = 8;
-  const int gy = cdiv(slots, wpb);
-  const long long total = (long long)g.N * g.qD * g.qH * g.qW;
-  int sms = vg_sm_count();
-  long long want_chunks = (long long)sms * 4 / gy;
-  if (want_chunks < 1) want_chunks = 1;
-  long long chunk = (total + want_chunks - 1) / want_chunks;
-  if (chunk < 256) chunk = 256;
-  chunk = (chunk + 31) / 32 * 32;
-  dim3 grid(cdiv(total, chunk), gy);
-  wgrad_kernel<CIN, COT><<<grid, wpb * 32, 0, st>>>(g, in, dy, sc, sh, dw, dbias, cout_full, co_splits, chunk);
-  VG_LAUNCH_CHECK();
-  return VG_OK;
-}
-
-static int launch_wgrad(int cin, int cout, const Geom& g, const float* in, const float* dy, const float* sc,
-                        const float* sh, float* dw, float* dbias, cudaStream_t st) {
-  if (cin == 1 && cout == 8) return launch_wgrad_t<1, 8>(g, 8, in, dy, sc, sh, dw, dbias, st);
-  if (cin == 8 && cout == 1) return launch_wgrad_t<8, 1>(g, 1, in, dy, sc, sh, dw, dbias, st);
-  if (cin == 8 && cout == 8) return launch_wgrad_t<8, 8>(g, 8, in, dy, sc, sh, dw, dbias, st);
-  if (cin == 8 && cout == 16) return launch_wgrad_t<8, 8>(g, 16, in, dy, sc, sh, dw, dbias, st);
-  if (cin == 16 && cout == 8) return launch_wgrad_t<16, 8>(g, 8, in, dy, sc, sh, dw, dbias, st);
-  if (cin == 16 && cout == 16) return launch_wgrad_t<16, 8>(g, 16, in, dy, sc, sh, dw, dbias, st);
-  if (cin == 1 && cout == 1) return launch_wgrad_t<1, 1>(g, 1, in, dy, sc, sh, dw, dbias, st);
-  if (cin == 1 && cout == 16) return launch_wgrad_t<1, 8>(g, 16, in, dy, sc, sh, dw, dbias, st);
-  if (cin == 16 && cout == 1) return launch_wgrad_t<16, 1>(g, 1, in, dy, sc, sh, dw, dbias, st);
-  set_error("unsupported channel pair (%d,%d): channels must be in {1,8,16}", cin, cout);
-  return VG_EINVAL;
-}
-
 }  // namespace vg
 
 using namespace vg;
@@ -533,13 +419,12 @@ extern "C" int vg_conv_dgrad(const VgConvDesc* d, const float* dy, const float* 
   return VG_OK;
 }
 
+int vg_conv_wgrad_tiled(const VgConvDesc* d, const float* x, const float* dy, const float* in_scale,
+                        const float* in_shift, float* dw, float* dbias, cudaStream_t st);   // wgrad.cu
+
 extern "C" int vg_conv_wgrad(const VgConvDesc* d, const float* x, const float* dy, const float* in_scale,
                              const float* in_shift, float* dw, float* dbias, void* stream) {
   VG_TRY(check_desc(d));
   VG_CHECK_ARG(x && dy && dw, "null tensor");
-  Geom gs[8];
-  const int ng = build_geoms(d, 0, gs);
-  for (int i = 0; i < ng; ++i)
-    VG_TRY(launch_wgrad(d->cin, d->cout, gs[i], x, dy, in_scale, in_shift, dw, dbias, as_stream(stream)));
-  return VG_OK;
+  return vg_conv_wgrad_tiled(d, x, dy, in_scale, in_shift, dw, dbias, as_stream(stream));
 }

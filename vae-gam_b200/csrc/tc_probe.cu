@@ -1,0 +1,268 @@
+// Stand-alone probe for the tcgen05 building blocks the implicit-GEMM convolution relies on.
+// One CTA issues bf16 tcgen05.mma (cta_group::1, M=128) from shared-memory descriptors in the
+// NO-SWIZZLE canonical layouts and checks the TMEM accumulator against a CPU product.  It
+// answers, on real hardware, the questions the design depends on:
+//   1. descriptor field semantics (LBO = K-direction / SBO = M-direction core-matrix strides);
+//   2. the "shifted window" trick: A descriptors whose core matrices OVERLAP in shared memory
+//      (LBO = 16 B, SBO = row pitch), i.e. an im2col view of a halo tile without copying;
+//   3. accumulation over several MMAs, N = 16 and N = 8 padding, MN-major operands.
+// Every wait is bounded, so a wrong guess produces a report, never a hang.
+//   build:  make -C vae-gam_b200/csrc tc_probe      run:  vae-gam_b200/csrc/build/tc_probe
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <vector>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(2); } } while (0)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+  return d;                 // layout_type = 0 (no swizzle), base_offset = 0, lbo_mode = 0
+}
+
+__device__ __forceinline__ uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  uint32_t d = 0;
+  d |= 1u << 4;                       // c_format = F32
+  d |= 1u << 7;                       // a_format = BF16
+  d |= 1u << 10;                      // b_format = BF16
+  d |= (uint32_t)(a_mn_major & 1) << 15;
+  d |= (uint32_t)(b_mn_major & 1) << 16;
+  d |= (uint32_t)(N >> 3) << 17;
+  d |= (uint32_t)(M >> 4) << 24;
+  return d;
+}
+
+struct ProbeCfg {
+  int n;               // MMA N (16 or 8.. must be legal for M=128: multiple of 16)
+  int nmma;            // number of K=16 MMAs accumulated
+  // A operand: byte offset of element (row r, k) inside the A buffer = a_row(r) + a_k(k)
+  int a_lbo, a_sbo;    // descriptor fields (bytes)
+  int a_step;          // descriptor start-address advance per MMA (bytes)
+  int a_mn_major;
+  int b_lbo, b_sbo, b_step, b_mn_major;
+};
+
+// out: 128 x n floats; status: 0 ok, 1 mma barrier timeout
+__global__ void __launch_bounds__(128) probe_kernel(const __nv_bfloat16* __restrict__ a_img, int a_bytes,
+                                                    const __nv_bfloat16* __restrict__ b_img, int b_bytes,
+                                                    ProbeCfg cfg, float* out, int* status) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  uint8_t* sa = smem;
+  uint8_t* sb = smem + ((a_bytes + 1023) / 1024) * 1024;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < a_bytes / 2; i += 128) reinterpret_cast<__nv_bfloat16*>(sa)[i] = a_img[i];
+  for (int i = tid; i < b_bytes / 2; i += 128) reinterpret_cast<__nv_bfloat16*>(sb)[i] = b_img[i];
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (MMA)
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" ::"r"(smem_u32(&tmem_base)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t taddr = tmem_base;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc(128, cfg.n, cfg.a_mn_major, cfg.b_mn_major);
+    for (int i = 0; i < cfg.nmma; ++i) {
+      const uint64_t da = make_desc(smem_u32(sa) + i * cfg.a_step, cfg.a_lbo, cfg.a_sbo);
+      const uint64_t db = make_desc(smem_u32(sb) + i * cfg.b_step, cfg.b_lbo, cfg.b_sbo);
+      const uint32_t acc = i > 0 ? 1u : 0u;
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+          "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(taddr),
+          "l"(da), "l"(db), "r"(idesc), "r"(acc)
+          : "memory");
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar))
+                 : "memory");
+  }
+  // bounded wait on phase 0
+  uint32_t done = 0;
+  for (int it = 0; it < (1 << 20) && !done; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(smem_u32(&bar)), "r"(0u)
+        : "memory");
+  }
+  if (!done) {
+    if (tid == 0) *status = 1;
+  } else {
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    // warp w reads TMEM lanes 32w..32w+31; 8 columns at a time
+    for (int c0 = 0; c0 < cfg.n; c0 += 8) {
+      uint32_t v[8];
+      const uint32_t addr = taddr + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                   : "r"(addr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      for (int j = 0; j < 8; ++j) out[(warp * 32 + lane) * cfg.n + c0 + j] = __uint_as_float(v[j]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(taddr));
+}
+
+static float bf(float x) { return __bfloat162float(__float2bfloat16(x)); }
+
+struct Case {
+  const char* name;
+  ProbeCfg cfg;
+  std::vector<__nv_bfloat16> a_img, b_img;
+  std::vector<float> ref;   // 128 x n
+};
+
+static float frand() { return (float)(rand() % 2001 - 1000) / 1000.f; }
+
+// Dense K-major operands: logical A (128 x K), B (n x K); image written with the canonical
+// no-swizzle layout: off(r,k) = (r/8)*SBO + (k/8)*LBO + (r%8)*16 + (k%8)*2 bytes.
+static Case dense_case(const char* name, int n, int nmma, int lbo_a, int sbo_a, bool swap_fields) {
+  const int K = 16 * nmma;
+  Case c; c.name = name;
+  std::vector<float> A(128 * K), B(n * K);
+  for (auto& v : A) v = bf(frand());
+  for (auto& v : B) v = bf(frand());
+  // per-MMA A block: 2 K-chunks.  Place K-chunks contiguously: LBO = 128 B, SBO = 128 * (K/8) B.
+  const int a_lbo = lbo_a, a_sbo = sbo_a;
+  const int a_bytes = 16 * a_sbo;                 // 16 row-groups
+  const int b_lbo = 128, b_sbo = 128 * (K / 8);
+  const int b_bytes = (n / 8) * b_sbo;
+  c.a_img.assign(a_bytes / 2, __float2bfloat16(0.f));
+  c.b_img.assign(b_bytes / 2, __float2bfloat16(0.f));
+  for (int r = 0; r < 128; ++r)
+    for (int k = 0; k < K; ++k)
+      c.a_img[((r / 8) * a_sbo + (k / 8) * a_lbo + (r % 8) * 16 + (k % 8) * 2) / 2] = __float2bfloat16(A[r * K + k]);
+  for (int r = 0; r < n; ++r)
+    for (int k = 0; k < K; ++k)
+      c.b_img[((r / 8) * b_sbo + (k / 8) * b_lbo + (r % 8) * 16 + (k % 8) * 2) / 2] = __float2bfloat16(B[r * K + k]);
+  c.ref.assign(128 * n, 0.f);
+  for (int r = 0; r < 128; ++r)
+    for (int j = 0; j < n; ++j) {
+      double s = 0;
+      for (int k = 0; k < K; ++k) s += (double)A[r * K + k] * B[j * K + k];
+      c.ref[r * n + j] = (float)s;
+    }
+  ProbeCfg& p = c.cfg;
+  p.n = n; p.nmma = nmma;
+  p.a_lbo = swap_fields ? a_sbo : a_lbo; p.a_sbo = swap_fields ? a_lbo : a_sbo; p.a_step = 2 * a_lbo; p.a_mn_major = 0;
+  p.b_lbo = swap_fields ? b_sbo : b_lbo; p.b_sbo = swap_fields ? b_lbo : b_sbo; p.b_step = 2 * b_lbo; p.b_mn_major = 0;
+  return c;
+}
+
+// Shifted-window (implicit im2col) case: a channels-last bf16 halo tile [H+2][W+2][8ch] for an
+// output tile of 16 (h) x 8 (w) voxels, 3x3 taps in the plane, 8 input channels, n output channels.
+// A row m = (h, w) = (m/8, m%8); for tap (kh, kw) the K-chunk is the 8 channels of voxel (h+kh, w+kw).
+// MMA i covers taps (kh, kw=0) and (kh, kw=1) via LBO = 16 B (overlapping core matrices), i = kh;
+// MMA 3+kh covers tap (kh, 2) paired with a zero-weight dummy (kh, 3) -> needs one spare column.
+static Case window_case(const char* name, int n) {
+  const int H = 16, W = 8, PW = W + 3 /* halo 2 + 1 spare */, PH = H + 2, C = 8;
+  Case c; c.name = name;
+  std::vector<float> X(PH * PW * C), Wt(9 * C * n);
+  for (auto& v : X) v = bf(frand());
+  for (auto& v : Wt) v = bf(frand());
+  const int pitch = PW * C * 2;                    // bytes per tile row
+  c.a_img.resize(PH * PW * C);
+  for (size_t i = 0; i < X.size(); ++i) c.a_img[i] = __float2bfloat16(X[i]);
+  // B blocks: 6 MMAs, each (n x 16) K-major canonical: LBO = 128, SBO = 256 -> block bytes = n/8*256
+  const int b_blk = (n / 8) * 256;
+  c.b_img.assign(6 * b_blk / 2, __float2bfloat16(0.f));
+  auto put_b = [&](int mma, int kk /*0..15*/, int j, float v) {
+    c.b_img[(mma * b_blk + (j / 8) * 256 + (kk / 8) * 128 + (j % 8) * 16 + (kk % 8) * 2) / 2] = __float2bfloat16(v);
+  };
+  for (int kh = 0; kh < 3; ++kh)
+    for (int kw = 0; kw < 3; ++kw)
+      for (int ci = 0; ci < C; ++ci)
+        for (int j = 0; j < n; ++j) {
+          const float w = Wt[((kh * 3 + kw) * C + ci) * n + j];
+          if (kw < 2) put_b(kh, kw * 8 + ci, j, w);
+          else put_b(3 + kh, ci, j, w);              // second K-chunk (dummy tap) stays zero
+        }
+  c.ref.assign(128 * n, 0.f);
+  for (int m = 0; m < 128; ++m)
+    for (int j = 0; j < n; ++j) {
+      double s = 0;
+      const int h = m / 8, w = m % 8;
+      for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw)
+          for (int ci = 0; ci < C; ++ci)
+            s += (double)X[((h + kh) * PW + (w + kw)) * C + ci] * Wt[((kh * 3 + kw) * C + ci) * n + j];
+      c.ref[m * n + j] = (float)s;
+    }
+  ProbeCfg& p = c.cfg;
+  p.n = n; p.nmma = 6;
+  p.a_lbo = 16; p.a_sbo = pitch; p.a_mn_major = 0;
+  p.a_step = -1;   // per-MMA start offsets are irregular: handled by the launcher through a table
+  p.b_lbo = 128; p.b_sbo = 256; p.b_step = b_blk; p.b_mn_major = 0;
+  return c;
+}
+
+int main() {
+  srand(1);
+  std::vector<Case> cases;
+  cases.push_back(dense_case("dense K-major  N=16 K=16  (LBO=K-dir 128B, SBO=M-dir 256B)", 16, 1, 128, 256, false));
+  cases.push_back(dense_case("dense K-major  N=16 K=16  fields swapped (expect mismatch)", 16, 1, 128, 256, true));
+  cases.push_back(dense_case("dense K-major  N=16 K=64  4 accumulated MMAs", 16, 4, 128, 1024, false));
+  cases.push_back(dense_case("dense K-major  N=32 K=32", 32, 2, 128, 512, false));
+  cases.push_back(dense_case("dense K-major  N=16 K=16  padded SBO=320B (row-group pitch != 256)", 16, 1, 128, 320, false));
+  cases.push_back(window_case("shifted-window 3x3 taps, 8ch, N=16 (overlapping core matrices)", 16));
+  int fails = 0;
+  for (auto& c : cases) {
+    __nv_bfloat16 *da, *db; float* dout; int* dstat;
+    const int a_bytes = (int)c.a_img.size() * 2, b_bytes = (int)c.b_img.size() * 2;
+    CK(cudaMalloc(&da, a_bytes)); CK(cudaMalloc(&db, b_bytes));
+    CK(cudaMalloc(&dout, 128 * c.cfg.n * 4)); CK(cudaMalloc(&dstat, 4));
+    CK(cudaMemcpy(da, c.a_img.data(), a_bytes, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(db, c.b_img.data(), b_bytes, cudaMemcpyHostToDevice));
+    CK(cudaMemset(dout, 0, 128 * c.cfg.n * 4)); CK(cudaMemset(dstat, 0, 4));
+    const int smem = ((a_bytes + 1023) / 1024) * 1024 + b_bytes + 1024;
+    CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (c.cfg.a_step >= 0) {
+      probe_kernel<<<1, 128, smem>>>(da, a_bytes, db, b_bytes, c.cfg, dout, dstat);
+      CK(cudaDeviceSynchronize());
+    } else {
+      // window case: run the 6 MMAs as 6 launches accumulating on the host (start offsets are a table)
+      const int PW = 11, C = 8, pitch = PW * C * 2;
+      std::vector<float> acc(128 * c.cfg.n, 0.f), tmp(128 * c.cfg.n);
+      for (int i = 0; i < 6; ++i) {
+        ProbeCfg p = c.cfg;
+        p.nmma = 1;
+        const int kh = i % 3, kw = i < 3 ? 0 : 2;
+        const int a_off = kh * pitch + kw * C * 2, b_off = i * p.b_step;
+        probe_kernel<<<1, 128, smem>>>(da + a_off / 2, a_bytes - a_off, db + b_off / 2, b_bytes - b_off, p, dout, dstat);
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(tmp.data(), dout, tmp.size() * 4, cudaMemcpyDeviceToHost));
+        for (size_t j = 0; j < acc.size(); ++j) acc[j] += tmp[j];
+      }
+      CK(cudaMemcpy(dout, acc.data(), acc.size() * 4, cudaMemcpyHostToDevice));
+    }
+    std::vector<float> got(128 * c.cfg.n);
+    int stat = 0;
+    CK(cudaMemcpy(got.data(), dout, got.size() * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&stat, dstat, 4, cudaMemcpyDeviceToHost));
+    double maxerr = 0, maxref = 0;
+    for (size_t i = 0; i < got.size(); ++i) { maxerr = fmax(maxerr, fabs(got[i] - c.ref[i])); maxref = fmax(maxref, fabs(c.ref[i])); }
+    const bool ok = stat == 0 && maxerr < 1e-3 * fmax(1.0, maxref);
+    printf("%-75s status=%d max|err|=%.3e max|ref|=%.2f %s\n", c.name, stat, maxerr, maxref, ok ? "OK" : "MISMATCH");
+    if (!ok) ++fails;
+    cudaFree(da); cudaFree(db); cudaFree(dout); cudaFree(dstat);
+  }
+  printf("tc_probe: %d case(s) mismatched (the 'fields swapped' case is expected to)\n", fails);
+  return 0;
+}
