@@ -73,6 +73,15 @@ typedef struct VgConvDesc {
   int64_t y_img_stride;    /* floats between consecutive images of y / dy; 0 = dense (D*H*W*cout) */
 } VgConvDesc;
 
+/* Arithmetic of the convolution forward / data-gradient kernels:
+ *   1 (default): bf16 operands on the tcgen05 tensor cores with fp32 accumulation in TMEM, for
+ *      every geometry the implicit-GEMM kernel covers (unit input stride, 8 or 16 input
+ *      channels); the remaining layers use the fp32 kernel;
+ *   0: fp32 CUDA-core kernels everywhere ("check mode", 1e-5 parity with PyTorch fp32).
+ * Initial value from the environment variable VAEGAM_CONV_MODE ("0"/"fp32" or "1"). */
+int vg_set_conv_mode(int mode);
+int vg_get_conv_mode(void);
+
 /* y = act(conv(x * in_scale[g,ci] + in_shift[g,ci]) + bias); zero padding is applied
  * AFTER the affine (it pads the normalised tensor).  in_scale/in_shift: (n/group_size, cin)
  * or NULL.  out_stats: (n/group_size, cout, 2) doubles, ACCUMULATED with sum(y), sum(y^2)

@@ -62,6 +62,91 @@ def torch_layer(spec, x, w, b):
     return F.conv3d(x, w, b, stride=s)
 
 
+@pytest.fixture(autouse=True)
+def _fp32_mode_by_default(lib):
+    """Tight fp32 parity runs on the CUDA-core kernels; tensor-core tests opt in explicitly."""
+    lib.vg_set_conv_mode(0)
+    yield
+    lib.vg_set_conv_mode(0)
+
+
+def bf16r(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+@pytest.mark.parametrize("name", list(LAYERS))
+def test_conv_tensor_core_path(lib, name):
+    """tcgen05 implicit-GEMM kernels (mode 1).  The kernel rounds the (BN-folded) input and the
+    weights to bf16 and accumulates in fp32, so a PyTorch fp32 reference fed the SAME rounded
+    operands must agree to fp32 accumulation error; layers the tensor-core kernel does not cover
+    (1 input channel, strided gathers) fall back to the fp32 kernel and still have to pass."""
+    native = nat()
+    spec = LAYERS[name]
+    tr, cin, cout, k, s, in_, pad, opad = spec
+    N, group = 4, 2
+    dev = "cuda"
+    gen = torch.Generator(device=dev).manual_seed(7 + sum(map(ord, name)))
+    x = torch.randn(N, cin, *in_, device=dev, generator=gen)
+    wshape = (cin, cout, *k) if tr else (cout, cin, *k)
+    w = torch.randn(*wshape, device=dev, generator=gen) * 0.2
+    b = torch.randn(cout, device=dev, generator=gen)
+    scale = torch.rand(N // group, cin, device=dev, generator=gen) + 0.5
+    shift = torch.randn(N // group, cin, device=dev, generator=gen)
+    d = native.conv_desc(tr, cin, cout, k, s, in_, N, group, pad, opad)
+    lib.vg_set_conv_mode(1)
+    assert lib.vg_get_conv_mode() == 1
+    xa = torch.addcmul(shift.repeat_interleave(group, 0)[:, :, None, None, None], x,
+                       scale.repeat_interleave(group, 0)[:, :, None, None, None])       # fma, as the kernel does
+    x_cl = to_cl(x)
+    y = torch.empty(N, *tuple(d.out), cout, device=dev)
+    stats = torch.zeros(N // group, cout, 2, dtype=torch.float64, device=dev)
+    st = native.stream_ptr()
+    native.check(lib.vg_conv_fwd(C.byref(d), native.ptr(x_cl), native.ptr(w), native.ptr(b), native.ptr(scale),
+                                 native.ptr(shift), native.ptr(y), native.ACT_RELU, native.ptr(stats), st))
+    torch.cuda.synchronize()
+    y_exact = torch.relu(torch_layer(spec, xa, w, b))
+    y_round = torch.relu(torch_layer(spec, bf16r(xa), bf16r(w), b))
+    err_round, err_exact = rel_err(from_cl(y).cpu(), y_round.cpu()), rel_err(from_cl(y).cpu(), y_exact.cpu())
+    assert min(err_round, err_exact) < 2e-5, (err_round, err_exact)     # exact operands when the fp32 kernel ran
+    assert err_exact < 1e-2                                             # and bf16 stays within 1e-2 of fp32
+    ref_stats = torch.stack([from_cl(y).permute(0, 1, 2, 3, 4).double().reshape(N // group, group, cout, -1).sum((1, 3)),
+                             (from_cl(y).double() ** 2).reshape(N // group, group, cout, -1).sum((1, 3))], -1)
+    assert rel_err(stats.cpu(), ref_stats.cpu()) < 1e-5
+    # data gradient: dy and w rounded
+    dy = torch.randn(N, cout, *tuple(d.out), device=dev, generator=gen)
+    xg = xa.clone().requires_grad_(True)
+    torch_layer(spec, xg, bf16r(w), b).backward(bf16r(dy))
+    gx_round = xg.grad.clone()
+    xg.grad = None
+    torch_layer(spec, xg, w, b).backward(dy)
+    gx_exact = xg.grad
+    dy_cl = to_cl(dy)
+    dx = torch.empty_like(x_cl)
+    act = torch.randn(N, cin, *in_, device=dev, generator=gen)
+    act_cl = to_cl(act)
+    native.check(lib.vg_conv_dgrad(C.byref(d), native.ptr(dy_cl), native.ptr(w), native.ptr(dx), native.ptr(act_cl),
+                                   None, None, None, None, st))
+    torch.cuda.synchronize()
+    mask = (act > 0)
+    e_r, e_e = rel_err(from_cl(dx).cpu(), (gx_round * mask).cpu()), rel_err(from_cl(dx).cpu(), (gx_exact * mask).cpu())
+    assert min(e_r, e_e) < 2e-5, (e_r, e_e)
+    assert e_e < 1e-2
+    # BatchNorm-backward sums epilogue
+    istd = torch.rand(N // group, cin, device=dev, generator=gen) + 0.5
+    mistd = torch.randn(N // group, cin, device=dev, generator=gen)
+    sums = torch.zeros(N // group, cin, 2, dtype=torch.float64, device=dev)
+    dxb = torch.empty_like(x_cl)
+    native.check(lib.vg_conv_dgrad(C.byref(d), native.ptr(dy_cl), native.ptr(w), native.ptr(dxb), None,
+                                   native.ptr(act_cl), native.ptr(istd), native.ptr(mistd), native.ptr(sums), st))
+    torch.cuda.synchronize()
+    got = from_cl(dxb)
+    xh = act * istd.repeat_interleave(group, 0)[:, :, None, None, None] - mistd.repeat_interleave(group, 0)[:, :, None, None, None]
+    ref_sums = torch.stack([got.double().reshape(N // group, group, cin, -1).sum((1, 3)),
+                            (got.double() * xh.double()).reshape(N // group, group, cin, -1).sum((1, 3))], -1)
+    assert rel_err(sums.cpu(), ref_sums.cpu()) < 2e-5
+    assert min(rel_err(got.cpu(), gx_round.cpu()), rel_err(got.cpu(), gx_exact.cpu())) < 2e-5
+
+
 @pytest.mark.parametrize("name", list(LAYERS))
 def test_conv_forward_dgrad_wgrad(lib, name):
     native = nat()

@@ -15,45 +15,12 @@
 // BatchNorm (batch statistics, per image group) never runs as its own pass: `pro` applies
 // scale/shift to in-range taps only (zero padding pads the NORMALISED tensor) and `epi`
 // accumulates the next layer's statistics, or the BatchNorm-backward sums.
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "conv_geom.cuh"
 
 namespace vg {
-
-constexpr int kMaxTaps = 48;
-
-struct Tap {
-  int8_t dd, dh, dw, pad_;
-  int32_t widx;
-};
-
-struct Geom {
-  int N, group_size;
-  int inD, inH, inW;
-  int outD, outH, outW;
-  int qD, qH, qW;
-  int sin, sout;
-  int rD, rH, rW;
-  int ntaps, check;
-  int wst_t, wst_ci, wst_co;
-  long long in_img, out_img;   // floats between images of the tensor read / written
-  Tap taps[kMaxTaps];
-};
-
-struct GatherArgs {
-  const float* in;
-  const float* w;
-  const float* bias;      // (COUT) or null
-  const float* in_scale;  // (groups, CIN) or null
-  const float* in_shift;
-  float* out;             // null: statistics only
-  int act;
-  double* stats;          // (groups, COUT, 2): sum y, sum y^2   (forward)
-  const float* aux;       // saved tensor at the output positions (backward)
-  int aux_mode;           // 0 none, 1 relu mask, 2 batch-norm backward sums
-  const float* aux_istd;  // (groups, COUT)
-  const float* aux_mistd;
-  double* aux_sums;       // (groups, COUT, 2): sum dy, sum dy*xhat
-};
 
 template <int C>
 __device__ __forceinline__ void load_vec(const float* __restrict__ p, float (&v)[C]) {
@@ -369,7 +336,17 @@ static int launch_gather_t(const Geom& g, const GatherArgs& a, cudaStream_t st) 
   return VG_OK;
 }
 
+static int g_conv_mode = -1;
+int conv_mode() {
+  if (g_conv_mode < 0) {
+    const char* e = getenv("VAEGAM_CONV_MODE");
+    g_conv_mode = (e && (e[0] == '0' || e[0] == 'f')) ? 0 : 1;     // "0" / "fp32" -> CUDA cores
+  }
+  return g_conv_mode;
+}
+
 static int launch_gather(int cin, int cout, const Geom& g, const GatherArgs& a, cudaStream_t st) {
+  if (conv_mode() == 1 && tc_supported(cin, cout, g)) return launch_tc_gather(cin, cout, g, a, st);
   if (cin == 1 && cout == 8) return launch_gather_t<1, 8, 4>(g, a, st);
   if (cin == 8 && cout == 1) return launch_gather_t<8, 1, 4>(g, a, st);
   if (cin == 8 && cout == 8) return launch_gather_t<8, 8, 4>(g, a, st);
@@ -386,6 +363,13 @@ static int launch_gather(int cin, int cout, const Geom& g, const GatherArgs& a, 
 }  // namespace vg
 
 using namespace vg;
+
+extern "C" int vg_set_conv_mode(int mode) {
+  VG_CHECK_ARG(mode == 0 || mode == 1, "mode must be 0 (fp32 CUDA cores) or 1 (bf16 tcgen05)");
+  g_conv_mode = mode;
+  return VG_OK;
+}
+extern "C" int vg_get_conv_mode(void) { return conv_mode(); }
 
 extern "C" int vg_conv_fwd(const VgConvDesc* d, const float* x, const float* w, const float* bias,
                            const float* in_scale, const float* in_shift, float* y, int act,

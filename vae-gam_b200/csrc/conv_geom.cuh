@@ -1,0 +1,50 @@
+// Geometry / argument structs shared by the CUDA-core gather (conv.cu) and the tcgen05
+// implicit-GEMM gather (tc_conv.cu).
+#pragma once
+#include "common.cuh"
+
+namespace vg {
+
+constexpr int kMaxTaps = 48;
+
+struct Tap {
+  int8_t dd, dh, dw, pad_;
+  int32_t widx;
+};
+
+struct Geom {
+  int N, group_size;
+  int inD, inH, inW;
+  int outD, outH, outW;
+  int qD, qH, qW;
+  int sin, sout;
+  int rD, rH, rW;
+  int ntaps, check;
+  int wst_t, wst_ci, wst_co;
+  long long in_img, out_img;   // floats between images of the tensor read / written
+  Tap taps[kMaxTaps];
+};
+
+struct GatherArgs {
+  const float* in;
+  const float* w;
+  const float* bias;      // (COUT) or null
+  const float* in_scale;  // (groups, CIN) or null
+  const float* in_shift;
+  float* out;             // null: statistics only
+  int act;
+  double* stats;          // (groups, COUT, 2): sum y, sum y^2   (forward)
+  const float* aux;       // saved tensor at the output positions (backward)
+  int aux_mode;           // 0 none, 1 relu mask, 2 batch-norm backward sums
+  const float* aux_istd;  // (groups, COUT)
+  const float* aux_mistd;
+  double* aux_sums;       // (groups, COUT, 2): sum dy, sum dy*xhat
+};
+
+
+// tc_conv.cu
+bool tc_supported(int cin, int cout, const Geom& g);
+int launch_tc_gather(int cin, int cout, const Geom& g, const GatherArgs& a, cudaStream_t st);
+int conv_mode();   // 0: fp32 CUDA cores ("check mode"), 1: bf16 tcgen05 where the geometry allows
+
+}  // namespace vg

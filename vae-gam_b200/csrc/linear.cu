@@ -19,6 +19,7 @@ struct GemmArgs {
   int act;
   int accumulate;                   // C += result (atomic when split-k > 1)
   int ksplit;                       // gridDim.z
+  float* rowsum;                    // (m) += sum_k A_eff(m,k)   (bias gradient, fused into the dW GEMM) or null
 };
 
 __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs a) {
@@ -31,6 +32,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs a) {
   const int kbeg = blockIdx.z * kper;
   const int kend = min(a.k, kbeg + kper);
   float acc[4][4];
+  float rs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -64,6 +66,15 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs a) {
       sB[kk][nn] = v;
     }
     __syncthreads();
+    if (a.rowsum && blockIdx.x == 0 && tx == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float s = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < TK; ++kk) s += sA[kk][ty * 4 + i];
+        rs[i] += s;
+      }
+    }
 #pragma unroll
     for (int kk = 0; kk < TK; ++kk) {
       float av[4], bv[4];
@@ -77,6 +88,13 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs a) {
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
     __syncthreads();
+  }
+  if (a.rowsum && blockIdx.x == 0 && tx == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int gm = m0 + ty * 4 + i;
+      if (gm < a.m) atomicAdd(a.rowsum + gm, rs[i]);
+    }
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -114,6 +132,25 @@ __global__ void colsum_kernel(const float* __restrict__ dy, const float* __restr
   db[col] += s;
 }
 
+__global__ void bias_act_kernel(float* __restrict__ y, const float* __restrict__ bias, int m, int n, int act) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m * n) return;
+  float v = y[i] + (bias ? __ldg(bias + i % n) : 0.f);
+  if (act == VG_ACT_RELU) v = fmaxf(v, 0.f);
+  else if (act == VG_ACT_SIGMOID) v = 1.f / (1.f + __expf(-v));
+  y[i] = v;
+}
+
+// split the reduction when the output grid alone cannot fill the machine
+static int pick_ksplit(int m, int n, int k) {
+  const int blocks = cdiv(n, TN) * cdiv(m, TM);
+  if (blocks >= 64 || k < 512) return 1;
+  int s = vg_sm_count() / blocks;
+  const int maxs = k / 128;
+  if (s > maxs) s = maxs;
+  return s < 1 ? 1 : s;
+}
+
 static int gemm(GemmArgs a, cudaStream_t st) {
   if (a.ksplit < 1) a.ksplit = 1;
   dim3 grid(cdiv(a.n, TN), cdiv(a.m, TM), a.ksplit);
@@ -133,8 +170,18 @@ extern "C" int vg_linear_fwd(const float* x, const float* w, const float* bias, 
   a.A = x; a.as_m = k; a.as_k = 1;
   a.B = w; a.bs_k = 1; a.bs_n = k;
   a.C = y; a.cs_m = n; a.cs_n = 1;
-  a.bias = bias; a.m = m; a.n = n; a.k = k; a.act = act; a.ksplit = 1;
-  return gemm(a, as_stream(stream));
+  a.m = m; a.n = n; a.k = k;
+  a.ksplit = pick_ksplit(m, n, k);
+  cudaStream_t st = as_stream(stream);
+  if (a.ksplit == 1) {
+    a.bias = bias; a.act = act;
+    return gemm(a, st);
+  }
+  VG_CUDA(cudaMemsetAsync(y, 0, (size_t)m * n * sizeof(float), st));
+  VG_TRY(gemm(a, st));
+  bias_act_kernel<<<cdiv((long long)m * n, 256), 256, 0, st>>>(y, bias, m, n, act);
+  VG_LAUNCH_CHECK();
+  return VG_OK;
 }
 
 extern "C" int vg_linear_bwd(const float* dy, const float* relu_out, const float* x, const float* w, float* dx,
@@ -146,7 +193,9 @@ extern "C" int vg_linear_bwd(const float* dy, const float* relu_out, const float
     a.A = dy; a.MA = relu_out; a.as_m = n; a.as_k = 1;
     a.B = w; a.bs_k = k; a.bs_n = 1;
     a.C = dx; a.cs_m = k; a.cs_n = 1;
-    a.m = m; a.n = k; a.k = n; a.ksplit = 1;
+    a.m = m; a.n = k; a.k = n;
+    a.ksplit = pick_ksplit(m, k, n);
+    if (a.ksplit > 1) VG_CUDA(cudaMemsetAsync(dx, 0, (size_t)m * k * sizeof(float), st));
     VG_TRY(gemm(a, st));
   }
   if (dw) {  // dw (n,k) += dYm^T (n,m) @ X (m,k)
@@ -155,9 +204,9 @@ extern "C" int vg_linear_bwd(const float* dy, const float* relu_out, const float
     a.B = x; a.bs_k = k; a.bs_n = 1;
     a.C = dw; a.cs_m = k; a.cs_n = 1;
     a.m = n; a.n = k; a.k = m; a.accumulate = 1; a.ksplit = 1;
+    a.rowsum = db;                 // db (n) += sum_m dYm(m, n): row sums of this GEMM's A operand
     VG_TRY(gemm(a, st));
-  }
-  if (db) {
+  } else if (db) {
     colsum_kernel<<<cdiv(n, 128), 128, 0, st>>>(dy, relu_out, m, n, db);
     VG_LAUNCH_CHECK();
   }
