@@ -66,12 +66,14 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t
 
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
-  while (!done) {
+  // bounded: a tensor-core operation that never completes must surface as an error, not a hang
+  for (int spin = 0; !done; ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
         : "=r"(done)
         : "r"(bar), "r"(parity)
         : "memory");
+    if (!done && spin > (1 << 22)) asm volatile("trap;");
   }
 }
 
