@@ -118,6 +118,44 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def fused_loss_roofline(device, B=128, iters=20):
+    """The fused reconstruction/likelihood/GLM pass timed alone at B=128 (maps 324 MB, larger than
+    the 126 MB L2, so every launch streams from HBM): algorithmic bytes / CUDA-event time."""
+    import ctypes as C
+    from vaegam import native
+    lib = native.load()
+    VP = native.VP
+    g = torch.Generator(device=device).manual_seed(0)
+    maps = torch.rand(9, B, VP, device=device, generator=g)
+    gains = torch.randn(8, B, device=device, generator=g)
+    x = torch.rand(B, V, device=device, generator=g)
+    eps = torch.full((VP,), -2.3, device=device)
+    glm = torch.rand(8, VP, device=device, generator=g)
+    logp = torch.empty(B, device=device); norms = torch.empty(8, B, device=device)
+    dpre = torch.empty(9, B, VP, device=device); dg = torch.empty(8, B, device=device); deps = torch.empty(VP, device=device)
+    nbytes = int(lib.vg_recon_workspace_bytes(B, V)); ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    st = native.stream_ptr()
+    fwd = lambda: native.check(lib.vg_recon_loss_fwd(native.ptr(maps), native.ptr(gains), native.ptr(x), native.ptr(eps),
+                                                     native.ptr(glm), B, V, native.ptr(logp), native.ptr(norms), None, None,
+                                                     native.ptr(ws), nbytes, st))
+    bwd = lambda: native.check(lib.vg_recon_loss_bwd(native.ptr(maps), native.ptr(gains), native.ptr(x), native.ptr(eps),
+                                                     native.ptr(glm), native.ptr(norms), B, V, 1.0, native.ptr(dpre),
+                                                     native.ptr(dg), native.ptr(deps), native.ptr(ws), nbytes, st))
+    out = {}
+    for name, fn, nb in (("fwd", fwd, 4.0 * (10 * B * V + 9 * V)), ("bwd", bwd, 4.0 * (19 * B * V + 10 * V))):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        out[name] = {"ms": round(ms, 4), "gbs": round(nb / (ms * 1e-3) / 1e9, 1), "bytes": nb}
+    return out
+
+
 def make_cohort_tensors(rank, device):
     from vaegam import synthetic as syn
     coh = syn.make_cohort(N_SUBJECTS, "checker", seed=rank)
@@ -338,6 +376,8 @@ def main():
                     "tensor_frac": round(top["gflops"] / 1e3 / tf_peak, 5)}
         rl = [r for r in rows if r["op"].startswith("recon_loss")]
         kernels["fused_loss"] = [{"op": r["op"], "gbs": r.get("gbs"), "frac_hbm": round(r.get("gbs", 0) / hbm_peak, 4)} for r in rl]
+        fl = fused_loss_roofline(device)
+        kernels["fused_loss_b128_alone"] = {k: dict(v, frac_hbm=round(v["gbs"] / hbm_peak, 4)) for k, v in fl.items()}
 
     if rank != 0:
         if world > 1:

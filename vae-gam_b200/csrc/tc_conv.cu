@@ -36,6 +36,7 @@ struct TcPlan {
   int span_d, span_h, span_w;  // largest - smallest
   int PH, PW;                  // staged box (voxels)
   int NP;                      // ring slots
+  int dchunk, nchunks;         // q planes per CTA, CTAs per column
   int8_t dd[TC_MAX_MMA], dh[TC_MAX_MMA], dw[TC_MAX_MMA];   // offsets relative to lo_*
   int8_t t0[TC_MAX_MMA], t1[TC_MAX_MMA];                   // tap ids of K-chunk 0 / 1 (-1 = zero weights)
 };
@@ -149,7 +150,9 @@ tc_gather_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __gri
 
   // ---- this CTA's column: image n, tile (th, tw), all d planes of the q grid
   const int tilesW = (g.qW + TC_TW - 1) / TC_TW, tilesH = (g.qH + TC_TH - 1) / TC_TH;
-  const int col = blockIdx.x;
+  const int col = blockIdx.x / pl.nchunks;
+  const int qd_beg = (blockIdx.x - col * pl.nchunks) * pl.dchunk;
+  const int qd_end = min(g.qD, qd_beg + pl.dchunk);
   const int n = col / (tilesH * tilesW);
   const int trem = col - n * (tilesH * tilesW);
   const int h0 = (trem / tilesW) * TC_TH, w0 = (trem % tilesW) * TC_TW;
@@ -158,24 +161,50 @@ tc_gather_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __gri
 
   float sc[CIN], sh[CIN];
   const bool affine = a.in_scale != nullptr;
-  // each thread stages fixed (voxel, group) slots of every plane: precompute them
-  const int per_plane = pl.PH * pl.PW;
-
-  auto stage_plane = [&](int rel) {     // rel = plane index relative to lo_d (0 .. qD-1+span_d)
-    const int gd = rel + pl.lo_d;       // input plane (sin == 1)
-    uint8_t* slot = tiles + (size_t)(rel % pl.NP) * slot_bytes;
-    const bool d_ok = gd >= 0 && gd < g.inD;
-    for (int v = tid; v < per_plane; v += blockDim.x) {
+  // each thread stages at most two fixed voxels of every plane (PH*PW <= 198 <= 2*128): their
+  // in-plane global offset (or -1 outside the grid / unused) and shared-memory offset are fixed
+  // for the whole column, so only the plane base moves in the loop.
+  int goff[2], soff[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int v = tid + k * 128;
+    goff[k] = -1;
+    soff[k] = v * 16;
+    if (v < pl.PH * pl.PW) {
       const int i = v / pl.PW, j = v - i * pl.PW;
       const int gh = h0 + pl.lo_h + i, gw = w0 + pl.lo_w + j;
-      const bool ok = d_ok && gh >= 0 && gh < g.inH && gw >= 0 && gw < g.inW;
-      const float* p = in_n + (((size_t)gd * g.inH + gh) * g.inW + gw) * CIN;
+      if (gh >= 0 && gh < g.inH && gw >= 0 && gw < g.inW) goff[k] = (gh * g.inW + gw) * CIN;
+      else goff[k] = -2;                         // inside the staged box but outside the grid: store zeros
+    }
+  }
+  const size_t plane_floats = (size_t)g.inH * g.inW * CIN;
+  float4 pre[2][2 * NG];                          // prefetch registers: loads of the NEXT plane stay in flight
+  bool pre_ok[2];
+
+  auto load_plane = [&](int rel) {                // rel = plane index relative to lo_d; issues the global loads
+    const int gd = rel + pl.lo_d;                 // input plane (unit input stride)
+    const bool d_ok = gd >= 0 && gd < g.inD;
+    const float* base = in_n + (size_t)(d_ok ? gd : 0) * plane_floats;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      pre_ok[k] = d_ok && goff[k] >= 0;
+      if (pre_ok[k]) {
+        const float4* p = reinterpret_cast<const float4*>(base + goff[k]);
+#pragma unroll
+        for (int q = 0; q < 2 * NG; ++q) pre[k][q] = __ldg(p + q);
+      }
+    }
+  };
+  auto store_plane = [&](int rel) {               // fold + convert the prefetched voxels into the ring slot
+    uint8_t* slot = tiles + (size_t)(rel % pl.NP) * slot_bytes;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (goff[k] == -1) continue;
 #pragma unroll
       for (int gi = 0; gi < NG; ++gi) {
         uint4 pk = make_uint4(0u, 0u, 0u, 0u);
-        if (ok) {
-          const float4 lo = __ldg(reinterpret_cast<const float4*>(p) + 2 * gi);
-          const float4 hi = __ldg(reinterpret_cast<const float4*>(p) + 2 * gi + 1);
+        if (pre_ok[k]) {
+          const float4 lo = pre[k][2 * gi], hi = pre[k][2 * gi + 1];
           float f[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
           if (affine) {
 #pragma unroll
@@ -183,7 +212,7 @@ tc_gather_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __gri
           }
           pk = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
         }
-        *reinterpret_cast<uint4*>(slot + (size_t)gi * group_bytes + (size_t)v * 16) = pk;
+        *reinterpret_cast<uint4*>(slot + (size_t)gi * group_bytes + soff[k]) = pk;
       }
     }
   };
@@ -217,9 +246,9 @@ tc_gather_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __gri
     }
   }
 
-  auto epilogue = [&](int qd, uint32_t use) {
-    const int b = qd & 1;
-    mbar_wait(smem_u32(&mbar[b]), use & 1);
+  auto epilogue = [&](int qd, int it) {           // it = iteration index within this CTA
+    const int b = it & 1;
+    mbar_wait(smem_u32(&mbar[b]), (uint32_t)((it >> 1) & 1));
     asm volatile("tcgen05.fence::after_thread_sync;");
     float acc[NLD];
     tmem_ld<NLD>(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(b * 16), acc);
@@ -283,15 +312,18 @@ tc_gather_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __gri
   const uint32_t tiles_addr = smem_u32(tiles), wblk_addr = smem_u32(wblk);
   const uint32_t sbo = (uint32_t)pl.PW * 16u;
   const uint32_t lbo = NG == 2 ? (uint32_t)group_bytes : 16u;
-  for (int rel = 0; rel < pl.span_d; ++rel) stage_plane(rel);
-  for (int qd = 0; qd < g.qD; ++qd) {
-    stage_plane(qd + pl.span_d);
+  // planes are addressed relative to lo_d: output plane qd reads ring planes qd .. qd + span_d
+  for (int rel = qd_beg; rel < qd_beg + pl.span_d; ++rel) { load_plane(rel); store_plane(rel); }
+  load_plane(qd_beg + pl.span_d);
+  for (int qd = qd_beg; qd < qd_end; ++qd) {
+    store_plane(qd + pl.span_d);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
+    const int it = qd - qd_beg;
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;");
-      const uint32_t d_tmem = tmem_base + (uint32_t)((qd & 1) * 16);
+      const uint32_t d_tmem = tmem_base + (uint32_t)((it & 1) * 16);
       for (int i = 0; i < pl.nmma; ++i) {
         const uint32_t slot = (uint32_t)((qd + pl.dd[i]) % pl.NP);
         const uint32_t a_addr = tiles_addr + slot * (uint32_t)slot_bytes + (uint32_t)(pl.dh[i] * pl.PW + pl.dw[i]) * 16u;
@@ -299,12 +331,13 @@ tc_gather_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __gri
                   i > 0 ? 1u : 0u);
       }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                       smem_u32(&mbar[qd & 1]))
+                       smem_u32(&mbar[it & 1]))
                    : "memory");
     }
-    if (qd > 0) epilogue(qd - 1, (uint32_t)((qd - 1) >> 1));
+    if (qd + 1 < qd_end) load_plane(qd + 1 + pl.span_d);      // in flight during the epilogue below
+    if (it > 0) epilogue(qd - 1, it - 1);
   }
-  epilogue(g.qD - 1, (uint32_t)((g.qD - 1) >> 1));
+  epilogue(qd_end - 1, qd_end - 1 - qd_beg);
 
   // ---- statistics flush + teardown
   if (want_stats || want_bn) {
@@ -354,6 +387,8 @@ static void build_plan(int cin, const Geom& g, TcPlan& pl) {
   pl.PH = TC_TH + pl.span_h;
   pl.PW = TC_TW + pl.span_w + 1;     // +1: the second K-chunk of an unpaired tap reads one voxel further
   pl.NP = pl.span_d + 2;
+  pl.dchunk = g.qD;
+  pl.nchunks = 1;
   pl.nmma = 0;
   bool used[kMaxTaps] = {false};
   auto find = [&](int dd, int dh, int dw) {
@@ -380,7 +415,7 @@ static void build_plan(int cin, const Geom& g, TcPlan& pl) {
 template <int CIN, int COUT>
 static int launch_tc_t(const Geom& g, const GatherArgs& a, const TcPlan& pl, cudaStream_t st) {
   const int tilesW = (g.qW + TC_TW - 1) / TC_TW, tilesH = (g.qH + TC_TH - 1) / TC_TH;
-  const long long cols = (long long)g.N * tilesH * tilesW;
+  const long long cols = (long long)g.N * tilesH * tilesW * pl.nchunks;
   const size_t smem = (size_t)pl.NP * (CIN / 8) * pl.PH * pl.PW * 16 + (size_t)pl.nmma * 512 + 1024 + 128;
   VG_CUDA(cudaFuncSetAttribute(tc_gather_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   tc_gather_kernel<CIN, COUT><<<(unsigned)cols, 128, smem, st>>>(g, a, pl);
@@ -400,6 +435,17 @@ int launch_tc_gather(int cin, int cout, const Geom& g_in, const GatherArgs& a, c
   }
   TcPlan pl{};
   build_plan(cin, g, pl);
+  {  // split columns along d until the grid can fill the machine (>= 4 CTAs per SM), keeping >= 6 planes per CTA
+    const int tilesW = (g.qW + TC_TW - 1) / TC_TW, tilesH = (g.qH + TC_TH - 1) / TC_TH;
+    const long long cols = (long long)g.N * tilesH * tilesW;
+    const long long want = 4LL * vg_sm_count();
+    int nch = (int)((want + cols - 1) / cols);
+    const int max_ch = g.qD / 6 > 0 ? g.qD / 6 : 1;
+    if (nch > max_ch) nch = max_ch;
+    if (nch < 1) nch = 1;
+    pl.dchunk = (g.qD + nch - 1) / nch;
+    pl.nchunks = (g.qD + pl.dchunk - 1) / pl.dchunk;
+  }
   if (pl.nmma > TC_MAX_MMA) { set_error("tensor-core plan needs %d MMAs (max %d)", pl.nmma, TC_MAX_MMA); return VG_EINVAL; }
   if (cin == 8 && cout == 1) return launch_tc_t<8, 1>(g, a, pl, st);
   if (cin == 8 && cout == 8) return launch_tc_t<8, 8>(g, a, pl, st);
