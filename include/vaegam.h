@@ -82,6 +82,10 @@ typedef struct VgConvDesc {
 int vg_set_conv_mode(int mode);
 int vg_get_conv_mode(void);
 
+/* Host-side description of the launches a layer maps to in the current mode (kind 0: forward,
+ * 1: data gradient), one text line per launch; returns the number of launches. */
+int vg_conv_describe(const VgConvDesc* d, int kind, char* buf, size_t cap);
+
 /* y = act(conv(x * in_scale[g,ci] + in_shift[g,ci]) + bias); zero padding is applied
  * AFTER the affine (it pads the normalised tensor).  in_scale/in_shift: (n/group_size, cin)
  * or NULL.  out_stats: (n/group_size, cout, 2) doubles, ACCUMULATED with sum(y), sum(y^2)

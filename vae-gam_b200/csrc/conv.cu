@@ -346,6 +346,7 @@ int conv_mode() {
 }
 
 static int launch_gather(int cin, int cout, const Geom& g, const GatherArgs& a, cudaStream_t st) {
+  if (conv_mode() == 1 && tc2_supported(cin, cout, g)) return launch_tc2_gather(cin, cout, g, a, st);
   if (conv_mode() == 1 && tc_supported(cin, cout, g)) return launch_tc_gather(cin, cout, g, a, st);
   if (cin == 1 && cout == 8) return launch_gather_t<1, 8, 4>(g, a, st);
   if (cin == 8 && cout == 1) return launch_gather_t<8, 1, 4>(g, a, st);
@@ -370,6 +371,30 @@ extern "C" int vg_set_conv_mode(int mode) {
   return VG_OK;
 }
 extern "C" int vg_get_conv_mode(void) { return conv_mode(); }
+
+// Which kernel serves each gather of a layer (kind 0 forward, 1 data gradient) in the current
+// convolution mode; one line per launch.  Host only, no device work.
+extern "C" int vg_conv_describe(const VgConvDesc* d, int kind, char* buf, size_t cap) {
+  VG_TRY(check_desc(d));
+  VG_CHECK_ARG(buf && cap > 0 && (kind == 0 || kind == 1), "bad arguments");
+  Geom gs[8];
+  const int ng = build_geoms(d, kind, gs);
+  const int cin = kind == 0 ? d->cin : d->cout, cout = kind == 0 ? d->cout : d->cin;
+  size_t off = 0;
+  buf[0] = 0;
+  for (int i = 0; i < ng && off + 8 < cap; ++i) {
+    int n = 0;
+    if (conv_mode() == 1) n = tc2_describe(cin, cout, gs[i], buf + off, cap - off);
+    if (n <= 0) {
+      const bool tc = conv_mode() == 1 && tc_supported(cin, cout, gs[i]);
+      n = snprintf(buf + off, cap - off, "%s cin=%d cout=%d q=(%d,%d,%d) taps=%d", tc ? "tc1" : "fp32", cin, cout,
+                   gs[i].qD, gs[i].qH, gs[i].qW, gs[i].ntaps);
+    }
+    off += (size_t)n < cap - off ? (size_t)n : cap - off - 1;
+    if (off + 2 < cap) { buf[off++] = '\n'; buf[off] = 0; }
+  }
+  return ng;
+}
 
 extern "C" int vg_conv_fwd(const VgConvDesc* d, const float* x, const float* w, const float* bias,
                            const float* in_scale, const float* in_shift, float* y, int act,

@@ -39,51 +39,42 @@ struct ReconArgs {
   int col_chunks;      // gridDim.x
 };
 
-// block reduce NV values per thread -> out[NV] written by thread 0.. (fixed order)
-template <int NV>
-__device__ __forceinline__ void block_reduce_store(float (&vals)[NV], float* out) {
-  __shared__ float sm[RL_THREADS / 32][NV];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const float r = warp_sum(vals[i]);
-    if (lane == 0) sm[warp][i] = r;
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < NV; i += RL_THREADS) {
-    float s = 0.f;
-#pragma unroll
-    for (int w = 0; w < RL_THREADS / 32; ++w) s += sm[w][i];
-    out[i] = s;
-  }
+// Row sums: every warp reduces a row's NV values with shuffles and lane 0 adds them to the warp's
+// own shared-memory slot (no atomics, fixed order), so no per-row accumulator lives in registers
+// across the loop — the kernels stay under 85 registers and three CTAs share an SM.
+__device__ __forceinline__ void warp_accumulate(float v, float* slot) {
+  const float r = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) *slot += r;
 }
 
 // partial layout: [rowgroup][chunk][ROWS][9]  (slot 0 = logp, 1..8 = squared norms)
-__global__ void __launch_bounds__(RL_THREADS)
+template <bool MAPS>
+__global__ void __launch_bounds__(RL_THREADS, 3)
 recon_fwd_kernel(const ReconArgs a, float* __restrict__ partial, float* cons_out, float* xrec_out) {
+  __shared__ float s_g[ROWS][KCOV];
+  __shared__ float s_acc[RL_THREADS / 32][ROWS * 9];
   const int rg = blockIdx.y;
   const int row0 = rg * ROWS;
+  const int warp = threadIdx.x >> 5;
   const size_t map_stride = (size_t)a.b * a.vp;
-  float acc[ROWS * 9];
-#pragma unroll
-  for (int i = 0; i < ROWS * 9; ++i) acc[i] = 0.f;
-  float gv[ROWS][KCOV];
-#pragma unroll
-  for (int r = 0; r < ROWS; ++r)
-#pragma unroll
-    for (int i = 0; i < KCOV; ++i) gv[r][i] = (row0 + r < a.b) ? __ldg(a.g + i * a.b + row0 + r) : 0.f;
+  if (threadIdx.x < ROWS * KCOV) {
+    const int r = threadIdx.x / KCOV, i = threadIdx.x % KCOV;
+    s_g[r][i] = (row0 + r < a.b) ? __ldg(a.g + i * a.b + row0 + r) : 0.f;
+  }
+  for (int i = threadIdx.x; i < (RL_THREADS / 32) * ROWS * 9; i += RL_THREADS) (&s_acc[0][0])[i] = 0.f;
+  __syncthreads();
 
-  for (int col = blockIdx.x * RL_THREADS + threadIdx.x; col < a.ncols; col += a.col_chunks * RL_THREADS) {
-    const int v0 = col * 4;
+  // the loop bound is warp-uniform (whole warps stay in the shuffles); out-of-range lanes add zeros
+  const int ncols_pad = (a.ncols + 31) & ~31;
+  for (int col = blockIdx.x * RL_THREADS + threadIdx.x; col < ncols_pad; col += a.col_chunks * RL_THREADS) {
+    const bool col_ok = col < a.ncols;
+    const int v0 = (col_ok ? col : 0) * 4;
     const float4 e4 = ld4_keep(a.eps + v0);
-    float4 G4[KCOV];
-#pragma unroll
-    for (int i = 0; i < KCOV; ++i) G4[i] = ld4_keep(a.glm + (size_t)i * a.vp + v0);
     const float ee[4] = {e4.x, e4.y, e4.z, e4.w};
     float ww[4];
 #pragma unroll
     for (int l = 0; l < 4; ++l) ww[l] = __expf(2.f * ee[l]);
-#pragma unroll
+#pragma unroll 1
     for (int r = 0; r < ROWS; ++r) {
       const int row = row0 + r;
       if (row >= a.b) break;
@@ -96,9 +87,10 @@ recon_fwd_kernel(const ReconArgs a, float* __restrict__ partial, float* cons_out
       float xr[4] = {m4[0].x, m4[0].y, m4[0].z, m4[0].w};
 #pragma unroll
       for (int i = 0; i < KCOV; ++i) {
-        const float gi = gv[r][i];
+        const float gi = s_g[r][i];
+        const float4 G = ld4_keep(a.glm + (size_t)i * a.vp + v0);     // L1-resident after the first row
         const float c[4] = {gi * m4[i + 1].x, gi * m4[i + 1].y, gi * m4[i + 1].z, gi * m4[i + 1].w};
-        const float Gs[4] = {G4[i].x, G4[i].y, G4[i].z, G4[i].w};
+        const float Gs[4] = {G.x, G.y, G.z, G.w};
         float s = 0.f;
 #pragma unroll
         for (int l = 0; l < 4; ++l) {
@@ -106,8 +98,8 @@ recon_fwd_kernel(const ReconArgs a, float* __restrict__ partial, float* cons_out
           const float d = c[l] - Gs[l];
           if (v0 + l < a.v) s = fmaf(d, d, s);
         }
-        acc[r * 9 + 1 + i] += s;
-        if (cons_out) {
+        warp_accumulate(col_ok ? s : 0.f, &s_acc[warp][r * 9 + 1 + i]);
+        if (MAPS && cons_out && col_ok) {
 #pragma unroll
           for (int l = 0; l < 4; ++l)
             if (v0 + l < a.v) cons_out[((size_t)i * a.b + row) * a.v + v0 + l] = c[l];
@@ -119,15 +111,21 @@ recon_fwd_kernel(const ReconArgs a, float* __restrict__ partial, float* cons_out
         const float rr = xs[l] - xr[l];
         if (v0 + l < a.v) lp += fmaf(-0.5f * rr * rr, ww[l], ee[l] - HALF_LOG_2PI);
       }
-      acc[r * 9] += lp;
-      if (xrec_out) {
+      warp_accumulate(col_ok ? lp : 0.f, &s_acc[warp][r * 9]);
+      if (MAPS && xrec_out && col_ok) {
 #pragma unroll
         for (int l = 0; l < 4; ++l)
           if (v0 + l < a.v) xrec_out[(size_t)row * a.v + v0 + l] = xr[l];
       }
     }
   }
-  block_reduce_store<ROWS * 9>(acc, partial + ((size_t)rg * a.col_chunks + blockIdx.x) * ROWS * 9);
+  __syncthreads();
+  for (int i = threadIdx.x; i < ROWS * 9; i += RL_THREADS) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < RL_THREADS / 32; ++w) s += s_acc[w][i];
+    partial[((size_t)rg * a.col_chunks + blockIdx.x) * ROWS * 9 + i] = s;
+  }
 }
 
 __global__ void recon_fwd_finalize(const float* __restrict__ partial, int b, int col_chunks, float* logp,
@@ -143,36 +141,34 @@ __global__ void recon_fwd_finalize(const float* __restrict__ partial, int b, int
 }
 
 // partial layout: [rowgroup][chunk][ROWS][8]  (dg partial sums)
-__global__ void __launch_bounds__(RL_THREADS)
+__global__ void __launch_bounds__(RL_THREADS, 3)
 recon_bwd_kernel(const ReconArgs a, const float* __restrict__ norms, float lam, float* __restrict__ dpre,
                  float* __restrict__ partial, float* __restrict__ deps) {
+  __shared__ float s_g[ROWS][KCOV], s_cf[ROWS][KCOV];     // gain and lam*B/norm
+  __shared__ float s_acc[RL_THREADS / 32][ROWS * KCOV];
   const int rg = blockIdx.y;
   const int row0 = rg * ROWS;
+  const int warp = threadIdx.x >> 5;
   const size_t map_stride = (size_t)a.b * a.vp;
   const float invB = 1.f / (float)a.b;
-  float acc[ROWS * KCOV];
-#pragma unroll
-  for (int i = 0; i < ROWS * KCOV; ++i) acc[i] = 0.f;
-  float gv[ROWS][KCOV], cf[ROWS][KCOV];   // gain and lam*B/norm
-#pragma unroll
-  for (int r = 0; r < ROWS; ++r)
-#pragma unroll
-    for (int i = 0; i < KCOV; ++i) {
-      const bool ok = row0 + r < a.b;
-      gv[r][i] = ok ? __ldg(a.g + i * a.b + row0 + r) : 0.f;
-      const float nn = ok ? __ldg(norms + i * a.b + row0 + r) : 0.f;
-      cf[r][i] = nn > 0.f ? lam * (float)a.b / nn : 0.f;
-    }
+  if (threadIdx.x < ROWS * KCOV) {
+    const int r = threadIdx.x / KCOV, i = threadIdx.x % KCOV;
+    const bool ok = row0 + r < a.b;
+    s_g[r][i] = ok ? __ldg(a.g + i * a.b + row0 + r) : 0.f;
+    const float nn = ok ? __ldg(norms + i * a.b + row0 + r) : 0.f;
+    s_cf[r][i] = nn > 0.f ? lam * (float)a.b / nn : 0.f;
+  }
+  for (int i = threadIdx.x; i < (RL_THREADS / 32) * ROWS * KCOV; i += RL_THREADS) (&s_acc[0][0])[i] = 0.f;
+  __syncthreads();
 
-  for (int col = blockIdx.x * RL_THREADS + threadIdx.x; col < a.ncols; col += a.col_chunks * RL_THREADS) {
-    const int v0 = col * 4;
+  const int ncols_pad = (a.ncols + 31) & ~31;
+  for (int col = blockIdx.x * RL_THREADS + threadIdx.x; col < ncols_pad; col += a.col_chunks * RL_THREADS) {
+    const bool col_ok = col < a.ncols;
+    const int v0 = (col_ok ? col : 0) * 4;
     const float4 e4 = ld4_keep(a.eps + v0);
-    float4 G4[KCOV];
-#pragma unroll
-    for (int i = 0; i < KCOV; ++i) G4[i] = ld4_keep(a.glm + (size_t)i * a.vp + v0);
-    float ww[4] = {__expf(2.f * e4.x), __expf(2.f * e4.y), __expf(2.f * e4.z), __expf(2.f * e4.w)};
+    const float ww[4] = {__expf(2.f * e4.x), __expf(2.f * e4.y), __expf(2.f * e4.z), __expf(2.f * e4.w)};
     float de[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
+#pragma unroll 1
     for (int r = 0; r < ROWS; ++r) {
       const int row = row0 + r;
       if (row >= a.b) break;
@@ -194,7 +190,7 @@ recon_bwd_kernel(const ReconArgs a, const float* __restrict__ norms, float lam, 
 #pragma unroll
       for (int i = 0; i < KCOV; ++i)
 #pragma unroll
-        for (int l = 0; l < 4; ++l) xr[l] = fmaf(gv[r][i], mm[i + 1][l], xr[l]);
+        for (int l = 0; l < 4; ++l) xr[l] = fmaf(s_g[r][i], mm[i + 1][l], xr[l]);
       float A[4];
 #pragma unroll
       for (int l = 0; l < 4; ++l) {
@@ -206,29 +202,41 @@ recon_bwd_kernel(const ReconArgs a, const float* __restrict__ norms, float lam, 
       float o[4];
 #pragma unroll
       for (int l = 0; l < 4; ++l) o[l] = A[l] * mm[0][l] * (1.f - mm[0][l]);
-      stg_stream(reinterpret_cast<float4*>(dpre + (size_t)row * a.vp + v0), make_float4(o[0], o[1], o[2], o[3]));
+      if (col_ok)
+        stg_stream(reinterpret_cast<float4*>(dpre + (size_t)row * a.vp + v0), make_float4(o[0], o[1], o[2], o[3]));
 #pragma unroll
       for (int i = 0; i < KCOV; ++i) {
-        const float Gs[4] = {G4[i].x, G4[i].y, G4[i].z, G4[i].w};
+        const float4 G = ld4_keep(a.glm + (size_t)i * a.vp + v0);     // L1-resident after the first row
+        const float Gs[4] = {G.x, G.y, G.z, G.w};
+        const float gi = s_g[r][i], cfi = s_cf[r][i];
         float s = 0.f;
 #pragma unroll
         for (int l = 0; l < 4; ++l) {
           const float D = mm[i + 1][l];
-          float dc = A[l] + cf[r][i] * (gv[r][i] * D - Gs[l]);     // d tot / d cons_i
+          float dc = A[l] + cfi * (gi * D - Gs[l]);     // d tot / d cons_i
           if (!(v0 + l < a.v)) dc = 0.f;
           s = fmaf(D, dc, s);
-          o[l] = gv[r][i] * dc * D * (1.f - D);
+          o[l] = gi * dc * D * (1.f - D);
         }
-        acc[r * KCOV + i] += s;
-        stg_stream(reinterpret_cast<float4*>(dpre + (i + 1) * map_stride + (size_t)row * a.vp + v0),
-                   make_float4(o[0], o[1], o[2], o[3]));
+        warp_accumulate(col_ok ? s : 0.f, &s_acc[warp][r * KCOV + i]);
+        if (col_ok)
+          stg_stream(reinterpret_cast<float4*>(dpre + (i + 1) * map_stride + (size_t)row * a.vp + v0),
+                     make_float4(o[0], o[1], o[2], o[3]));
       }
     }
+    if (col_ok) {
 #pragma unroll
-    for (int l = 0; l < 4; ++l)
-      if (v0 + l < a.v) atomicAdd(deps + v0 + l, de[l]);
+      for (int l = 0; l < 4; ++l)
+        if (v0 + l < a.v) atomicAdd(deps + v0 + l, de[l]);
+    }
   }
-  block_reduce_store<ROWS * KCOV>(acc, partial + ((size_t)rg * a.col_chunks + blockIdx.x) * ROWS * KCOV);
+  __syncthreads();
+  for (int i = threadIdx.x; i < ROWS * KCOV; i += RL_THREADS) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < RL_THREADS / 32; ++w) s += s_acc[w][i];
+    partial[((size_t)rg * a.col_chunks + blockIdx.x) * ROWS * KCOV + i] = s;
+  }
 }
 
 __global__ void recon_bwd_finalize(const float* __restrict__ partial, int b, int col_chunks, float* dg) {
@@ -271,7 +279,8 @@ extern "C" int vg_recon_loss_fwd(const float* maps, const float* g, const float*
   const int rgs = (b + ROWS - 1) / ROWS;
   a.col_chunks = pick_chunks(a.ncols, rgs);
   cudaStream_t st = as_stream(stream);
-  recon_fwd_kernel<<<dim3(a.col_chunks, rgs), RL_THREADS, 0, st>>>(a, (float*)workspace, cons, x_rec);
+  if (cons || x_rec) recon_fwd_kernel<true><<<dim3(a.col_chunks, rgs), RL_THREADS, 0, st>>>(a, (float*)workspace, cons, x_rec);
+  else recon_fwd_kernel<false><<<dim3(a.col_chunks, rgs), RL_THREADS, 0, st>>>(a, (float*)workspace, nullptr, nullptr);
   VG_LAUNCH_CHECK();
   recon_fwd_finalize<<<cdiv(b * 9, 128), 128, 0, st>>>((const float*)workspace, b, a.col_chunks, logp, norms);
   VG_LAUNCH_CHECK();
