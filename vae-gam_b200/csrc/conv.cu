@@ -346,7 +346,7 @@ int conv_mode() {
 }
 
 static int launch_gather(int cin, int cout, const Geom& g, const GatherArgs& a, cudaStream_t st) {
-  if (conv_mode() == 1 && tc2_supported(cin, cout, g)) return launch_tc2_gather(cin, cout, g, a, st);
+  if (conv_mode() == 1 && tc2_supported(cin, cout, &g, 1)) return launch_tc2_gather(cin, cout, &g, 1, a, st);
   if (conv_mode() == 1 && tc_supported(cin, cout, g)) return launch_tc_gather(cin, cout, g, a, st);
   if (cin == 1 && cout == 8) return launch_gather_t<1, 8, 4>(g, a, st);
   if (cin == 8 && cout == 1) return launch_gather_t<8, 1, 4>(g, a, st);
@@ -359,6 +359,13 @@ static int launch_gather(int cin, int cout, const Geom& g, const GatherArgs& a, 
   if (cin == 16 && cout == 1) return launch_gather_t<16, 1, 4>(g, a, st);
   set_error("unsupported channel pair (%d,%d): channels must be in {1,8,16}", cin, cout);
   return VG_EINVAL;
+}
+
+// every gather of one layer pass: one fused multi-phase launch when the plane-folded kernel covers it
+static int launch_all(int cin, int cout, const Geom* gs, int ng, const GatherArgs& a, cudaStream_t st) {
+  if (ng > 1 && conv_mode() == 1 && tc2_supported(cin, cout, gs, ng)) return launch_tc2_gather(cin, cout, gs, ng, a, st);
+  for (int i = 0; i < ng; ++i) VG_TRY(launch_gather(cin, cout, gs[i], a, st));
+  return VG_OK;
 }
 
 }  // namespace vg
@@ -382,9 +389,14 @@ extern "C" int vg_conv_describe(const VgConvDesc* d, int kind, char* buf, size_t
   const int cin = kind == 0 ? d->cin : d->cout, cout = kind == 0 ? d->cout : d->cin;
   size_t off = 0;
   buf[0] = 0;
+  if (ng > 1 && conv_mode() == 1 && tc2_supported(cin, cout, gs, ng)) {
+    const int n = tc2_describe(cin, cout, gs, ng, buf, cap);
+    if (n > 0 && (size_t)n + 2 < cap) { buf[n] = '\n'; buf[n + 1] = 0; }
+    return 1;
+  }
   for (int i = 0; i < ng && off + 8 < cap; ++i) {
     int n = 0;
-    if (conv_mode() == 1) n = tc2_describe(cin, cout, gs[i], buf + off, cap - off);
+    if (conv_mode() == 1) n = tc2_describe(cin, cout, &gs[i], 1, buf + off, cap - off);
     if (n <= 0) {
       const bool tc = conv_mode() == 1 && tc_supported(cin, cout, gs[i]);
       n = snprintf(buf + off, cap - off, "%s cin=%d cout=%d q=(%d,%d,%d) taps=%d", tc ? "tc1" : "fp32", cin, cout,
@@ -406,8 +418,7 @@ extern "C" int vg_conv_fwd(const VgConvDesc* d, const float* x, const float* w, 
   GatherArgs a{};
   a.in = x; a.w = w; a.bias = bias; a.in_scale = in_scale; a.in_shift = in_shift;
   a.out = y; a.act = act; a.stats = out_stats;
-  for (int i = 0; i < ng; ++i) VG_TRY(launch_gather(d->cin, d->cout, gs[i], a, as_stream(stream)));
-  return VG_OK;
+  return launch_all(d->cin, d->cout, gs, ng, a, as_stream(stream));
 }
 
 extern "C" int vg_conv_dgrad(const VgConvDesc* d, const float* dy, const float* w, float* dx,
@@ -424,8 +435,7 @@ extern "C" int vg_conv_dgrad(const VgConvDesc* d, const float* dy, const float* 
   if (mask_act) { a.aux = mask_act; a.aux_mode = 1; }
   if (bn_x) { a.aux = bn_x; a.aux_mode = 2; a.aux_istd = bn_istd; a.aux_mistd = bn_mistd; a.aux_sums = bn_sums; }
   // the gather reads dy (cout channels) and produces cin channels
-  for (int i = 0; i < ng; ++i) VG_TRY(launch_gather(d->cout, d->cin, gs[i], a, as_stream(stream)));
-  return VG_OK;
+  return launch_all(d->cout, d->cin, gs, ng, a, as_stream(stream));
 }
 
 int vg_conv_wgrad_tiled(const VgConvDesc* d, const float* x, const float* dy, const float* in_scale,

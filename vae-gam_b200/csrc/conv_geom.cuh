@@ -46,9 +46,10 @@ struct GatherArgs {
 bool tc_supported(int cin, int cout, const Geom& g);
 int launch_tc_gather(int cin, int cout, const Geom& g, const GatherArgs& a, cudaStream_t st);
 // tc2_conv.cu (plane-folded tcgen05 kernel: unit-stride gathers with 1 or 8 input channels)
-bool tc2_supported(int cin, int cout, const Geom& g);
-int launch_tc2_gather(int cin, int cout, const Geom& g, const GatherArgs& a, cudaStream_t st);
-int tc2_describe(int cin, int cout, const Geom& g, char* buf, size_t cap);
+// gs[0..ng): gathers of one layer pass sharing their input (ng > 1: the output-parity phases of a stride-2 layer)
+bool tc2_supported(int cin, int cout, const Geom* gs, int ng);
+int launch_tc2_gather(int cin, int cout, const Geom* gs, int ng, const GatherArgs& a, cudaStream_t st);
+int tc2_describe(int cin, int cout, const Geom* gs, int ng, char* buf, size_t cap);
 int conv_mode();   // 0: fp32 CUDA cores ("check mode"), 1: bf16 tcgen05 where the geometry allows
 
 }  // namespace vg

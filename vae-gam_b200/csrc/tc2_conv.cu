@@ -13,26 +13,26 @@
 // shifted-window descriptors over the same staged plane: rows are the plane's voxels flattened
 // with a padded pitch, so a tap is a constant row shift and a tile is 128 consecutive rows.
 // Inputs with ONE channel use the 8 consecutive w-voxels of a row as the K-chunk (the dw taps sit
-// inside K).  Stride-2 transposed layers run as their output-parity phases (sout = 2).
+// inside K).  A stride-2 transposed layer is ONE launch: its (up to 8) output-parity phases share
+// the staged input planes and differ only in their MMA lists, weight blocks and output offsets.
 //
-// Roles (416 threads, one persistent CTA per SM):
-//   warps 0-3   epilogue: tcgen05.ld -> bias / activation / BatchNorm statistics / backward masks
-//               -> global; re-zero the accumulator buffer (all MMAs accumulate)
-//   warps 4-11  producers: fp32 global -> BatchNorm fold -> bf16 -> ring of plane pairs in smem
-//   warp 12     one lane issues the tcgen05.mma list of a block of OB output planes
+// Roles (416 threads, one persistent CTA per SM), ES = 1 or 2 epilogue sets:
+//   warps [0, 4*ES)      epilogue: tcgen05.ld -> bias / activation / BatchNorm statistics / backward
+//                        masks -> global; re-zero the accumulator columns (all MMAs accumulate)
+//   warps [4*ES, 12)     producers: fp32 global -> BatchNorm fold -> bf16 -> ring of plane pairs
+//   warp 12              one elected lane issues the tcgen05.mma list of a (block, phase)
 // Pipelines: full/empty mbarriers per ring slot (producers <-> MMA via tcgen05.commit), and
 // full/empty per accumulator buffer (MMA <-> epilogue), accumulators double-buffered in TMEM.
+#include <type_traits>
+
 #include "common.cuh"
 #include "conv_geom.cuh"
 #include "tc_common.cuh"
 
 namespace vg {
 
-constexpr int T2_EPI_WARPS = 4, T2_PROD_WARPS = 8;
-constexpr int T2_PROD_THREADS = T2_PROD_WARPS * 32;
-constexpr int T2_THREADS = (T2_EPI_WARPS + T2_PROD_WARPS + 1) * 32;
-constexpr int T2_MAX_MMA = 96, T2_MAX_BLK = 96, T2_MAX_PAIR = 10, T2_MAX_RING = 16;
-constexpr int T2_MAX_CHUNK = 3;                 // staged 16-byte chunks per producer thread and plane
+constexpr int T2_THREADS = 13 * 32, T2_MMA_WARP = 12;
+constexpr int T2_MAX_MMA = 128, T2_MAX_BLK = 128, T2_MAX_PAIR = 10, T2_MAX_RING = 16, T2_MAX_PH = 8;
 
 struct T2Mma {
   uint16_t a_shift;    // row shift of the A window inside the staged plane
@@ -42,30 +42,48 @@ struct T2Mma {
   uint8_t pad[2];
 };
 struct T2Blk {
-  int8_t i0, j0, nj, dh, dw, pad[3];   // window plane of K-chunk 0; output planes [j0, j0+nj); tap offsets relative to lo_*
+  int8_t i0, j0, nj, dh, dw, ph, pad[2];   // window plane of K-chunk 0; output planes [j0, j0+nj); taps relative to lo_*
+};
+struct T2Phase {
+  int16_t qD, qH, qW;
+  int8_t rD, rH, rW;
+  uint8_t pad;
+  uint8_t pair_begin[T2_MAX_PAIR + 1];
+  uint8_t pad2;
 };
 struct T2Plan {
   int PW, RTOT, TR, ntiles, SR, OB, NPAIR, R, nrb, ACCW, tmem_cols;
   int lo_d, lo_h, lo_w, span_d, span_h, span_w;
-  int dchunk, ndchunks;
-  int nblk, wbytes;
-  int pair_begin[T2_MAX_PAIR + 1];
+  int qDmax, dchunk, ndchunks;
+  int nph, nmma, nblk, wbytes;
+  T2Phase ph[T2_MAX_PH];
   T2Mma mma[T2_MAX_MMA];
   T2Blk blk[T2_MAX_BLK];
   uint16_t blk_off16[T2_MAX_BLK];
 };
 
+// roles per (cin, cout): the side that moves more bytes gets more warps
+__host__ __device__ constexpr int t2_epi_sets(int cin, int cout) { return (cin == 8 && cout == 1) ? 1 : 2; }
+__host__ __device__ constexpr int t2_max_chunk(int cin, int es) { return cin == 8 ? (es == 1 ? 2 : 4) : (es == 1 ? 3 : 5); }
+
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(T2_THREADS, 1)
 tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_constant__ T2Plan pl) {
+  constexpr int ES = t2_epi_sets(CIN, COUT);
+  constexpr int EPI_WARPS = 4 * ES, PROD_WARPS = 12 - EPI_WARPS, PT = PROD_WARPS * 32;
+  constexpr int MAXC = t2_max_chunk(CIN, ES);
+  constexpr bool PIPE = (CIN == 1) || (ES == 1);       // register double-buffering of the staged pair
+  constexpr int NJ = 16 / COUT;                        // output planes per epilogue item (16 TMEM columns)
+
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[T2_MAX_RING], empty_bar[T2_MAX_RING], accf_bar[2], acce_bar[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ int lut[5 * 3 * 3];
+  __shared__ int lut[T2_MAX_PH][45];
   __shared__ float s_bias[16];
+  __shared__ uint4 s_mma[T2_MAX_MMA];           // {A row shift, B descriptor low word, instruction descriptor, D column}
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int SRB = pl.SR * 16;                 // bytes per staged plane
+  const int SRB = pl.SR * 16;                   // bytes per staged plane
   const int PAIRB = 2 * SRB;
   uint8_t* ring = smem;
   uint8_t* wts = smem + (size_t)pl.R * PAIRB;
@@ -74,18 +92,24 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
   // ---------------------------------------------------------------- one-time setup
   if (tid == 0) {
     for (int s = 0; s < pl.R; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), T2_PROD_THREADS);
+      mbar_init(smem_u32(&full_bar[s]), PT);
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&accf_bar[b]), 1);
-      mbar_init(smem_u32(&acce_bar[b]), T2_EPI_WARPS * 32);
+      mbar_init(smem_u32(&acce_bar[b]), EPI_WARPS * 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
-  if (tid < 45) lut[tid] = -1;
+  for (int i = tid; i < T2_MAX_PH * 45; i += T2_THREADS) (&lut[0][0])[i] = -1;
   if (tid < 16) s_bias[tid] = (a.bias && tid < COUT) ? __ldg(a.bias + tid) : 0.f;
-  if (warp == T2_EPI_WARPS + T2_PROD_WARPS) {
+  if (tid < pl.nmma) {
+    const T2Mma mm = pl.mma[tid];
+    const uint32_t w16 = (smem_u32(smem) + (uint32_t)pl.R * (uint32_t)PAIRB) >> 4;
+    s_mma[tid] = make_uint4((uint32_t)mm.a_shift, ((w16 + mm.b_off16) & 0x3FFFu) | (8u << 16),
+                            umma_idesc_m128((uint32_t)mm.n8 << 3), (uint32_t)mm.dcol);
+  }
+  if (warp == T2_MMA_WARP) {
     const uint32_t dst = smem_u32(&tmem_base_s);
     switch (pl.tmem_cols) {
       case 32: asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" ::"r"(dst)); break;
@@ -98,8 +122,8 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
   }
   __syncthreads();
   if (tid < g.ntaps) {
-    const Tap tp = g.taps[tid];
-    lut[(tp.dd - pl.lo_d) * 9 + (tp.dh - pl.lo_h) * 3 + (tp.dw - pl.lo_w)] = tp.widx;
+    const Tap tp = g.taps[tid];                 // pad_ = phase of the tap
+    lut[tp.pad_][(tp.dd - pl.lo_d) * 9 + (tp.dh - pl.lo_h) * 3 + (tp.dw - pl.lo_w)] = tp.widx;
   }
   tc_fence_before();
   __syncthreads();
@@ -120,13 +144,13 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
       if constexpr (CIN == 1) { ci = 0; dwr = el; } else { ci = el; dwr = bk.dw; }
       float w = 0.f;
       if (ddr >= 0 && ddr <= pl.span_d && dwr <= pl.span_w) {
-        const int widx = lut[ddr * 9 + bk.dh * 3 + dwr];
+        const int widx = lut[bk.ph][ddr * 9 + bk.dh * 3 + dwr];
         if (widx >= 0) w = __ldg(a.w + (size_t)widx * g.wst_t + (size_t)ci * g.wst_ci + (size_t)co * g.wst_co);
       }
       dst[(((n >> 3) * 256 + chunk * 128 + (n & 7) * 16) >> 1) + el] = __float2bfloat16(w);
     }
   }
-  if (warp < T2_EPI_WARPS) {                    // all MMAs accumulate: start from zero
+  if (warp < 4) {                               // all MMAs accumulate: start from zero
     for (int c = 0; c < pl.tmem_cols; c += 16) tmem_zero16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c);
     tmem_st_wait();
   }
@@ -136,15 +160,18 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
   tc_fence_after();
 
   const int ncols = g.N * pl.ntiles * pl.ndchunks;
-  int pair_base = 0, block_base = 0;            // running counters, identical in every role
+  int pair_base = 0, acc_base = 0;              // running counters, identical in every role
 
-  if (warp < T2_EPI_WARPS) {
+  if (warp < EPI_WARPS) {
     // ================================================================ epilogue warps
     const bool want_stats = a.stats != nullptr, want_bn = a.aux_mode == 2;
-    constexpr int JG = COUT == 1 ? 16 : (COUT == 8 ? 4 : 2);      // output planes per TMEM load group
+    const int eset = warp >> 2, etid = tid & 127;            // TMEM lane = etid
+    const int ipr = pl.ACCW >> 4, nitems = pl.nrb * ipr;     // 16-column items per row block / per accumulator
+    const size_t plane_out = (size_t)g.outH * g.outW * COUT;
+    struct Item { int rb, k, qd; bool row_ok; size_t o0; };
     for (int col = blockIdx.x; col < ncols; col += gridDim.x) {
       const int dc = col % pl.ndchunks, t = (col / pl.ndchunks) % pl.ntiles, n = col / (pl.ndchunks * pl.ntiles);
-      const int qd0 = dc * pl.dchunk, qd1 = min(g.qD, qd0 + pl.dchunk);
+      const int qd0 = dc * pl.dchunk, qd1 = min(pl.qDmax, qd0 + pl.dchunk);
       const int nblocks = (qd1 - qd0 + pl.OB - 1) / pl.OB;
       const int grp = n / g.group_size;
       float istd[COUT], mistd[COUT], s1[COUT], s2[COUT];
@@ -154,77 +181,53 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
         istd[c] = want_bn ? __ldg(a.aux_istd + grp * COUT + c) : 0.f;
         mistd[c] = want_bn ? __ldg(a.aux_mistd + grp * COUT + c) : 0.f;
       }
-      const size_t plane_out = (size_t)g.outH * g.outW * COUT;
-      for (int b = 0; b < nblocks; ++b) {
-        const int bg = block_base + b, buf = bg & 1;
-        mbar_wait(smem_u32(&accf_bar[buf]), (uint32_t)((bg >> 1) & 1));
-        tc_fence_after();
-        for (int rb = 0; rb < pl.nrb; ++rb) {
-          const int r = t * pl.TR + rb * 128 + tid;
-          const int qh = r / pl.PW, qw = r - qh * pl.PW;
-          const bool row_ok = r < pl.RTOT && qw < g.qW;
-          const size_t o_row = (size_t)n * g.out_img +
-                               ((size_t)(qh * g.sout + g.rH) * g.outW + (size_t)(qw * g.sout + g.rW)) * COUT;
-          const uint32_t tacc = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((buf * pl.nrb + rb) * pl.ACCW);
-          for (int j0 = 0; j0 < pl.OB; j0 += JG) {
-            float acc[JG][COUT];
-            {
-              if constexpr (COUT == 1) {
-                uint32_t rr[16];
-                tmem_ld16(tacc + (uint32_t)j0, rr);
-                tmem_ld_wait();
+      for (int b = 0; b < nblocks; ++b)
+        for (int ph = 0; ph < pl.nph; ++ph) {
+          const T2Phase& P = pl.ph[ph];
+          const int au = acc_base + b * pl.nph + ph, buf = au & 1;
+          const int qd_end = min((int)P.qD, qd1);
+          auto setup = [&](int it, Item& I) {
+            I.rb = it / ipr; I.k = it - I.rb * ipr;
+            const int r = t * pl.TR + I.rb * 128 + etid;
+            const int qh = r / pl.PW, qw = r - qh * pl.PW;
+            I.row_ok = qh < P.qH && qw < P.qW;
+            I.qd = qd0 + b * pl.OB + I.k * NJ;
+            I.o0 = (size_t)n * g.out_img + (size_t)(I.qd * g.sout + P.rD) * plane_out +
+                   ((size_t)(qh * g.sout + P.rH) * g.outW + (size_t)(qw * g.sout + P.rW)) * COUT;
+          };
+          auto load_aux = [&](const Item& I, float (&ax)[NJ][COUT]) {
+            if (a.aux_mode == 0 || !I.row_ok) return;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) acc[j][0] = __uint_as_float(rr[j]);
-              } else if constexpr (COUT == 8) {
-                uint32_t rr[JG][8];
+            for (int j = 0; j < NJ; ++j) {
+              if (I.qd + j >= qd_end) continue;
+              const float* p = a.aux + I.o0 + (size_t)j * g.sout * plane_out;
+              if constexpr (COUT % 4 == 0) {
 #pragma unroll
-                for (int j = 0; j < JG; ++j) tmem_ld8(tacc + (uint32_t)((j0 + j) * 8), rr[j]);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < JG; ++j)
-#pragma unroll
-                  for (int c = 0; c < 8; ++c) acc[j][c] = __uint_as_float(rr[j][c]);
-              } else {
-                uint32_t rr[JG][16];
-#pragma unroll
-                for (int j = 0; j < JG; ++j) tmem_ld16(tacc + (uint32_t)((j0 + j) * 16), rr[j]);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < JG; ++j)
-#pragma unroll
-                  for (int c = 0; c < 16; ++c) acc[j][c] = __uint_as_float(rr[j][c]);
-              }
-            }
-            if (!row_ok) continue;
-            // issue the auxiliary loads of the whole group first (memory-level parallelism)
-            float ax[JG][COUT];
-            bool pok[JG];
-            size_t oo[JG];
-#pragma unroll
-            for (int j = 0; j < JG; ++j) {
-              const int qd = qd0 + b * pl.OB + j0 + j;
-              pok[j] = qd < qd1;
-              oo[j] = o_row + (size_t)(qd * g.sout + g.rD) * plane_out;
-              if (a.aux_mode != 0 && pok[j]) {
-                if constexpr (COUT % 4 == 0) {
-#pragma unroll
-                  for (int i = 0; i < COUT / 4; ++i) {
-                    const float4 v = __ldg(reinterpret_cast<const float4*>(a.aux + oo[j]) + i);
-                    ax[j][4 * i] = v.x; ax[j][4 * i + 1] = v.y; ax[j][4 * i + 2] = v.z; ax[j][4 * i + 3] = v.w;
-                  }
-                } else {
-#pragma unroll
-                  for (int c = 0; c < COUT; ++c) ax[j][c] = __ldg(a.aux + oo[j] + c);
+                for (int i = 0; i < COUT / 4; ++i) {
+                  const float4 v = __ldg(reinterpret_cast<const float4*>(p) + i);
+                  ax[j][4 * i] = v.x; ax[j][4 * i + 1] = v.y; ax[j][4 * i + 2] = v.z; ax[j][4 * i + 3] = v.w;
                 }
+              } else {
+#pragma unroll
+                for (int c = 0; c < COUT; ++c) ax[j][c] = __ldg(p + c);
               }
             }
+          };
+          auto process = [&](const Item& I, const float (&ax)[NJ][COUT]) {
+            const uint32_t tcol = tmem_base + ((uint32_t)((etid >> 5) * 32) << 16) +
+                                  (uint32_t)((buf * pl.nrb + I.rb) * pl.ACCW + I.k * 16);
+            uint32_t rr[16];
+            tmem_ld16(tcol, rr);
+            tmem_ld_wait();
+            tmem_zero16(tcol);                    // drained: ready for the (block, phase) after next
+            if (!I.row_ok) return;
 #pragma unroll
-            for (int j = 0; j < JG; ++j) {
-              if (!pok[j]) continue;
+            for (int j = 0; j < NJ; ++j) {
+              if (I.qd + j >= qd_end) continue;
               float y[COUT];
 #pragma unroll
               for (int c = 0; c < COUT; ++c) {
-                float v = acc[j][c] + s_bias[c];
+                float v = __uint_as_float(rr[j * COUT + c]) + s_bias[c];
                 if (a.act == VG_ACT_RELU) v = fmaxf(v, 0.f);
                 else if (a.act == VG_ACT_SIGMOID) v = 1.f / (1.f + __expf(-v));
                 y[c] = v;
@@ -248,25 +251,38 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
                 }
               }
               if (a.out) {
+                float* p = a.out + I.o0 + (size_t)j * g.sout * plane_out;
                 if constexpr (COUT % 4 == 0) {
 #pragma unroll
                   for (int i = 0; i < COUT / 4; ++i)
-                    reinterpret_cast<float4*>(a.out + oo[j])[i] =
-                        make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+                    reinterpret_cast<float4*>(p)[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
                 } else {
 #pragma unroll
-                  for (int c = 0; c < COUT; ++c) a.out[oo[j] + c] = y[c];
+                  for (int c = 0; c < COUT; ++c) p[c] = y[c];
                 }
               }
             }
+          };
+          // items of this set, the auxiliary loads of the next item in flight while the current one is processed
+          Item I0, I1;
+          float ax0[NJ][COUT], ax1[NJ][COUT];
+          int it = eset;
+          if (it < nitems) { setup(it, I0); load_aux(I0, ax0); }
+          mbar_wait(smem_u32(&accf_bar[buf]), (uint32_t)((au >> 1) & 1));
+          tc_fence_after();
+          while (it < nitems) {
+            if (it + ES < nitems) { setup(it + ES, I1); load_aux(I1, ax1); }
+            process(I0, ax0);
+            it += ES;
+            if (it >= nitems) break;
+            if (it + ES < nitems) { setup(it + ES, I0); load_aux(I0, ax0); }
+            process(I1, ax1);
+            it += ES;
           }
-          // this row block of the buffer is drained: zero it for the block after next
-          for (int c = 0; c < pl.ACCW; c += 16) tmem_zero16(tacc + (uint32_t)c);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(smem_u32(&acce_bar[buf]));
         }
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(smem_u32(&acce_bar[buf]));
-      }
       if (want_stats || want_bn) {
         double* dst = (want_stats ? a.stats : a.aux_sums) + (size_t)grp * COUT * 2;
 #pragma unroll
@@ -280,16 +296,16 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
         }
       }
       pair_base += nblocks * H2 + (pl.NPAIR - H2);
-      block_base += nblocks;
+      acc_base += nblocks * pl.nph;
     }
-  } else if (warp < T2_EPI_WARPS + T2_PROD_WARPS) {
+  } else if (warp < T2_MMA_WARP) {
     // ================================================================ producer warps
-    const int ptid = tid - T2_EPI_WARPS * 32;
+    const int ptid = tid - EPI_WARPS * 32;
     const bool affine = a.in_scale != nullptr;
     const size_t plane_in = (size_t)g.inH * g.inW * CIN;
     for (int col = blockIdx.x; col < ncols; col += gridDim.x) {
       const int dc = col % pl.ndchunks, t = (col / pl.ndchunks) % pl.ntiles, n = col / (pl.ndchunks * pl.ntiles);
-      const int qd0 = dc * pl.dchunk, qd1 = min(g.qD, qd0 + pl.dchunk);
+      const int qd0 = dc * pl.dchunk, qd1 = min(pl.qDmax, qd0 + pl.dchunk);
       const int nblocks = (qd1 - qd0 + pl.OB - 1) / pl.OB;
       const int npairs = nblocks * H2 + (pl.NPAIR - H2);
       const int grp = n / g.group_size;
@@ -301,133 +317,155 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
         sh[c] = affine ? __ldg(a.in_shift + grp * CIN + c) : 0.f;
       }
       // the chunks this thread stages are the same for every plane of the column
-      int goff[T2_MAX_CHUNK];      // CIN 8: float offset of the voxel inside its plane; -2 zero chunk; -1 none
-      int wlim[T2_MAX_CHUNK];      // CIN 1: number of in-range w elements of the chunk
+      int goff[MAXC];      // float offset of the chunk's first voxel inside its plane; -2 zero chunk; -1 none
+      int wlim[MAXC];      // CIN 1: number of in-range w elements of the chunk
 #pragma unroll
-      for (int k = 0; k < T2_MAX_CHUNK; ++k) {
-        const int s = ptid + k * T2_PROD_THREADS;
+      for (int k = 0; k < MAXC; ++k) {
+        const int s = ptid + k * PT;
         goff[k] = -1; wlim[k] = 0;
         if (s < pl.SR) {
           const int rr = t * pl.TR + s;
           const int hh = rr / pl.PW, ww = rr - hh * pl.PW;
           const int ih = hh + pl.lo_h, iw = ww + pl.lo_w;
           goff[k] = -2;
-          if constexpr (CIN == 1) {
-            if (ih >= 0 && ih < g.inH && iw >= 0 && iw < g.inW) {
-              goff[k] = ih * g.inW + iw;
-              wlim[k] = min(pl.span_w + 1, g.inW - iw);
-            }
-          } else {
-            if (ih >= 0 && ih < g.inH && iw >= 0 && iw < g.inW) goff[k] = (ih * g.inW + iw) * CIN;
+          if (ih >= 0 && ih < g.inH && iw >= 0 && iw < g.inW) {
+            goff[k] = (ih * g.inW + iw) * CIN;
+            wlim[k] = min(pl.span_w + 1, g.inW - iw);
           }
         }
       }
-      for (int P = 0; P < npairs; ++P) {
-        const int G = pair_base + P, slot = G % pl.R, use = G / pl.R;
-        if (use > 0) mbar_wait(smem_u32(&empty_bar[slot]), (uint32_t)((use - 1) & 1));
-        uint8_t* dst0 = ring + (size_t)slot * PAIRB;
-        if constexpr (CIN == 8) {
-          float4 v[2][T2_MAX_CHUNK][2];
-          bool ok[2][T2_MAX_CHUNK];
+      using Buf = typename std::conditional<CIN == 8, float4[2][MAXC][2], float[2][MAXC][3]>::type;
+      auto load_pair = [&](int P, Buf& v) {
 #pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            const int ip = qd0 + pl.lo_d + 2 * P + hf;
-            const bool p_ok = ip >= 0 && ip < g.inD;
-            const float* base = in_n + (size_t)(p_ok ? ip : 0) * plane_in;
+        for (int hf = 0; hf < 2; ++hf) {
+          const int ip = qd0 + pl.lo_d + 2 * P + hf;
+          const bool p_ok = ip >= 0 && ip < g.inD;
+          const float* base = in_n + (size_t)(p_ok ? ip : 0) * plane_in;
 #pragma unroll
-            for (int k = 0; k < T2_MAX_CHUNK; ++k) {
-              ok[hf][k] = p_ok && goff[k] >= 0;
-              if (ok[hf][k]) {
+          for (int k = 0; k < MAXC; ++k) {
+            if constexpr (CIN == 8) {
+              if (p_ok && goff[k] >= 0) {
                 const float4* p = reinterpret_cast<const float4*>(base + goff[k]);
                 v[hf][k][0] = __ldg(p);
                 v[hf][k][1] = __ldg(p + 1);
               }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 3; ++e) {
+                v[hf][k][e] = 0.f;
+                if (p_ok && goff[k] >= 0 && e < wlim[k]) v[hf][k][e] = __ldg(base + goff[k] + e);
+              }
             }
           }
+        }
+      };
+      auto store_pair = [&](int P, const Buf& v) {
+        const int G = pair_base + P, slot = G % pl.R, use = G / pl.R;
+        if (use > 0) mbar_wait(smem_u32(&empty_bar[slot]), (uint32_t)((use - 1) & 1));
+        uint8_t* dst0 = ring + (size_t)slot * PAIRB;
 #pragma unroll
-          for (int hf = 0; hf < 2; ++hf)
+        for (int hf = 0; hf < 2; ++hf) {
+          const int ip = qd0 + pl.lo_d + 2 * P + hf;
+          const bool p_ok = ip >= 0 && ip < g.inD;
 #pragma unroll
-            for (int k = 0; k < T2_MAX_CHUNK; ++k) {
-              if (goff[k] == -1) continue;
-              uint4 pk = make_uint4(0u, 0u, 0u, 0u);
-              if (ok[hf][k]) {
+          for (int k = 0; k < MAXC; ++k) {
+            if (goff[k] == -1) continue;
+            uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+            if (p_ok && goff[k] >= 0) {
+              if constexpr (CIN == 8) {
                 const float4 lo = v[hf][k][0], hi = v[hf][k][1];
                 pk = make_uint4(pack_bf16(fmaf(lo.x, sc[0], sh[0]), fmaf(lo.y, sc[1], sh[1])),
                                 pack_bf16(fmaf(lo.z, sc[2], sh[2]), fmaf(lo.w, sc[3], sh[3])),
                                 pack_bf16(fmaf(hi.x, sc[4], sh[4]), fmaf(hi.y, sc[5], sh[5])),
                                 pack_bf16(fmaf(hi.z, sc[6], sh[6]), fmaf(hi.w, sc[7], sh[7])));
+              } else {
+                // one input channel: the K-chunk of a row is its own voxel and the next span_w voxels along w
+                float f[3];
+#pragma unroll
+                for (int e = 0; e < 3; ++e) f[e] = e < wlim[k] ? fmaf(v[hf][k][e], sc[0], sh[0]) : 0.f;
+                pk = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], 0.f), 0u, 0u);
               }
-              *reinterpret_cast<uint4*>(dst0 + (size_t)hf * SRB + (size_t)(ptid + k * T2_PROD_THREADS) * 16) = pk;
             }
-        } else {
-          // one input channel: the K-chunk of a row is its own voxel and the next span_w voxels along w
-          float v[2][T2_MAX_CHUNK][3];
-#pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            const int ip = qd0 + pl.lo_d + 2 * P + hf;
-            const bool p_ok = ip >= 0 && ip < g.inD;
-            const float* base = in_n + (size_t)(p_ok ? ip : 0) * plane_in;
-#pragma unroll
-            for (int k = 0; k < T2_MAX_CHUNK; ++k)
-#pragma unroll
-              for (int e = 0; e < 3; ++e) {
-                v[hf][k][e] = 0.f;
-                if (p_ok && goff[k] >= 0 && e < wlim[k]) v[hf][k][e] = fmaf(__ldg(base + goff[k] + e), sc[0], sh[0]);
-              }
+            *reinterpret_cast<uint4*>(dst0 + (size_t)hf * SRB + (size_t)(ptid + k * PT) * 16) = pk;
           }
-#pragma unroll
-          for (int hf = 0; hf < 2; ++hf)
-#pragma unroll
-            for (int k = 0; k < T2_MAX_CHUNK; ++k) {
-              if (goff[k] == -1) continue;
-              const uint4 pk = make_uint4(pack_bf16(v[hf][k][0], v[hf][k][1]), pack_bf16(v[hf][k][2], 0.f), 0u, 0u);
-              *reinterpret_cast<uint4*>(dst0 + (size_t)hf * SRB + (size_t)(ptid + k * T2_PROD_THREADS) * 16) = pk;
-            }
         }
         fence_async_smem();
         mbar_arrive(smem_u32(&full_bar[slot]));
+      };
+      if constexpr (PIPE) {
+        Buf v0, v1;
+        load_pair(0, v0);
+        for (int P = 0; P < npairs; P += 2) {
+          if (P + 1 < npairs) load_pair(P + 1, v1);
+          store_pair(P, v0);
+          if (P + 1 < npairs) {
+            if (P + 2 < npairs) load_pair(P + 2, v0);
+            store_pair(P + 1, v1);
+          }
+        }
+      } else {
+        Buf v0;
+        for (int P = 0; P < npairs; ++P) {
+          load_pair(P, v0);
+          store_pair(P, v0);
+        }
       }
       pair_base += npairs;
-      block_base += nblocks;
+      acc_base += nblocks * pl.nph;
     }
-  } else if (lane == 0) {
-    // ================================================================ MMA issuer (one thread)
-    const uint32_t ring_addr = smem_u32(ring), w_addr = smem_u32(wts);
+  } else {
+    // ================================================================ MMA warp
+    // The whole warp walks the loops (uniform control flow, waits included); one elected lane
+    // issues the tcgen05.mma / tcgen05.commit instructions, so operands stay in uniform registers.
+    const uint32_t ring16 = smem_u32(ring) >> 4;
+    const uint32_t lbo_field = ((uint32_t)SRB >> 4) << 16;
+    const uint32_t a_hi = (128u >> 4) | (1u << 14), b_hi = (256u >> 4) | (1u << 14);
     for (int col = blockIdx.x; col < ncols; col += gridDim.x) {
       const int dc = col % pl.ndchunks;
-      const int qd0 = dc * pl.dchunk, qd1 = min(g.qD, qd0 + pl.dchunk);
+      const int qd0 = dc * pl.dchunk, qd1 = min(pl.qDmax, qd0 + pl.dchunk);
       const int nblocks = (qd1 - qd0 + pl.OB - 1) / pl.OB;
-      for (int b = 0; b < nblocks; ++b) {
-        const int bg = block_base + b, buf = bg & 1;
-        mbar_wait(smem_u32(&acce_bar[buf]), (uint32_t)(((bg >> 1) & 1) ^ 1));
-        tc_fence_after();
-        for (int p = 0; p < pl.NPAIR; ++p) {
-          const int G = pair_base + b * H2 + p, slot = G % pl.R, use = G / pl.R;
-          mbar_wait(smem_u32(&full_bar[slot]), (uint32_t)(use & 1));
+      for (int b = 0; b < nblocks; ++b)
+        for (int ph = 0; ph < pl.nph; ++ph) {
+          const int au = acc_base + b * pl.nph + ph, buf = au & 1;
+          mbar_wait(smem_u32(&acce_bar[buf]), (uint32_t)(((au >> 1) & 1) ^ 1));
           tc_fence_after();
-          const uint32_t a_slot = ring_addr + (uint32_t)slot * (uint32_t)PAIRB;
-          for (int m = pl.pair_begin[p]; m < pl.pair_begin[p + 1]; ++m) {
-            const T2Mma mm = pl.mma[m];
-            const uint64_t bdesc = umma_desc(w_addr + (uint32_t)mm.b_off16 * 16u, 128u, 256u);
-            const uint32_t idesc = umma_idesc_m128((uint32_t)mm.n8 << 3);
-            for (int rb = 0; rb < pl.nrb; ++rb) {
-              const uint64_t adesc = umma_desc(a_slot + (uint32_t)(rb * 128 + mm.a_shift) * 16u, (uint32_t)SRB, 128u);
-              umma_bf16(tmem_base + (uint32_t)((buf * pl.nrb + rb) * pl.ACCW + mm.dcol), adesc, bdesc, idesc, 1u);
+          const uint32_t d_buf = tmem_base + (uint32_t)(buf * pl.nrb * pl.ACCW);
+          const bool last_ph = ph == pl.nph - 1;
+          for (int p = 0; p < pl.NPAIR; ++p) {
+            const int G = pair_base + b * H2 + p, slot = G % pl.R, use = G / pl.R;
+            if (ph == 0) {
+              mbar_wait(smem_u32(&full_bar[slot]), (uint32_t)(use & 1));
+              tc_fence_after();
             }
+            if (elect_one()) {
+              const uint32_t a_lo0 = ((ring16 + (uint32_t)slot * ((uint32_t)PAIRB >> 4)) & 0x3FFFu) | lbo_field;
+              const int m1 = pl.ph[ph].pair_begin[p + 1];
+#pragma unroll 2
+              for (int m = pl.ph[ph].pair_begin[p]; m < m1; ++m) {
+                const uint4 e = s_mma[m];
+                uint32_t a_lo = a_lo0 + e.x, d = d_buf + e.w;
+                const uint64_t bdesc = ((uint64_t)b_hi << 32) | e.y;
+                for (int rb = 0; rb < pl.nrb; ++rb) {
+                  umma_bf16(d, ((uint64_t)a_hi << 32) | a_lo, bdesc, e.z, 1u);
+                  a_lo += 128u;                   // next 128 rows (16-byte units)
+                  d += (uint32_t)pl.ACCW;
+                }
+              }
+              if (last_ph && (p < H2 || b == nblocks - 1)) umma_commit(smem_u32(&empty_bar[slot]));
+              if (p == pl.NPAIR - 1) umma_commit(smem_u32(&accf_bar[buf]));
+            }
+            __syncwarp();
           }
-          if (p < H2 || b == nblocks - 1) umma_commit(smem_u32(&empty_bar[slot]));
         }
-        umma_commit(smem_u32(&accf_bar[buf]));
-      }
       pair_base += nblocks * H2 + (pl.NPAIR - H2);
-      block_base += nblocks;
+      acc_base += nblocks * pl.nph;
     }
   }
 
   // ---------------------------------------------------------------- teardown
   tc_fence_before();
   __syncthreads();
-  if (warp == T2_EPI_WARPS + T2_PROD_WARPS) {
+  if (warp == T2_MMA_WARP) {
     tc_fence_after();
     switch (pl.tmem_cols) {
       case 32: asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(tmem_base)); break;
@@ -440,94 +478,135 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
 }
 
 // ------------------------------------------------------------------------------- host planner
-static constexpr int kT2SmemBudget = 214 * 1024;
+static constexpr int kT2SmemBudget = 212 * 1024;
 
-static bool t2_build_plan(int cin, int cout, const Geom& g, T2Plan& pl) {
-  if (g.sin != 1 || g.ntaps < 1) return false;
+// gs[0..ng): the gathers of one layer pass that share their input (ng > 1: output-parity phases).
+// merged: gs[0] with every phase's taps (Tap::pad_ = phase).
+static bool t2_build_plan(int cin, int cout, const Geom* gs, int ng, Geom& merged, T2Plan& pl) {
+  if (ng < 1 || ng > T2_MAX_PH) return false;
   if (cin != 1 && cin != 8) return false;
   if (cout != 1 && cout != 8 && cout != 16) return false;
+  merged = gs[0];
+  int ntaps = 0;
   int lo[3] = {127, 127, 127}, hi[3] = {-127, -127, -127};
-  for (int t = 0; t < g.ntaps; ++t) {
-    const int o[3] = {g.taps[t].dd, g.taps[t].dh, g.taps[t].dw};
-    for (int i = 0; i < 3; ++i) { lo[i] = o[i] < lo[i] ? o[i] : lo[i]; hi[i] = o[i] > hi[i] ? o[i] : hi[i]; }
+  int qmax[3] = {0, 0, 0};
+  for (int p = 0; p < ng; ++p) {
+    const Geom& g = gs[p];
+    if (g.sin != 1 || g.ntaps < 1 || g.sout != gs[0].sout) return false;
+    if (g.inD != gs[0].inD || g.inH != gs[0].inH || g.inW != gs[0].inW) return false;
+    if (g.qD > 32767 || g.qH > 32767 || g.qW > 32767) return false;
+    for (int t = 0; t < g.ntaps; ++t) {
+      if (ntaps >= kMaxTaps) return false;
+      merged.taps[ntaps] = g.taps[t];
+      merged.taps[ntaps].pad_ = (int8_t)p;
+      ++ntaps;
+      const int o[3] = {g.taps[t].dd, g.taps[t].dh, g.taps[t].dw};
+      for (int i = 0; i < 3; ++i) { lo[i] = o[i] < lo[i] ? o[i] : lo[i]; hi[i] = o[i] > hi[i] ? o[i] : hi[i]; }
+    }
+    qmax[0] = g.qD > qmax[0] ? g.qD : qmax[0];
+    qmax[1] = g.qH > qmax[1] ? g.qH : qmax[1];
+    qmax[2] = g.qW > qmax[2] ? g.qW : qmax[2];
+    pl.ph[p].qD = (int16_t)g.qD; pl.ph[p].qH = (int16_t)g.qH; pl.ph[p].qW = (int16_t)g.qW;
+    pl.ph[p].rD = (int8_t)g.rD; pl.ph[p].rH = (int8_t)g.rH; pl.ph[p].rW = (int8_t)g.rW;
   }
+  merged.ntaps = ntaps;
+  pl.nph = ng;
   pl.lo_d = lo[0]; pl.lo_h = lo[1]; pl.lo_w = lo[2];
   pl.span_d = hi[0] - lo[0]; pl.span_h = hi[1] - lo[1]; pl.span_w = hi[2] - lo[2];
   if (pl.span_d > 2 || pl.span_h > 2 || pl.span_w > 2) return false;
-  int lut[45];
-  for (int i = 0; i < 45; ++i) lut[i] = -1;
-  for (int t = 0; t < g.ntaps; ++t)
-    lut[(g.taps[t].dd - lo[0]) * 9 + (g.taps[t].dh - lo[1]) * 3 + (g.taps[t].dw - lo[2])] = g.taps[t].widx;
+  int lut[T2_MAX_PH][45];
+  for (int p = 0; p < ng; ++p)
+    for (int i = 0; i < 45; ++i) lut[p][i] = -1;
+  for (int t = 0; t < ntaps; ++t) {
+    const Tap& tp = merged.taps[t];
+    lut[tp.pad_][(tp.dd - lo[0]) * 9 + (tp.dh - lo[1]) * 3 + (tp.dw - lo[2])] = tp.widx;
+  }
 
-  pl.PW = cin == 1 ? g.qW : g.qW + pl.span_w;
-  pl.RTOT = g.qH * pl.PW;
+  pl.PW = cin == 1 ? qmax[2] : qmax[2] + pl.span_w;
+  pl.RTOT = qmax[1] * pl.PW;
+  pl.qDmax = qmax[0];
   pl.OB = cout == 1 ? 16 : 8;
   pl.NPAIR = (pl.OB + pl.span_d + 1) / 2;
   pl.ACCW = pl.OB * cout;
   if (pl.NPAIR > T2_MAX_PAIR) return false;
 
   // MMA list + weight blocks (deduplicated: interior pairs share one shift-invariant block)
-  struct Key { int rel, nj, dh, dw, off16; };
+  struct Key { int ph, rel, nj, dh, dw, off16; };
   Key keys[T2_MAX_BLK];
   int nblk = 0, nmma = 0, woff = 0;
-  for (int p = 0; p < pl.NPAIR; ++p) {
-    pl.pair_begin[p] = nmma;
-    const int j0 = cout == 1 ? 0 : (2 * p - 2 > 0 ? 2 * p - 2 : 0);
-    const int j1 = cout == 1 ? pl.OB - 1 : (2 * p + 1 < pl.OB - 1 ? 2 * p + 1 : pl.OB - 1);
-    if (j1 < j0) continue;
-    const int nj = j1 - j0 + 1;
-    for (int dh = 0; dh <= pl.span_h; ++dh)
-      for (int dw = 0; dw <= (cin == 1 ? 0 : pl.span_w); ++dw) {
-        bool any = false;                       // does the block hold any tap?
-        for (int chunk = 0; chunk < 2 && !any; ++chunk)
-          for (int j = j0; j <= j1 && !any; ++j) {
-            const int ddr = 2 * p + chunk - j;
-            if (ddr < 0 || ddr > pl.span_d) continue;
-            for (int e = 0; e <= (cin == 1 ? pl.span_w : 0); ++e)
-              if (lut[ddr * 9 + dh * 3 + (cin == 1 ? e : dw)] >= 0) any = true;
+  for (int ph = 0; ph < ng; ++ph)
+    for (int p = 0; p <= pl.NPAIR; ++p) {
+      if (nmma > 255) return false;
+      pl.ph[ph].pair_begin[p] = (uint8_t)nmma;
+      if (p == pl.NPAIR) break;
+      const int j0 = cout == 1 ? 0 : (2 * p - 2 > 0 ? 2 * p - 2 : 0);
+      const int j1 = cout == 1 ? pl.OB - 1 : (2 * p + 1 < pl.OB - 1 ? 2 * p + 1 : pl.OB - 1);
+      if (j1 < j0) continue;
+      const int nj = j1 - j0 + 1;
+      for (int dh = 0; dh <= pl.span_h; ++dh)
+        for (int dw = 0; dw <= (cin == 1 ? 0 : pl.span_w); ++dw) {
+          bool any = false;                       // does the block hold any tap?
+          for (int chunk = 0; chunk < 2 && !any; ++chunk)
+            for (int j = j0; j <= j1 && !any; ++j) {
+              const int ddr = 2 * p + chunk - j;
+              if (ddr < 0 || ddr > pl.span_d) continue;
+              for (int e = 0; e <= (cin == 1 ? pl.span_w : 0); ++e)
+                if (lut[ph][ddr * 9 + dh * 3 + (cin == 1 ? e : dw)] >= 0) any = true;
+            }
+          if (!any) continue;
+          int found = -1;
+          for (int k = 0; k < nblk; ++k)
+            if (keys[k].ph == ph && keys[k].rel == 2 * p - j0 && keys[k].nj == nj && keys[k].dh == dh && keys[k].dw == dw)
+              found = k;
+          if (found < 0) {
+            if (nblk >= T2_MAX_BLK) return false;
+            found = nblk++;
+            keys[found] = Key{ph, 2 * p - j0, nj, dh, dw, woff >> 4};
+            pl.blk[found].i0 = (int8_t)(2 * p); pl.blk[found].j0 = (int8_t)j0; pl.blk[found].nj = (int8_t)nj;
+            pl.blk[found].dh = (int8_t)dh; pl.blk[found].dw = (int8_t)dw; pl.blk[found].ph = (int8_t)ph;
+            pl.blk_off16[found] = (uint16_t)(woff >> 4);
+            woff += nj * cout * 32;
           }
-        if (!any) continue;
-        int found = -1;
-        for (int k = 0; k < nblk; ++k)
-          if (keys[k].rel == 2 * p - j0 && keys[k].nj == nj && keys[k].dh == dh && keys[k].dw == dw) found = k;
-        if (found < 0) {
-          if (nblk >= T2_MAX_BLK) return false;
-          found = nblk++;
-          keys[found] = Key{2 * p - j0, nj, dh, dw, woff >> 4};
-          pl.blk[found].i0 = (int8_t)(2 * p); pl.blk[found].j0 = (int8_t)j0; pl.blk[found].nj = (int8_t)nj;
-          pl.blk[found].dh = (int8_t)dh; pl.blk[found].dw = (int8_t)dw;
-          pl.blk_off16[found] = (uint16_t)(woff >> 4);
-          woff += nj * cout * 32;
+          if (nmma >= T2_MAX_MMA) return false;
+          T2Mma& m = pl.mma[nmma++];
+          m.a_shift = (uint16_t)(dh * pl.PW + (cin == 1 ? 0 : dw));
+          m.b_off16 = (uint16_t)keys[found].off16;
+          m.n8 = (uint8_t)((nj * cout) >> 3);
+          m.dcol = (uint8_t)(j0 * cout);
         }
-        if (nmma >= T2_MAX_MMA) return false;
-        T2Mma& m = pl.mma[nmma++];
-        m.a_shift = (uint16_t)(dh * pl.PW + (cin == 1 ? 0 : dw));
-        m.b_off16 = (uint16_t)keys[found].off16;
-        m.n8 = (uint8_t)((nj * cout) >> 3);
-        m.dcol = (uint8_t)(j0 * cout);
-      }
-  }
-  pl.pair_begin[pl.NPAIR] = nmma;
+    }
+  pl.nmma = nmma;
   pl.nblk = nblk;
   pl.wbytes = (woff + 1023) & ~1023;
+  if (pl.wbytes > 96 * 1024) return false;
 
-  // rows per tile: as many 128-row blocks as TMEM (2 buffers) and shared memory allow
-  int nrb = 512 / (2 * pl.ACCW);
-  if (nrb > 4) nrb = 4;
+  // rows per tile: as many 128-row blocks as TMEM (2 buffers), the producers' reach and shared memory allow
+  const int es = t2_epi_sets(cin, cout);
+  const int max_sr = t2_max_chunk(cin, es) * (12 - 4 * es) * 32;
+  int nrb_max = 512 / (2 * pl.ACCW);
+  if (nrb_max > 4) nrb_max = 4;
   const int need = (pl.RTOT + 127) / 128;
-  if (nrb > need) nrb = need;
-  for (;; --nrb) {
-    if (nrb < 1) return false;
-    pl.nrb = nrb;
-    pl.TR = 128 * nrb;
-    pl.SR = pl.TR + pl.span_h * pl.PW + (cin == 1 ? 0 : pl.span_w);
-    pl.SR = (pl.SR + 7) & ~7;
-    pl.R = pl.NPAIR + 3;
-    if (pl.R > T2_MAX_RING) pl.R = T2_MAX_RING;
-    if (pl.SR > T2_MAX_CHUNK * T2_PROD_THREADS) continue;
-    while (pl.R > pl.NPAIR + 1 && (size_t)pl.R * 2 * pl.SR * 16 + pl.wbytes > (size_t)kT2SmemBudget) --pl.R;
-    if ((size_t)pl.R * 2 * pl.SR * 16 + pl.wbytes <= (size_t)kT2SmemBudget) break;
+  if (nrb_max > need) nrb_max = need;
+  int best = 0, best_r = 0;
+  double best_eff = 0.0;
+  for (int nrb = nrb_max; nrb >= 1; --nrb) {
+    const int tr = 128 * nrb;
+    const int sr = (tr + pl.span_h * pl.PW + (cin == 1 ? 0 : pl.span_w) + 7) & ~7;
+    if (sr > max_sr) continue;
+    int r = pl.NPAIR + 3;
+    if (r > T2_MAX_RING) r = T2_MAX_RING;
+    while (r > pl.NPAIR + 1 && (size_t)r * 2 * sr * 16 + pl.wbytes > (size_t)kT2SmemBudget) --r;
+    if ((size_t)r * 2 * sr * 16 + pl.wbytes > (size_t)kT2SmemBudget) continue;
+    const int nt = (pl.RTOT + tr - 1) / tr;
+    // useful rows per staged row: tile quantisation and the h-halo that every tile re-stages
+    const double eff = (double)pl.RTOT / ((double)nt * sr);
+    if (eff > best_eff * 1.03) { best_eff = eff; best = nrb; best_r = r; }
   }
+  if (best < 1) return false;
+  pl.nrb = best;
+  pl.TR = 128 * best;
+  pl.SR = (pl.TR + pl.span_h * pl.PW + (cin == 1 ? 0 : pl.span_w) + 7) & ~7;
+  pl.R = best_r;
   pl.ntiles = (pl.RTOT + pl.TR - 1) / pl.TR;
   int tc = 32;
   while (tc < 2 * pl.nrb * pl.ACCW) tc <<= 1;
@@ -535,32 +614,34 @@ static bool t2_build_plan(int cin, int cout, const Geom& g, T2Plan& pl) {
   pl.tmem_cols = tc;
 
   // split columns along d until the persistent grid has at least ~2 columns per SM
-  const int nblocks_all = (g.qD + pl.OB - 1) / pl.OB;
-  const long long cols = (long long)g.N * pl.ntiles;
+  const int nblocks_all = (pl.qDmax + pl.OB - 1) / pl.OB;
+  const long long cols = (long long)merged.N * pl.ntiles;
   const long long want = 2LL * vg_sm_count();
   int nch = (int)((want + cols - 1) / cols);
   if (nch > nblocks_all) nch = nblocks_all;
   if (nch < 1) nch = 1;
   pl.dchunk = ((nblocks_all + nch - 1) / nch) * pl.OB;
-  pl.ndchunks = (g.qD + pl.dchunk - 1) / pl.dchunk;
+  pl.ndchunks = (pl.qDmax + pl.dchunk - 1) / pl.dchunk;
   return true;
 }
 
-bool tc2_supported(int cin, int cout, const Geom& g) {
-  T2Plan pl{};
-  return t2_build_plan(cin, cout, g, pl);
+bool tc2_supported(int cin, int cout, const Geom* gs, int ng) {
+  T2Plan pl;
+  Geom merged;
+  return t2_build_plan(cin, cout, gs, ng, merged, pl);
 }
 
 // human-readable plan (vg_conv_describe): tile shape, ring, MMA list size, shared memory
-int tc2_describe(int cin, int cout, const Geom& g, char* buf, size_t cap) {
-  T2Plan pl{};
-  if (!t2_build_plan(cin, cout, g, pl)) return 0;
-  const long long cols = (long long)g.N * pl.ntiles * pl.ndchunks;
+int tc2_describe(int cin, int cout, const Geom* gs, int ng, char* buf, size_t cap) {
+  T2Plan pl;
+  Geom merged;
+  if (!t2_build_plan(cin, cout, gs, ng, merged, pl)) return 0;
+  const long long cols = (long long)merged.N * pl.ntiles * pl.ndchunks;
   return snprintf(buf, cap,
-                  "tc2 cin=%d cout=%d q=(%d,%d,%d) taps=%d PW=%d RTOT=%d TR=%d ntiles=%d SR=%d OB=%d NPAIR=%d R=%d ACCW=%d "
-                  "tmem=%d nmma=%d nblk=%d wbytes=%d smem=%zu dchunk=%d ndchunks=%d cols=%lld",
-                  cin, cout, g.qD, g.qH, g.qW, g.ntaps, pl.PW, pl.RTOT, pl.TR, pl.ntiles, pl.SR, pl.OB, pl.NPAIR, pl.R,
-                  pl.ACCW, pl.tmem_cols, pl.pair_begin[pl.NPAIR], pl.nblk, pl.wbytes,
+                  "tc2 cin=%d cout=%d phases=%d q=(%d,%d,%d) taps=%d PW=%d RTOT=%d TR=%d ntiles=%d SR=%d OB=%d NPAIR=%d R=%d "
+                  "ACCW=%d tmem=%d nmma=%d nblk=%d wbytes=%d smem=%zu dchunk=%d ndchunks=%d cols=%lld",
+                  cin, cout, ng, pl.qDmax, pl.RTOT / pl.PW, merged.qW, merged.ntaps, pl.PW, pl.RTOT, pl.TR, pl.ntiles,
+                  pl.SR, pl.OB, pl.NPAIR, pl.R, pl.ACCW, pl.tmem_cols, pl.nmma, pl.nblk, pl.wbytes,
                   (size_t)pl.R * 2 * pl.SR * 16 + pl.wbytes, pl.dchunk, pl.ndchunks, cols);
 }
 
@@ -576,14 +657,15 @@ static int launch_tc2_t(const Geom& g, const GatherArgs& a, const T2Plan& pl, cu
   return VG_OK;
 }
 
-int launch_tc2_gather(int cin, int cout, const Geom& g, const GatherArgs& a, cudaStream_t st) {
-  T2Plan pl{};
-  if (!t2_build_plan(cin, cout, g, pl)) { set_error("plane-folded tensor-core path: unsupported geometry"); return VG_EINVAL; }
-  if (cin == 1 && cout == 8) return launch_tc2_t<1, 8>(g, a, pl, st);
-  if (cin == 1 && cout == 16) return launch_tc2_t<1, 16>(g, a, pl, st);
-  if (cin == 8 && cout == 1) return launch_tc2_t<8, 1>(g, a, pl, st);
-  if (cin == 8 && cout == 8) return launch_tc2_t<8, 8>(g, a, pl, st);
-  if (cin == 8 && cout == 16) return launch_tc2_t<8, 16>(g, a, pl, st);
+int launch_tc2_gather(int cin, int cout, const Geom* gs, int ng, const GatherArgs& a, cudaStream_t st) {
+  T2Plan pl;
+  Geom merged;
+  if (!t2_build_plan(cin, cout, gs, ng, merged, pl)) { set_error("plane-folded tensor-core path: unsupported geometry"); return VG_EINVAL; }
+  if (cin == 1 && cout == 8) return launch_tc2_t<1, 8>(merged, a, pl, st);
+  if (cin == 1 && cout == 16) return launch_tc2_t<1, 16>(merged, a, pl, st);
+  if (cin == 8 && cout == 1) return launch_tc2_t<8, 1>(merged, a, pl, st);
+  if (cin == 8 && cout == 8) return launch_tc2_t<8, 8>(merged, a, pl, st);
+  if (cin == 8 && cout == 16) return launch_tc2_t<8, 16>(merged, a, pl, st);
   set_error("plane-folded tensor-core path: unsupported channel pair (%d,%d)", cin, cout);
   return VG_EINVAL;
 }
