@@ -16,13 +16,16 @@
 // inside K).  A stride-2 transposed layer is ONE launch: its (up to 8) output-parity phases share
 // the staged input planes and differ only in their MMA lists, weight blocks and output offsets.
 //
-// Roles (416 threads, one persistent CTA per SM), ES = 1 or 2 epilogue sets:
+// Roles (512 threads, one persistent CTA per SM), ES = 1 or 2 epilogue sets:
 //   warps [0, 4*ES)      epilogue: tcgen05.ld -> bias / activation / BatchNorm statistics / backward
 //                        masks -> global; re-zero the accumulator columns (all MMAs accumulate)
 //   warps [4*ES, 12)     producers: fp32 global -> BatchNorm fold -> bf16 -> ring of plane pairs
-//   warp 12              one elected lane issues the tcgen05.mma list of a (block, phase)
+//   warps 12..15         one per 128-row block of the tile: an elected lane issues the block's
+//                        tcgen05.mma list of a (block, phase)
 // Pipelines: full/empty mbarriers per ring slot (producers <-> MMA via tcgen05.commit), and
 // full/empty per accumulator buffer (MMA <-> epilogue), accumulators double-buffered in TMEM.
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "common.cuh"
@@ -31,15 +34,16 @@
 
 namespace vg {
 
-constexpr int T2_THREADS = 13 * 32, T2_MMA_WARP = 12;
-constexpr int T2_MAX_MMA = 128, T2_MAX_BLK = 128, T2_MAX_PAIR = 10, T2_MAX_RING = 16, T2_MAX_PH = 8;
+constexpr int T2_THREADS = 16 * 32, T2_MMA_WARP = 12;   // warps 12..15: one MMA issuer per 128-row block
+constexpr int T2_MAX_MMA = 96, T2_MAX_BLK = 96, T2_MAX_PAIR = 10, T2_MAX_RING = 16, T2_MAX_PH = 8;
 
+// One tcgen05.mma of the list, pre-digested on the host so that the issuing lane only adds bases
+// (the table sits in the kernel parameters = constant bank, read straight into uniform registers).
 struct T2Mma {
-  uint16_t a_shift;    // row shift of the A window inside the staged plane
-  uint16_t b_off16;    // weight block offset / 16 bytes
-  uint8_t n8;          // N >> 3
-  uint8_t dcol;        // first accumulator column
-  uint8_t pad[2];
+  uint32_t a_shift;    // row shift of the A window inside the staged plane (16-byte units)
+  uint32_t b_lo;       // low descriptor word of the weight block relative to the weight area: offset/16 | LBO field
+  uint32_t idesc;      // instruction descriptor (M = 128, N = nj * cout)
+  uint32_t dcol;       // first accumulator column
 };
 struct T2Blk {
   int8_t i0, j0, nj, dh, dw, ph, pad[2];   // window plane of K-chunk 0; output planes [j0, j0+nj); taps relative to lo_*
@@ -80,7 +84,6 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
   __shared__ uint32_t tmem_base_s;
   __shared__ int lut[T2_MAX_PH][45];
   __shared__ float s_bias[16];
-  __shared__ uint4 s_mma[T2_MAX_MMA];           // {A row shift, B descriptor low word, instruction descriptor, D column}
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int SRB = pl.SR * 16;                   // bytes per staged plane
@@ -93,22 +96,16 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
   if (tid == 0) {
     for (int s = 0; s < pl.R; ++s) {
       mbar_init(smem_u32(&full_bar[s]), PT);
-      mbar_init(smem_u32(&empty_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), (uint32_t)pl.nrb);
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(smem_u32(&accf_bar[b]), 1);
+      mbar_init(smem_u32(&accf_bar[b]), (uint32_t)pl.nrb);
       mbar_init(smem_u32(&acce_bar[b]), EPI_WARPS * 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
   for (int i = tid; i < T2_MAX_PH * 45; i += T2_THREADS) (&lut[0][0])[i] = -1;
   if (tid < 16) s_bias[tid] = (a.bias && tid < COUT) ? __ldg(a.bias + tid) : 0.f;
-  if (tid < pl.nmma) {
-    const T2Mma mm = pl.mma[tid];
-    const uint32_t w16 = (smem_u32(smem) + (uint32_t)pl.R * (uint32_t)PAIRB) >> 4;
-    s_mma[tid] = make_uint4((uint32_t)mm.a_shift, ((w16 + mm.b_off16) & 0x3FFFu) | (8u << 16),
-                            umma_idesc_m128((uint32_t)mm.n8 << 3), (uint32_t)mm.dcol);
-  }
   if (warp == T2_MMA_WARP) {
     const uint32_t dst = smem_u32(&tmem_base_s);
     switch (pl.tmem_cols) {
@@ -413,11 +410,12 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
       pair_base += npairs;
       acc_base += nblocks * pl.nph;
     }
-  } else {
-    // ================================================================ MMA warp
+  } else if (warp - T2_MMA_WARP < pl.nrb) {
+    // ================================================================ MMA warps (one per 128-row block)
     // The whole warp walks the loops (uniform control flow, waits included); one elected lane
     // issues the tcgen05.mma / tcgen05.commit instructions, so operands stay in uniform registers.
-    const uint32_t ring16 = smem_u32(ring) >> 4;
+    const int rb = warp - T2_MMA_WARP;
+    const uint32_t ring16 = (smem_u32(ring) >> 4) + (uint32_t)rb * 128u, w16 = smem_u32(wts) >> 4;
     const uint32_t lbo_field = ((uint32_t)SRB >> 4) << 16;
     const uint32_t a_hi = (128u >> 4) | (1u << 14), b_hi = (256u >> 4) | (1u << 14);
     for (int col = blockIdx.x; col < ncols; col += gridDim.x) {
@@ -429,7 +427,7 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
           const int au = acc_base + b * pl.nph + ph, buf = au & 1;
           mbar_wait(smem_u32(&acce_bar[buf]), (uint32_t)(((au >> 1) & 1) ^ 1));
           tc_fence_after();
-          const uint32_t d_buf = tmem_base + (uint32_t)(buf * pl.nrb * pl.ACCW);
+          const uint32_t d_buf = tmem_base + (uint32_t)((buf * pl.nrb + rb) * pl.ACCW);
           const bool last_ph = ph == pl.nph - 1;
           for (int p = 0; p < pl.NPAIR; ++p) {
             const int G = pair_base + b * H2 + p, slot = G % pl.R, use = G / pl.R;
@@ -440,16 +438,11 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
             if (elect_one()) {
               const uint32_t a_lo0 = ((ring16 + (uint32_t)slot * ((uint32_t)PAIRB >> 4)) & 0x3FFFu) | lbo_field;
               const int m1 = pl.ph[ph].pair_begin[p + 1];
-#pragma unroll 2
+#pragma unroll 4
               for (int m = pl.ph[ph].pair_begin[p]; m < m1; ++m) {
-                const uint4 e = s_mma[m];
-                uint32_t a_lo = a_lo0 + e.x, d = d_buf + e.w;
-                const uint64_t bdesc = ((uint64_t)b_hi << 32) | e.y;
-                for (int rb = 0; rb < pl.nrb; ++rb) {
-                  umma_bf16(d, ((uint64_t)a_hi << 32) | a_lo, bdesc, e.z, 1u);
-                  a_lo += 128u;                   // next 128 rows (16-byte units)
-                  d += (uint32_t)pl.ACCW;
-                }
+                const T2Mma e = pl.mma[m];
+                umma_bf16(d_buf + e.dcol, ((uint64_t)a_hi << 32) | (uint64_t)(a_lo0 + e.a_shift),
+                          ((uint64_t)b_hi << 32) | (uint64_t)(e.b_lo + w16), e.idesc, 1u);
               }
               if (last_ph && (p < H2 || b == nblocks - 1)) umma_commit(smem_u32(&empty_bar[slot]));
               if (p == pl.NPAIR - 1) umma_commit(smem_u32(&accf_bar[buf]));
@@ -569,10 +562,11 @@ static bool t2_build_plan(int cin, int cout, const Geom* gs, int ng, Geom& merge
           }
           if (nmma >= T2_MAX_MMA) return false;
           T2Mma& m = pl.mma[nmma++];
-          m.a_shift = (uint16_t)(dh * pl.PW + (cin == 1 ? 0 : dw));
-          m.b_off16 = (uint16_t)keys[found].off16;
-          m.n8 = (uint8_t)((nj * cout) >> 3);
-          m.dcol = (uint8_t)(j0 * cout);
+          m.a_shift = (uint32_t)(dh * pl.PW + (cin == 1 ? 0 : dw));
+          if (getenv("VAEGAM_T2_EXPERIMENT_ALIGN")) m.a_shift &= ~7u;      // timing experiment only (wrong results)
+          m.b_lo = (uint32_t)keys[found].off16 | (8u << 16);          // LBO = 128 bytes between the two K chunks
+          m.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((nj * cout) >> 3) << 17) | ((128u >> 4) << 24);
+          m.dcol = (uint32_t)(j0 * cout);
         }
     }
   pl.nmma = nmma;
@@ -600,7 +594,7 @@ static bool t2_build_plan(int cin, int cout, const Geom* gs, int ng, Geom& merge
     const int nt = (pl.RTOT + tr - 1) / tr;
     // useful rows per staged row: tile quantisation and the h-halo that every tile re-stages
     const double eff = (double)pl.RTOT / ((double)nt * sr);
-    if (eff > best_eff * 1.03) { best_eff = eff; best = nrb; best_r = r; }
+    if (eff > best_eff * 1.15) { best_eff = eff; best = nrb; best_r = r; }
   }
   if (best < 1) return false;
   pl.nrb = best;
