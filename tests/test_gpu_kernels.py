@@ -145,6 +145,22 @@ def test_conv_tensor_core_path(lib, name):
                             (got.double() * xh.double()).reshape(N // group, group, cin, -1).sum((1, 3))], -1)
     assert rel_err(sums.cpu(), ref_sums.cpu()) < 2e-5
     assert min(rel_err(got.cpu(), gx_round.cpu()), rel_err(got.cpu(), gx_exact.cpu())) < 2e-5
+    # weight gradient (bf16 mma.sync kernel): folded input and dy rounded to bf16, fp32 accumulation
+    wr = w.clone().requires_grad_(True)
+    torch_layer(spec, bf16r(xa), wr, b).backward(bf16r(dy))
+    gw_round = wr.grad.clone()
+    wr.grad = None
+    br = b.clone().requires_grad_(True)
+    torch_layer(spec, xa, wr, br).backward(dy)
+    gw_exact, gb_exact = wr.grad, br.grad
+    dw, db = torch.zeros_like(w), torch.zeros_like(b)
+    native.check(lib.vg_conv_wgrad(C.byref(d), native.ptr(x_cl), native.ptr(dy_cl), native.ptr(scale),
+                                   native.ptr(shift), native.ptr(dw), native.ptr(db), st))
+    torch.cuda.synchronize()
+    e_r, e_e = rel_err(dw.cpu(), gw_round.cpu()), rel_err(dw.cpu(), gw_exact.cpu())
+    assert min(e_r, e_e) < 5e-5, (e_r, e_e)
+    assert e_e < 1e-2
+    assert rel_err(db.cpu(), gb_exact.cpu()) < 2e-5
 
 
 @pytest.mark.parametrize("name", list(LAYERS))

@@ -438,6 +438,11 @@ extern "C" int vg_conv_dgrad(const VgConvDesc* d, const float* dy, const float* 
   return launch_all(d->cout, d->cin, gs, ng, a, as_stream(stream));
 }
 
+namespace vg {
+// wgrad_mma.cu: bf16 mma.sync weight gradient; VG_OK, a negative error, or 1 = channel pair not covered
+int wgrad_mma(const VgConvDesc* d, const float* x, const float* dy, const float* in_scale, const float* in_shift,
+              float* dw, float* dbias, cudaStream_t st);
+}
 int vg_conv_wgrad_tiled(const VgConvDesc* d, const float* x, const float* dy, const float* in_scale,
                         const float* in_shift, float* dw, float* dbias, cudaStream_t st);   // wgrad.cu
 
@@ -445,5 +450,9 @@ extern "C" int vg_conv_wgrad(const VgConvDesc* d, const float* x, const float* d
                              const float* in_shift, float* dw, float* dbias, void* stream) {
   VG_TRY(check_desc(d));
   VG_CHECK_ARG(x && dy && dw, "null tensor");
+  if (conv_mode() == 1) {
+    const int rc = wgrad_mma(d, x, dy, in_scale, in_shift, dw, dbias, as_stream(stream));   // bias gradient fused
+    if (rc <= 0) return rc;
+  }
   return vg_conv_wgrad_tiled(d, x, dy, in_scale, in_shift, dw, dbias, as_stream(stream));
 }

@@ -287,7 +287,8 @@ int vg_conv_wgrad_tiled(const VgConvDesc* d, const float* x, const float* dy, co
   pick_tile(d, d->cin, d->cout, g);
   int rc = VG_EINVAL;
   const int ci = d->cin, co = d->cout;
-  if (ci == 1 && co == 8) rc = launch_wgrad_tiled<1, 8, 1>(g, x, dy, in_scale, in_shift, dw, st);
+  if (!dw) rc = VG_OK;                      // weight gradient already produced by the tensor-core kernel
+  else if (ci == 1 && co == 8) rc = launch_wgrad_tiled<1, 8, 1>(g, x, dy, in_scale, in_shift, dw, st);
   else if (ci == 8 && co == 1) rc = launch_wgrad_tiled<8, 1, 8>(g, x, dy, in_scale, in_shift, dw, st);
   else if (ci == 8 && co == 8) rc = launch_wgrad_tiled<8, 8, 4>(g, x, dy, in_scale, in_shift, dw, st);
   else if (ci == 8 && co == 16) rc = launch_wgrad_tiled<8, 16, 4>(g, x, dy, in_scale, in_shift, dw, st);

@@ -1,0 +1,421 @@
+// Tensor-core weight gradients of Conv3d / ConvTranspose3d (autograd of vae_reg_GP.py:238-242,
+// 260-264) in bf16 with fp32 accumulation (convolution mode 1).
+//
+//   dW[t][ci][co] = sum_{n, q} X[n, q*s + k_t (mode 0) | q (mode 1)][ci] * dY[n, q (mode 0) | q*s + k_t - p (mode 1)][co]
+//
+// The result is a few thousand numbers reduced over tens of millions of voxels, so the GEMM is
+// D[(tap, shifted channel)][unshifted channel] with K = voxels: M <= 360, N <= 16.  A tcgen05
+// formulation would have to keep one TMEM accumulator per (dh,dw) shift (> 512 columns for the
+// stride-2 layers) and re-read both operands from shared memory for every 16 voxels, so this
+// kernel uses warp-level mma.sync.m16n8k16 with register accumulators instead: each warp owns a
+// private copy of the whole (or half the) weight gradient, walks 16-voxel chunks of the CTA's
+// tile, and gets its fragments with ldmatrix.trans straight from channels-last bf16 tiles — the
+// tap shift and the stride are just per-lane row addresses.  CTAs are persistent over tiles;
+// accumulators are flushed once per CTA (shared-memory reduce, then one global atomic per weight).
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace vg {
+
+struct WmGeom {
+  int N, group_size;
+  int mode, s;
+  int kD, kH, kW, pD, pH, pW;
+  int bD, bH, bW;        // base grid (q)
+  int xD, xH, xW;        // module input grid
+  int yD, yH, yW;        // module output grid
+  int tD, tH, tW;        // tile (q voxels)
+  int nTd, nTh, nTw;
+  int sD, sH, sW;        // shifted-operand box of a tile
+  long long x_img, y_img;
+  int wst_t, wst_ci, wst_co;
+  int ntaps, tg, taps_per_group;
+  uint32_t mul_tH, mul_tW, mul_sH, mul_sW;   // ceil(2^32 / d) for the staging index decomposition (0: d == 1)
+};
+
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2_t(uint32_t addr, uint32_t (&r)[2]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// exact e / d for e * d < 2^32 with mul = ceil(2^32 / d) (d >= 2); d == 1 is passed as mul = 0
+__device__ __forceinline__ int fast_div(int e, uint32_t mul) { return mul ? (int)__umulhi((uint32_t)e, mul) : e; }
+
+// Stage a box of voxels of a channels-last fp32 tensor as bf16 (BatchNorm fold on in-range voxels, zeros
+// outside).  Flat element index (full lane utilisation for any box shape, divisions by multiply-high), four
+// independent elements per thread in flight before the first is converted.  BIAS: also sum the raw values
+// of the voxels this tile OWNS (own*: global coordinate ranges) per channel — a thread always handles the
+// same 8-channel part (blockDim is a multiple of the parts per voxel), so the sums live in 8 registers.
+template <int C, bool BIAS>
+__device__ __forceinline__ void stage_box_bf16(__nv_bfloat16* dst, const float* __restrict__ src, int oD, int oH, int oW,
+                                               int bh, int bw, int nvox, uint32_t mul_h, uint32_t mul_w, int gD, int gH,
+                                               int gW, const float* sc, const float* sh, const int (&own)[6],
+                                               float (&bs)[8]) {
+  constexpr int PER = C >= 8 ? C / 8 : 1;        // 16-byte bf16 chunks per voxel
+  constexpr int U = C >= 8 ? 2 : 4;              // elements in flight per thread (registers are shared with the accumulators)
+  const int nel = nvox * PER;
+  for (int e0 = threadIdx.x; e0 < nel; e0 += U * blockDim.x) {
+    float4 va[U], vb[U];
+    float v1[U];
+    int state[U];                                // 0: beyond the box, 1: zero fill, 2: loaded, 3: loaded + owned
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int e = e0 + u * blockDim.x;
+      state[u] = 0;
+      if (e >= nel) continue;
+      const int v = e / PER, part = e & (PER - 1);
+      const int r = fast_div(v, mul_w), l = v - r * bw;
+      const int i = fast_div(r, mul_h), j = r - i * bh;
+      const int gd = oD + i, gh = oH + j, gw = oW + l;
+      state[u] = 1;
+      if (gd >= 0 && gd < gD && gh >= 0 && gh < gH && gw >= 0 && gw < gW) {
+        state[u] = 2;
+        if (BIAS && gd >= own[0] && gd < own[1] && gh >= own[2] && gh < own[3] && gw >= own[4] && gw < own[5]) state[u] = 3;
+        const size_t off = (((size_t)gd * gH + gh) * gW + gw) * C;
+        if constexpr (C >= 8) {
+          const float4* p = reinterpret_cast<const float4*>(src + off) + part * 2;
+          va[u] = __ldg(p);
+          vb[u] = __ldg(p + 1);
+        } else {
+          v1[u] = __ldg(src + off);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (state[u] == 0) continue;
+      const int e = e0 + u * blockDim.x;
+      if constexpr (C >= 8) {
+        uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+        if (state[u] >= 2) {
+          float4 a = va[u], b = vb[u];
+          if (BIAS && state[u] == 3) {
+            bs[0] += a.x; bs[1] += a.y; bs[2] += a.z; bs[3] += a.w;
+            bs[4] += b.x; bs[5] += b.y; bs[6] += b.z; bs[7] += b.w;
+          }
+          if (sc) {
+            const int c0 = (e & (PER - 1)) * 8;
+            a.x = fmaf(a.x, sc[c0], sh[c0]); a.y = fmaf(a.y, sc[c0 + 1], sh[c0 + 1]);
+            a.z = fmaf(a.z, sc[c0 + 2], sh[c0 + 2]); a.w = fmaf(a.w, sc[c0 + 3], sh[c0 + 3]);
+            b.x = fmaf(b.x, sc[c0 + 4], sh[c0 + 4]); b.y = fmaf(b.y, sc[c0 + 5], sh[c0 + 5]);
+            b.z = fmaf(b.z, sc[c0 + 6], sh[c0 + 6]); b.w = fmaf(b.w, sc[c0 + 7], sh[c0 + 7]);
+          }
+          __nv_bfloat162 t0 = __floats2bfloat162_rn(a.x, a.y), t1 = __floats2bfloat162_rn(a.z, a.w);
+          __nv_bfloat162 t2 = __floats2bfloat162_rn(b.x, b.y), t3 = __floats2bfloat162_rn(b.z, b.w);
+          pk = make_uint4(*reinterpret_cast<uint32_t*>(&t0), *reinterpret_cast<uint32_t*>(&t1),
+                          *reinterpret_cast<uint32_t*>(&t2), *reinterpret_cast<uint32_t*>(&t3));
+        }
+        reinterpret_cast<uint4*>(dst)[e] = pk;
+      } else {
+        float t = 0.f;
+        if (state[u] >= 2) {
+          t = v1[u];
+          if (BIAS && state[u] == 3) bs[0] += t;
+          if (sc) t = fmaf(t, sc[0], sh[0]);
+        }
+        dst[e] = __float2bfloat16(t);
+      }
+    }
+  }
+}
+
+// CS: channels of the tap-shifted operand (1, 8, 16); CU: channels of the un-shifted operand (8, 16);
+// MT: m16 tiles of (tap, shifted channel) rows a warp accumulates.
+template <int CS, int CU, int MT, int MODE>
+__global__ void __launch_bounds__(256, 2)
+wgrad_mma_kernel(const __grid_constant__ WmGeom g, const float* __restrict__ x, const float* __restrict__ dy,
+                 const float* __restrict__ in_scale, const float* __restrict__ in_shift, float* dw, float* dbias) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __shared__ int s_tapoff[48];
+  __shared__ float s_bias[16];
+  constexpr int NT = CU / 8;                       // n8 tiles
+  constexpr int TPM = CS == 8 ? 2 : (CS == 16 ? 1 : 16);   // taps per m16 tile
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvw = (blockDim.x >> 5) / g.tg;        // warps sharing a tap group split the voxel chunks
+  const int tgi = warp % g.tg, vwi = warp / g.tg;
+  const int tap_lo = tgi * g.taps_per_group;
+  const int tap_hi = min(g.ntaps, tap_lo + g.taps_per_group);
+  const int tile_vox = g.tD * g.tH * g.tW, box_vox = g.sD * g.sH * g.sW;
+  const int nchunks = (tile_vox + 15) >> 4;
+  __nv_bfloat16* Ssh = reinterpret_cast<__nv_bfloat16*>(smem_raw);                       // shifted operand: box
+  const size_t sh_bytes = (((size_t)box_vox * CS * 2 + 64) + 15) & ~(size_t)15;           // + slack for clamped taps
+  __nv_bfloat16* Sun = reinterpret_cast<__nv_bfloat16*>(smem_raw + sh_bytes);             // un-shifted operand: tile (+ pad chunk)
+  // box offset of every tile voxel (the tile geometry is the same for all tiles): no divisions in the chunk loop
+  unsigned short* s_vo = reinterpret_cast<unsigned short*>(smem_raw + sh_bytes + (size_t)nchunks * 16 * CU * 2);
+  for (int v = threadIdx.x; v < nchunks * 16; v += blockDim.x) {
+    const int vv = min(v, tile_vox - 1);               // padded rows of the last chunk meet zero B rows
+    const int l = vv % g.tW, rr = vv / g.tW;
+    const int j = rr % g.tH, i = rr / g.tH;
+    s_vo[v] = (unsigned short)(((i * g.s) * g.sH + j * g.s) * g.sW + l * g.s);
+  }
+  if (threadIdx.x < 16) s_bias[threadIdx.x] = 0.f;
+  float bsum[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) bsum[c] = 0.f;
+  const uint32_t ssh_addr = (uint32_t)__cvta_generic_to_shared(Ssh), sun_addr = (uint32_t)__cvta_generic_to_shared(Sun);
+
+  if (threadIdx.x < 48) {
+    const int t = min((int)threadIdx.x, g.ntaps - 1);
+    const int ka = t / (g.kH * g.kW), kb = (t / g.kW) % g.kH, kc = t % g.kW;
+    s_tapoff[threadIdx.x] = (ka * g.sH + kb) * g.sW + kc;
+  }
+
+  float acc[MT][NT][4];
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[i][j][k] = 0.f;
+
+  const int tiles_per_img = g.nTd * g.nTh * g.nTw;
+  const long long ntiles = (long long)tiles_per_img * g.N;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int n = (int)(tile / tiles_per_img);
+    int tr = (int)(tile - (long long)n * tiles_per_img);
+    const int tw = tr % g.nTw; tr /= g.nTw;
+    const int th = tr % g.nTh;
+    const int td = tr / g.nTh;
+    const int q0d = td * g.tD, q0h = th * g.tH, q0w = tw * g.tW;
+    const float* xn = x + (size_t)n * g.x_img;
+    const float* yn = dy + (size_t)n * g.y_img;
+    const float* sc = in_scale ? in_scale + (n / g.group_size) * (MODE == 0 ? CS : CU) : nullptr;
+    const float* sh = in_scale ? in_shift + (n / g.group_size) * (MODE == 0 ? CS : CU) : nullptr;
+    __syncthreads();   // previous tile fully consumed
+    // un-shifted tile: clipped to the base grid (voxels of the tile beyond it contribute zeros)
+    const int none[6] = {0, 0, 0, 0, 0, 0};
+    if (MODE == 0) {
+      // dY is the un-shifted tile: tiles partition the output grid
+      const int own[6] = {q0d, q0d + g.tD, q0h, q0h + g.tH, q0w, q0w + g.tW};
+      stage_box_bf16<CS, false>(Ssh, xn, q0d * g.s, q0h * g.s, q0w * g.s, g.sH, g.sW, box_vox, g.mul_sH, g.mul_sW, g.xD, g.xH,
+                                g.xW, sc, sh, none, bsum);
+      if (dbias) stage_box_bf16<CU, true>(Sun, yn, q0d, q0h, q0w, g.tH, g.tW, tile_vox, g.mul_tH, g.mul_tW, g.yD, g.yH, g.yW,
+                                          nullptr, nullptr, own, bsum);
+      else stage_box_bf16<CU, false>(Sun, yn, q0d, q0h, q0w, g.tH, g.tW, tile_vox, g.mul_tH, g.mul_tW, g.yD, g.yH, g.yW,
+                                     nullptr, nullptr, none, bsum);
+    } else {
+      // dY is the shifted box (boxes of neighbouring tiles overlap): a tile owns the outputs
+      // [q0*s - p, (q0+t)*s - p), the first / last tile of a dimension also the grid's margins
+      const int own[6] = {td == 0 ? 0 : q0d * g.s - g.pD, td == g.nTd - 1 ? g.yD : (q0d + g.tD) * g.s - g.pD,
+                          th == 0 ? 0 : q0h * g.s - g.pH, th == g.nTh - 1 ? g.yH : (q0h + g.tH) * g.s - g.pH,
+                          tw == 0 ? 0 : q0w * g.s - g.pW, tw == g.nTw - 1 ? g.yW : (q0w + g.tW) * g.s - g.pW};
+      stage_box_bf16<CU, false>(Sun, xn, q0d, q0h, q0w, g.tH, g.tW, tile_vox, g.mul_tH, g.mul_tW, g.xD, g.xH, g.xW, sc, sh,
+                                none, bsum);
+      if (dbias) stage_box_bf16<CS, true>(Ssh, yn, q0d * g.s - g.pD, q0h * g.s - g.pH, q0w * g.s - g.pW, g.sH, g.sW, box_vox,
+                                          g.mul_sH, g.mul_sW, g.yD, g.yH, g.yW, nullptr, nullptr, own, bsum);
+      else stage_box_bf16<CS, false>(Ssh, yn, q0d * g.s - g.pD, q0h * g.s - g.pH, q0w * g.s - g.pW, g.sH, g.sW, box_vox,
+                                     g.mul_sH, g.mul_sW, g.yD, g.yH, g.yW, nullptr, nullptr, none, bsum);
+    }
+    // zero the un-shifted rows of the last chunk's padding (tile_vox .. 16*nchunks)
+    for (int e = threadIdx.x; e < (nchunks * 16 - tile_vox) * CU / 8; e += blockDim.x)
+      reinterpret_cast<uint4*>(Sun + (size_t)tile_vox * CU)[e] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    if (tap_lo >= tap_hi) continue;
+
+    for (int c = vwi; c < nchunks; c += nvw) {
+      // ---- B fragments: un-shifted operand, 16 voxels x CU channels
+      uint32_t bf[NT][2];
+      {
+        const int mat = lane >> 3, r = lane & 7;
+        if constexpr (CU == 8) {
+          const int v = c * 16 + (mat & 1) * 8 + r;
+          uint32_t t2[2];
+          ldsm_x2_t(sun_addr + (uint32_t)v * 16u, t2);
+          bf[0][0] = t2[0]; bf[0][1] = t2[1];
+        } else {
+          const int v = c * 16 + (mat & 1) * 8 + r;
+          uint32_t t4[4];
+          ldsm_x4_t(sun_addr + (uint32_t)v * 32u + (uint32_t)(mat >> 1) * 16u, t4);
+          bf[0][0] = t4[0]; bf[0][1] = t4[1]; bf[1][0] = t4[2]; bf[1][1] = t4[3];
+        }
+      }
+      // ---- A fragments: tap-shifted operand
+      if constexpr (CS >= 8) {
+        const int mat = lane >> 3, r = lane & 7;
+        const int base = s_vo[c * 16 + (mat >> 1) * 8 + r];                 // box voxel of the un-tapped position
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          const int t0 = tap_lo + mt * TPM;
+          if (t0 >= tap_hi) break;
+          uint32_t af[4];
+          if constexpr (CS == 8) {
+            const int t = min(t0 + (mat & 1), tap_hi - 1);
+            ldsm_x4_t(ssh_addr + (uint32_t)(base + s_tapoff[t]) * 16u, af);
+          } else {
+            ldsm_x4_t(ssh_addr + (uint32_t)(base + s_tapoff[t0]) * 32u + (uint32_t)(mat & 1) * 16u, af);
+          }
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) mma_bf16(acc[mt][nt], af, bf[nt][0], bf[nt][1]);
+        }
+      } else {
+        // one shifted channel: rows of the m16 tile are taps, fragments are gathered element-wise
+        const int gq = lane >> 2, q4 = lane & 3;
+        int vo[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) vo[k] = s_vo[c * 16 + 2 * q4 + (k & 1) + (k >> 1) * 8];
+        const unsigned short* S16 = reinterpret_cast<const unsigned short*>(Ssh);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          const int ta = min(tap_lo + mt * 16 + gq, tap_hi - 1), tb = min(tap_lo + mt * 16 + gq + 8, tap_hi - 1);
+          const int oa = s_tapoff[ta], ob = s_tapoff[tb];
+          uint32_t af[4];
+          af[0] = (uint32_t)S16[vo[0] + oa] | ((uint32_t)S16[vo[1] + oa] << 16);
+          af[1] = (uint32_t)S16[vo[0] + ob] | ((uint32_t)S16[vo[1] + ob] << 16);
+          af[2] = (uint32_t)S16[vo[2] + oa] | ((uint32_t)S16[vo[3] + oa] << 16);
+          af[3] = (uint32_t)S16[vo[2] + ob] | ((uint32_t)S16[vo[3] + ob] << 16);
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) mma_bf16(acc[mt][nt], af, bf[nt][0], bf[nt][1]);
+        }
+      }
+    }
+  }
+
+  // ---- bias gradient: a lane's sums belong to the 8-channel part (lane mod parts) of dY
+  if (dbias) {
+    constexpr int CY = MODE == 0 ? CU : CS;
+    constexpr int PERY = CY >= 8 ? CY / 8 : 1;
+    const int part = lane & (PERY - 1);
+#pragma unroll
+    for (int c = 0; c < (CY >= 8 ? 8 : 1); ++c) {
+      float v = bsum[c];
+      // lanes with equal (lane mod PERY) hold the same channels
+      for (int o = 16; o >= PERY; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane < PERY) atomicAdd(&s_bias[part * 8 + c], v);
+    }
+  }
+  // ---- flush: reduce the warps through shared memory, then one global atomic per weight
+  __syncthreads();
+  if (dbias && threadIdx.x < (MODE == 0 ? CU : CS)) atomicAdd(dbias + threadIdx.x, s_bias[threadIdx.x]);
+  float* red = reinterpret_cast<float*>(smem_raw);            // [tap][shifted ch][un-shifted ch]
+  const int nred = g.ntaps * CS * CU;
+  for (int e = threadIdx.x; e < nred; e += blockDim.x) red[e] = 0.f;
+  __syncthreads();
+  {
+    const int gq = lane >> 2, q4 = lane & 3;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int row = mt * 16 + gq + (k >> 1) * 8;                // (tap, shifted channel) within the group
+          const int colu = nt * 8 + 2 * q4 + (k & 1);                 // un-shifted channel
+          int t, cs;
+          if constexpr (CS == 1) { t = tap_lo + row; cs = 0; }
+          else { t = tap_lo + row / CS; cs = row % CS; }
+          if (t < tap_hi) atomicAdd(&red[((size_t)t * CS + cs) * CU + colu], acc[mt][nt][k]);
+        }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < nred; e += blockDim.x) {
+    const int colu = e % CU, rest = e / CU;
+    const int cs = rest % CS, t = rest / CS;
+    const int ci = MODE == 0 ? cs : colu, co = MODE == 0 ? colu : cs;
+    atomicAdd(dw + (size_t)t * g.wst_t + (size_t)ci * g.wst_ci + (size_t)co * g.wst_co, red[e]);
+  }
+}
+
+static void wm_pick_tile(int cs, int cu, WmGeom& g) {
+  // q-voxel tile: staged bf16 bytes under ~72 KB (two CTAs per SM), prefer tiles whose staged
+  // box is small relative to the useful voxels (halo amortisation) and that tile the grid evenly
+  const long long budget = 72 * 1024;
+  int best[3] = {1, 1, 1};
+  double best_score = -1.0;
+  const int candD[] = {1, 2, 3, 4, 6, 8}, candH[] = {1, 2, 4, 6, 8, 12}, candW[] = {4, 7, 8, 14, 16, 17, 33, 35};
+  for (int a : candD)
+    for (int b : candH)
+      for (int c : candW) {
+        if (a > g.bD || b > g.bH || c > g.bW) continue;
+        const long long tile = (long long)a * b * c;
+        const long long box = (long long)((a - 1) * g.s + g.kD) * ((b - 1) * g.s + g.kH) * ((c - 1) * g.s + g.kW);
+        const long long bytes = box * cs * 2 + ((tile + 15) / 16 * 16) * (cu * 2 + 2) + 256;
+        if (box > 65535) continue;
+        if (bytes > budget) continue;
+        const long long nT = (long long)((g.bD + a - 1) / a) * ((g.bH + b - 1) / b) * ((g.bW + c - 1) / c);
+        const double useful = (double)g.bD * g.bH * g.bW;
+        // staged bytes per useful voxel (lower is better), chunk quantisation
+        const double cost = (double)nT * (double)(box * cs + tile * cu) / useful;
+        const double chunk_eff = (double)tile / (double)((tile + 15) / 16 * 16);
+        const double score = chunk_eff / cost;
+        if (score > best_score) { best_score = score; best[0] = a; best[1] = b; best[2] = c; }
+      }
+  g.tD = best[0]; g.tH = best[1]; g.tW = best[2];
+  g.nTd = (g.bD + g.tD - 1) / g.tD; g.nTh = (g.bH + g.tH - 1) / g.tH; g.nTw = (g.bW + g.tW - 1) / g.tW;
+  g.sD = (g.tD - 1) * g.s + g.kD; g.sH = (g.tH - 1) * g.s + g.kH; g.sW = (g.tW - 1) * g.s + g.kW;
+  auto magic = [](int d) { return d <= 1 ? 0u : (uint32_t)((0x100000000ULL + (uint64_t)d - 1) / (uint64_t)d); };
+  g.mul_tH = magic(g.tH); g.mul_tW = magic(g.tW); g.mul_sH = magic(g.sH); g.mul_sW = magic(g.sW);
+}
+
+template <int CS, int CU, int MT>
+static int launch_wm(const WmGeom& g, const float* x, const float* dy, const float* sc, const float* sh, float* dw,
+                     float* dbias, cudaStream_t st) {
+  const long long tile = (long long)g.tD * g.tH * g.tW, box = (long long)g.sD * g.sH * g.sW;
+  size_t smem = ((size_t)box * CS * 2 + 64 + 15) / 16 * 16 + (size_t)((tile + 15) / 16 * 16) * (CU * 2 + 2) + 64;
+  const size_t red = (size_t)g.ntaps * CS * CU * sizeof(float);
+  if (red > smem) smem = red;
+  const long long ntiles = (long long)g.nTd * g.nTh * g.nTw * g.N;
+  long long blocks = 2LL * vg_sm_count();
+  if (blocks > ntiles) blocks = ntiles;
+  if (g.mode == 0) {
+    VG_CUDA(cudaFuncSetAttribute(wgrad_mma_kernel<CS, CU, MT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    wgrad_mma_kernel<CS, CU, MT, 0><<<(unsigned)blocks, 256, smem, st>>>(g, x, dy, sc, sh, dw, dbias);
+  } else {
+    VG_CUDA(cudaFuncSetAttribute(wgrad_mma_kernel<CS, CU, MT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    wgrad_mma_kernel<CS, CU, MT, 1><<<(unsigned)blocks, 256, smem, st>>>(g, x, dy, sc, sh, dw, dbias);
+  }
+  VG_LAUNCH_CHECK();
+  return VG_OK;
+}
+
+// returns VG_OK, or 1 when the channel pair is not covered (caller falls back to the fp32 kernel)
+int wgrad_mma(const VgConvDesc* d, const float* x, const float* dy, const float* in_scale, const float* in_shift,
+              float* dw, float* dbias, cudaStream_t st) {
+  WmGeom g{};
+  g.N = d->n; g.group_size = d->group_size;
+  g.mode = d->transposed ? 1 : 0;
+  g.s = d->stride;
+  g.kD = d->k[0]; g.kH = d->k[1]; g.kW = d->k[2];
+  g.pD = d->pad[0]; g.pH = d->pad[1]; g.pW = d->pad[2];
+  const int* base = d->transposed ? d->in : d->out;
+  g.bD = base[0]; g.bH = base[1]; g.bW = base[2];
+  g.xD = d->in[0]; g.xH = d->in[1]; g.xW = d->in[2];
+  g.yD = d->out[0]; g.yH = d->out[1]; g.yW = d->out[2];
+  g.x_img = d->x_img_stride ? d->x_img_stride : (long long)d->in[0] * d->in[1] * d->in[2] * d->cin;
+  g.y_img = d->y_img_stride ? d->y_img_stride : (long long)d->out[0] * d->out[1] * d->out[2] * d->cout;
+  const int K = g.kD * g.kH * g.kW;
+  if (K > 48) return 1;
+  g.ntaps = K;
+  g.wst_t = 1;
+  if (!d->transposed) { g.wst_ci = K; g.wst_co = d->cin * K; }        // w[co][ci][K]
+  else                { g.wst_ci = d->cout * K; g.wst_co = K; }        // w[ci][co][K]
+  const int cs = d->transposed ? d->cout : d->cin, cu = d->transposed ? d->cin : d->cout;
+  // 1-channel images need 16-byte aligned rows only through the vector path (C >= 8): always true for dense tensors
+  if ((cs >= 8 && ((d->transposed ? g.y_img : g.x_img) % 4)) || ((d->transposed ? g.x_img : g.y_img) % 4)) return 1;
+  auto groups = [&](int tpm, int mt) {       // tap groups so that a warp's m16 tiles fit MT
+    const int tiles = (K + tpm - 1) / tpm;
+    int tg = (tiles + mt - 1) / mt;
+    while (8 % tg) ++tg;
+    g.tg = tg;
+    g.taps_per_group = ((tiles + tg - 1) / tg) * tpm;
+  };
+  wm_pick_tile(cs, cu, g);
+  if (cs == 1 && cu == 8) { groups(16, 3); return launch_wm<1, 8, 3>(g, x, dy, in_scale, in_shift, dw, dbias, st); }
+  // MT keeps the accumulators at <= 56 registers so that two CTAs share an SM without spills
+  if (cs == 8 && cu == 8) { groups(2, 12); return launch_wm<8, 8, 12>(g, x, dy, in_scale, in_shift, dw, dbias, st); }
+  if (cs == 8 && cu == 16) { groups(2, 7); return launch_wm<8, 16, 7>(g, x, dy, in_scale, in_shift, dw, dbias, st); }
+  if (cs == 16 && cu == 16) { groups(1, 7); return launch_wm<16, 16, 7>(g, x, dy, in_scale, in_shift, dw, dbias, st); }
+  if (cs == 16 && cu == 8) { groups(1, 14); return launch_wm<16, 8, 14>(g, x, dy, in_scale, in_shift, dw, dbias, st); }
+  return 1;
+}
+
+}  // namespace vg
