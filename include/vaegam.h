@@ -81,6 +81,9 @@ typedef struct VgConvDesc {
  * Initial value from the environment variable VAEGAM_CONV_MODE ("0"/"fp32" or "1"). */
 int vg_set_conv_mode(int mode);
 int vg_get_conv_mode(void);
+/* Dispatch tuning.  "t2_min_voxels": output voxels per launch from which the persistent plane-folded
+ * tcgen05 kernel is preferred over the per-tile kernels (default 400000; env VAEGAM_T2_MIN_VOXELS). */
+int vg_set_conv_tuning(const char* key, long long value);
 
 /* Host-side description of the launches a layer maps to in the current mode (kind 0: forward,
  * 1: data gradient), one text line per launch; returns the number of launches. */

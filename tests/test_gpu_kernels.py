@@ -68,15 +68,18 @@ def _fp32_mode_by_default(lib):
     lib.vg_set_conv_mode(0)
     yield
     lib.vg_set_conv_mode(0)
+    lib.vg_set_conv_tuning(b"t2_min_voxels", 400000)
 
 
 def bf16r(t):
     return t.to(torch.bfloat16).to(torch.float32)
 
 
+@pytest.mark.parametrize("big", [True, False], ids=["plane_folded", "default_dispatch"])
 @pytest.mark.parametrize("name", list(LAYERS))
-def test_conv_tensor_core_path(lib, name):
-    """tcgen05 implicit-GEMM kernels (mode 1).  The kernel rounds the (BN-folded) input and the
+def test_conv_tensor_core_path(lib, name, big):
+    """tcgen05 implicit-GEMM kernels (mode 1); `big` forces the persistent plane-folded kernel onto the small
+    test problems (production dispatch uses it from 4e5 output voxels per launch).  The kernel rounds the (BN-folded) input and the
     weights to bf16 and accumulates in fp32, so a PyTorch fp32 reference fed the SAME rounded
     operands must agree to fp32 accumulation error; layers the tensor-core kernel does not cover
     (1 input channel, strided gathers) fall back to the fp32 kernel and still have to pass."""
@@ -95,6 +98,7 @@ def test_conv_tensor_core_path(lib, name):
     d = native.conv_desc(tr, cin, cout, k, s, in_, N, group, pad, opad)
     lib.vg_set_conv_mode(1)
     assert lib.vg_get_conv_mode() == 1
+    native.check(lib.vg_set_conv_tuning(b"t2_min_voxels", 0 if big else 400000))
     xa = torch.addcmul(shift.repeat_interleave(group, 0)[:, :, None, None, None], x,
                        scale.repeat_interleave(group, 0)[:, :, None, None, None])       # fma, as the kernel does
     x_cl = to_cl(x)

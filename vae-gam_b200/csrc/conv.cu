@@ -16,6 +16,7 @@
 // scale/shift to in-range taps only (zero padding pads the NORMALISED tensor) and `epi`
 // accumulates the next layer's statistics, or the BatchNorm-backward sums.
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "conv_geom.cuh"
@@ -345,8 +346,18 @@ int conv_mode() {
   return g_conv_mode;
 }
 
+// The plane-folded kernel is persistent with a per-CTA set-up (weight blocks, TMEM): worth it from a few
+// hundred thousand output voxels per launch
+static long long g_t2_min_voxels = -1;
+static bool tc2_worthwhile(const Geom* gs, int ng) {
+  long long vox = 0;
+  for (int i = 0; i < ng; ++i) vox += (long long)gs[i].N * gs[i].qD * gs[i].qH * gs[i].qW;
+  if (g_t2_min_voxels < 0) { const char* e = getenv("VAEGAM_T2_MIN_VOXELS"); g_t2_min_voxels = e ? atoll(e) : 400000; }
+  return vox >= g_t2_min_voxels;
+}
+
 static int launch_gather(int cin, int cout, const Geom& g, const GatherArgs& a, cudaStream_t st) {
-  if (conv_mode() == 1 && tc2_supported(cin, cout, &g, 1)) return launch_tc2_gather(cin, cout, &g, 1, a, st);
+  if (conv_mode() == 1 && tc2_worthwhile(&g, 1) && tc2_supported(cin, cout, &g, 1)) return launch_tc2_gather(cin, cout, &g, 1, a, st);
   if (conv_mode() == 1 && tc_supported(cin, cout, g)) return launch_tc_gather(cin, cout, g, a, st);
   if (cin == 1 && cout == 8) return launch_gather_t<1, 8, 4>(g, a, st);
   if (cin == 8 && cout == 1) return launch_gather_t<8, 1, 4>(g, a, st);
@@ -363,7 +374,8 @@ static int launch_gather(int cin, int cout, const Geom& g, const GatherArgs& a, 
 
 // every gather of one layer pass: one fused multi-phase launch when the plane-folded kernel covers it
 static int launch_all(int cin, int cout, const Geom* gs, int ng, const GatherArgs& a, cudaStream_t st) {
-  if (ng > 1 && conv_mode() == 1 && tc2_supported(cin, cout, gs, ng)) return launch_tc2_gather(cin, cout, gs, ng, a, st);
+  if (ng > 1 && conv_mode() == 1 && tc2_worthwhile(gs, ng) && tc2_supported(cin, cout, gs, ng))
+    return launch_tc2_gather(cin, cout, gs, ng, a, st);
   for (int i = 0; i < ng; ++i) VG_TRY(launch_gather(cin, cout, gs[i], a, st));
   return VG_OK;
 }
@@ -378,6 +390,12 @@ extern "C" int vg_set_conv_mode(int mode) {
   return VG_OK;
 }
 extern "C" int vg_get_conv_mode(void) { return conv_mode(); }
+extern "C" int vg_set_conv_tuning(const char* key, long long value) {
+  VG_CHECK_ARG(key != nullptr, "null key");
+  if (strcmp(key, "t2_min_voxels") == 0) { VG_CHECK_ARG(value >= 0, "negative threshold"); g_t2_min_voxels = value; return VG_OK; }
+  set_error("unknown tuning key '%s'", key);
+  return VG_EINVAL;
+}
 
 // Which kernel serves each gather of a layer (kind 0 forward, 1 data gradient) in the current
 // convolution mode; one line per launch.  Host only, no device work.
@@ -389,14 +407,14 @@ extern "C" int vg_conv_describe(const VgConvDesc* d, int kind, char* buf, size_t
   const int cin = kind == 0 ? d->cin : d->cout, cout = kind == 0 ? d->cout : d->cin;
   size_t off = 0;
   buf[0] = 0;
-  if (ng > 1 && conv_mode() == 1 && tc2_supported(cin, cout, gs, ng)) {
+  if (ng > 1 && conv_mode() == 1 && tc2_worthwhile(gs, ng) && tc2_supported(cin, cout, gs, ng)) {
     const int n = tc2_describe(cin, cout, gs, ng, buf, cap);
     if (n > 0 && (size_t)n + 2 < cap) { buf[n] = '\n'; buf[n + 1] = 0; }
     return 1;
   }
   for (int i = 0; i < ng && off + 8 < cap; ++i) {
     int n = 0;
-    if (conv_mode() == 1) n = tc2_describe(cin, cout, &gs[i], 1, buf + off, cap - off);
+    if (conv_mode() == 1 && tc2_worthwhile(&gs[i], 1)) n = tc2_describe(cin, cout, &gs[i], 1, buf + off, cap - off);
     if (n <= 0) {
       const bool tc = conv_mode() == 1 && tc_supported(cin, cout, gs[i]);
       n = snprintf(buf + off, cap - off, "%s cin=%d cout=%d q=(%d,%d,%d) taps=%d", tc ? "tc1" : "fp32", cin, cout,

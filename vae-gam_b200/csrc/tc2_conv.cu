@@ -13,7 +13,10 @@
 // shifted-window descriptors over the same staged plane: rows are the plane's voxels flattened
 // with a padded pitch, so a tap is a constant row shift and a tile is 128 consecutive rows.
 // Inputs with ONE channel use the 8 consecutive w-voxels of a row as the K-chunk (the dw taps sit
-// inside K).  A stride-2 transposed layer is ONE launch: its (up to 8) output-parity phases share
+// inside K); inputs with 16 channels put the two 8-channel halves of ONE plane into K.  A gather
+// with input stride 2 (Conv3d stride 2, the data gradient of a stride-2 ConvTranspose3d) stages
+// each input plane as its four (h,w)-parity sub-grids, so that every tap is again a unit-stride
+// row shift inside one sub-grid.  A stride-2 transposed layer is ONE launch: its (up to 8) output-parity phases share
 // the staged input planes and differ only in their MMA lists, weight blocks and output offsets.
 //
 // Roles (512 threads, one persistent CTA per SM), ES = 1 or 2 epilogue sets:
@@ -60,6 +63,10 @@ struct T2Plan {
   int lo_d, lo_h, lo_w, span_d, span_h, span_w;
   int qDmax, dchunk, ndchunks;
   int nph, nmma, nblk, wbytes;
+  int sd;                      // input stride of the gather (1 or 2)
+  int pps;                     // input planes per ring slot: 2 (1 or 8 channels) or 1 (16 channels: K = the plane's two halves)
+  int nsg;                     // (h,w)-parity sub-grids per staged plane: 1, or 4 when sd == 2
+  int ppb;                     // ring slots consumed per block of OB output planes
   T2Phase ph[T2_MAX_PH];
   T2Mma mma[T2_MAX_MMA];
   T2Blk blk[T2_MAX_BLK];
@@ -67,16 +74,19 @@ struct T2Plan {
 };
 
 // roles per (cin, cout): the side that moves more bytes gets more warps
-__host__ __device__ constexpr int t2_epi_sets(int cin, int cout) { return (cin == 8 && cout == 1) ? 1 : 2; }
-__host__ __device__ constexpr int t2_max_chunk(int cin, int es) { return cin == 8 ? (es == 1 ? 2 : 4) : (es == 1 ? 3 : 5); }
+__host__ __device__ constexpr int t2_epi_sets(int cin, int cout, int sd) { return (sd == 2 || (cin == 8 && cout == 1)) ? 1 : 2; }
+__host__ __device__ constexpr int t2_max_chunk(int cin, int es, int sd) {
+  return sd == 2 ? 1 : (cin == 8 ? (es == 1 ? 2 : 4) : (cin == 16 ? (es == 1 ? 2 : 3) : (es == 1 ? 3 : 5)));
+}
 
-template <int CIN, int COUT>
+template <int CIN, int COUT, int SD>
 __global__ void __launch_bounds__(T2_THREADS, 1)
 tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_constant__ T2Plan pl) {
-  constexpr int ES = t2_epi_sets(CIN, COUT);
+  constexpr int ES = t2_epi_sets(CIN, COUT, SD);
+  constexpr int NSG = SD == 2 ? 4 : 1;
   constexpr int EPI_WARPS = 4 * ES, PROD_WARPS = 12 - EPI_WARPS, PT = PROD_WARPS * 32;
-  constexpr int MAXC = t2_max_chunk(CIN, ES);
-  constexpr bool PIPE = (CIN == 1) || (ES == 1);       // register double-buffering of the staged pair
+  constexpr int MAXC = t2_max_chunk(CIN, ES, SD);
+  constexpr bool PIPE = SD == 1 && CIN != 16 && ((CIN == 1) || (ES == 1));   // register double-buffering of the staged pair
   constexpr int NJ = 16 / COUT;                        // output planes per epilogue item (16 TMEM columns)
 
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -87,10 +97,10 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int SRB = pl.SR * 16;                   // bytes per staged plane
-  const int PAIRB = 2 * SRB;
+  const int PAIRB = 2 * NSG * SRB;              // ring slot: [K half][sub-grid][rows]
   uint8_t* ring = smem;
   uint8_t* wts = smem + (size_t)pl.R * PAIRB;
-  const int H2 = pl.OB / 2;
+  const int H2 = pl.ppb;                        // ring slots consumed per block
 
   // ---------------------------------------------------------------- one-time setup
   if (tid == 0) {
@@ -127,24 +137,34 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  // Toeplitz weight blocks: element (n, k) of a block = W[tap(i - j, dh, dw)][ci][co], canonical K-major layout
-  for (int b = 0; b < pl.nblk; ++b) {
-    const T2Blk bk = pl.blk[b];
-    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(wts + (size_t)pl.blk_off16[b] * 16);
-    const int nel = bk.nj * COUT * 16;
-    for (int e = tid; e < nel; e += T2_THREADS) {
-      const int n = e >> 4, k = e & 15;
-      const int chunk = k >> 3, el = k & 7;
-      const int j = bk.j0 + n / COUT, co = n % COUT;
-      const int ddr = bk.i0 + chunk - j;
-      int ci, dwr;
-      if constexpr (CIN == 1) { ci = 0; dwr = el; } else { ci = el; dwr = bk.dw; }
-      float w = 0.f;
-      if (ddr >= 0 && ddr <= pl.span_d && dwr <= pl.span_w) {
-        const int widx = lut[bk.ph][ddr * 9 + bk.dh * 3 + dwr];
-        if (widx >= 0) w = __ldg(a.w + (size_t)widx * g.wst_t + (size_t)ci * g.wst_ci + (size_t)co * g.wst_co);
+  // Toeplitz weight blocks: element (n, k) of a block = W[tap(i - j, dh, dw)][ci][co], canonical K-major layout.
+  // The raw weights (a few KB, contiguous) are first copied into the still unused ring area, coalesced.
+  {
+    float* wraw = reinterpret_cast<float*>(ring);
+    const int nraw = min(g.wst_ci, g.wst_co) * CIN * COUT;      // kernel volume * cin * cout
+    for (int i = tid; i < nraw; i += T2_THREADS) wraw[i] = __ldg(a.w + i);
+    __syncthreads();
+    for (int b = 0; b < pl.nblk; ++b) {
+      const T2Blk bk = pl.blk[b];
+      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(wts + (size_t)pl.blk_off16[b] * 16);
+      const int nel = bk.nj * COUT * 16;
+      for (int e = tid; e < nel; e += T2_THREADS) {
+        const int n = e >> 4, k = e & 15;
+        const int chunk = k >> 3, el = k & 7;
+        const int j = bk.j0 + n / COUT, co = n % COUT;
+        // bk.i0 = window plane of K half 0; the second half is the next plane (1 / 8 channels) or the same plane's
+        // channels 8..15; an output plane j reads window plane SD*j + kd
+        const int ddr = bk.i0 + (CIN == 16 ? 0 : chunk) - SD * j;
+        int ci, dwr;
+        if constexpr (CIN == 1) { ci = 0; dwr = el; } else if constexpr (CIN == 16) { ci = chunk * 8 + el; dwr = bk.dw; }
+        else { ci = el; dwr = bk.dw; }
+        float w = 0.f;
+        if (ddr >= 0 && ddr <= pl.span_d && dwr <= pl.span_w) {
+          const int widx = lut[bk.ph][ddr * 9 + bk.dh * 3 + dwr];
+          if (widx >= 0) w = wraw[widx * g.wst_t + ci * g.wst_ci + co * g.wst_co];
+        }
+        dst[(((n >> 3) * 256 + chunk * 128 + (n & 7) * 16) >> 1) + el] = __float2bfloat16(w);
       }
-      dst[(((n >> 3) * 256 + chunk * 128 + (n & 7) * 16) >> 1) + el] = __float2bfloat16(w);
     }
   }
   if (warp < 4) {                               // all MMAs accumulate: start from zero
@@ -314,82 +334,85 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
         sh[c] = affine ? __ldg(a.in_shift + grp * CIN + c) : 0.f;
       }
       // the chunks this thread stages are the same for every plane of the column
-      int goff[MAXC];      // float offset of the chunk's first voxel inside its plane; -2 zero chunk; -1 none
+      int goff[NSG][MAXC]; // float offset of the chunk's first voxel inside its plane; -2 zero chunk; -1 none
       int wlim[MAXC];      // CIN 1: number of in-range w elements of the chunk
 #pragma unroll
-      for (int k = 0; k < MAXC; ++k) {
-        const int s = ptid + k * PT;
-        goff[k] = -1; wlim[k] = 0;
-        if (s < pl.SR) {
-          const int rr = t * pl.TR + s;
-          const int hh = rr / pl.PW, ww = rr - hh * pl.PW;
-          const int ih = hh + pl.lo_h, iw = ww + pl.lo_w;
-          goff[k] = -2;
-          if (ih >= 0 && ih < g.inH && iw >= 0 && iw < g.inW) {
-            goff[k] = (ih * g.inW + iw) * CIN;
-            wlim[k] = min(pl.span_w + 1, g.inW - iw);
-          }
-        }
-      }
-      using Buf = typename std::conditional<CIN == 8, float4[2][MAXC][2], float[2][MAXC][3]>::type;
-      auto load_pair = [&](int P, Buf& v) {
+      for (int sg = 0; sg < NSG; ++sg)
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          const int ip = qd0 + pl.lo_d + 2 * P + hf;
-          const bool p_ok = ip >= 0 && ip < g.inD;
-          const float* base = in_n + (size_t)(p_ok ? ip : 0) * plane_in;
-#pragma unroll
-          for (int k = 0; k < MAXC; ++k) {
-            if constexpr (CIN == 8) {
-              if (p_ok && goff[k] >= 0) {
-                const float4* p = reinterpret_cast<const float4*>(base + goff[k]);
-                v[hf][k][0] = __ldg(p);
-                v[hf][k][1] = __ldg(p + 1);
-              }
-            } else {
-#pragma unroll
-              for (int e = 0; e < 3; ++e) {
-                v[hf][k][e] = 0.f;
-                if (p_ok && goff[k] >= 0 && e < wlim[k]) v[hf][k][e] = __ldg(base + goff[k] + e);
-              }
+        for (int k = 0; k < MAXC; ++k) {
+          const int s = ptid + k * PT;
+          goff[sg][k] = -1;
+          if (sg == 0) wlim[k] = 0;
+          if (s < pl.SR) {
+            const int rr = t * pl.TR + s;
+            const int hh = rr / pl.PW, ww = rr - hh * pl.PW;
+            const int ih = SD * hh + (sg >> 1) + pl.lo_h, iw = SD * ww + (sg & 1) + pl.lo_w;
+            goff[sg][k] = -2;
+            if (ih >= 0 && ih < g.inH && iw >= 0 && iw < g.inW) {
+              goff[sg][k] = (ih * g.inW + iw) * CIN;
+              if (sg == 0) wlim[k] = min(pl.span_w + 1, g.inW - iw);
             }
           }
         }
-      };
-      auto store_pair = [&](int P, const Buf& v) {
-        const int G = pair_base + P, slot = G % pl.R, use = G / pl.R;
-        if (use > 0) mbar_wait(smem_u32(&empty_bar[slot]), (uint32_t)((use - 1) & 1));
-        uint8_t* dst0 = ring + (size_t)slot * PAIRB;
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          const int ip = qd0 + pl.lo_d + 2 * P + hf;
-          const bool p_ok = ip >= 0 && ip < g.inD;
-#pragma unroll
-          for (int k = 0; k < MAXC; ++k) {
-            if (goff[k] == -1) continue;
-            uint4 pk = make_uint4(0u, 0u, 0u, 0u);
-            if (p_ok && goff[k] >= 0) {
-              if constexpr (CIN == 8) {
-                const float4 lo = v[hf][k][0], hi = v[hf][k][1];
-                pk = make_uint4(pack_bf16(fmaf(lo.x, sc[0], sh[0]), fmaf(lo.y, sc[1], sh[1])),
-                                pack_bf16(fmaf(lo.z, sc[2], sh[2]), fmaf(lo.w, sc[3], sh[3])),
-                                pack_bf16(fmaf(hi.x, sc[4], sh[4]), fmaf(hi.y, sc[5], sh[5])),
-                                pack_bf16(fmaf(hi.z, sc[6], sh[6]), fmaf(hi.w, sc[7], sh[7])));
-              } else {
-                // one input channel: the K-chunk of a row is its own voxel and the next span_w voxels along w
-                float f[3];
-#pragma unroll
-                for (int e = 0; e < 3; ++e) f[e] = e < wlim[k] ? fmaf(v[hf][k][e], sc[0], sh[0]) : 0.f;
-                pk = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], 0.f), 0u, 0u);
-              }
-            }
-            *reinterpret_cast<uint4*>(dst0 + (size_t)hf * SRB + (size_t)(ptid + k * PT) * 16) = pk;
-          }
-        }
-        fence_async_smem();
-        mbar_arrive(smem_u32(&full_bar[slot]));
-      };
       if constexpr (PIPE) {
+        using Buf = typename std::conditional<CIN == 8, float4[2][MAXC][2], float[2][MAXC][3]>::type;
+        auto load_pair = [&](int P, Buf& v) {
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const int ip = qd0 + pl.lo_d + 2 * P + hf;
+            const bool p_ok = ip >= 0 && ip < g.inD;
+            const float* base = in_n + (size_t)(p_ok ? ip : 0) * plane_in;
+#pragma unroll
+            for (int k = 0; k < MAXC; ++k) {
+              if constexpr (CIN == 8) {
+                if (p_ok && goff[0][k] >= 0) {
+                  const float4* p = reinterpret_cast<const float4*>(base + goff[0][k]);
+                  v[hf][k][0] = __ldg(p);
+                  v[hf][k][1] = __ldg(p + 1);
+                }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 3; ++e) {
+                  v[hf][k][e] = 0.f;
+                  if (p_ok && goff[0][k] >= 0 && e < wlim[k]) v[hf][k][e] = __ldg(base + goff[0][k] + e);
+                }
+              }
+            }
+          }
+        };
+        auto store_pair = [&](int P, const Buf& v) {
+          const int G = pair_base + P, slot = G % pl.R, use = G / pl.R;
+          if (use > 0) mbar_wait(smem_u32(&empty_bar[slot]), (uint32_t)((use - 1) & 1));
+          uint8_t* dst0 = ring + (size_t)slot * PAIRB;
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const int ip = qd0 + pl.lo_d + 2 * P + hf;
+            const bool p_ok = ip >= 0 && ip < g.inD;
+#pragma unroll
+            for (int k = 0; k < MAXC; ++k) {
+              if (goff[0][k] == -1) continue;
+              uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+              if (p_ok && goff[0][k] >= 0) {
+                if constexpr (CIN == 8) {
+                  const float4 lo = v[hf][k][0], hi = v[hf][k][1];
+                  pk = make_uint4(pack_bf16(fmaf(lo.x, sc[0], sh[0]), fmaf(lo.y, sc[1], sh[1])),
+                                  pack_bf16(fmaf(lo.z, sc[2], sh[2]), fmaf(lo.w, sc[3], sh[3])),
+                                  pack_bf16(fmaf(hi.x, sc[4], sh[4]), fmaf(hi.y, sc[5], sh[5])),
+                                  pack_bf16(fmaf(hi.z, sc[6], sh[6]), fmaf(hi.w, sc[7], sh[7])));
+                } else {
+                  // one input channel: the K-chunk of a row is its own voxel and the next span_w voxels along w
+                  float f[3];
+#pragma unroll
+                  for (int e = 0; e < 3; ++e) f[e] = e < wlim[k] ? fmaf(v[hf][k][e], sc[0], sh[0]) : 0.f;
+                  pk = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], 0.f), 0u, 0u);
+                }
+              }
+              *reinterpret_cast<uint4*>(dst0 + (size_t)hf * SRB + (size_t)(ptid + k * PT) * 16) = pk;
+            }
+          }
+          fence_async_smem();
+          mbar_arrive(smem_u32(&full_bar[slot]));
+        };
         Buf v0, v1;
         load_pair(0, v0);
         for (int P = 0; P < npairs; P += 2) {
@@ -401,10 +424,96 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
           }
         }
       } else {
-        Buf v0;
+        // generic path: one [K half][sub-grid] array at a time, its chunks in flight together
         for (int P = 0; P < npairs; ++P) {
-          load_pair(P, v0);
-          store_pair(P, v0);
+          const int G = pair_base + P, slot = G % pl.R, use = G / pl.R;
+          if (use > 0) mbar_wait(smem_u32(&empty_bar[slot]), (uint32_t)((use - 1) & 1));
+          uint8_t* dst0 = ring + (size_t)slot * PAIRB;
+          if constexpr (CIN == 16) {
+            const int ip = SD * qd0 + pl.lo_d + P;
+            const bool p_ok = ip >= 0 && ip < g.inD;
+            const float* base = in_n + (size_t)(p_ok ? ip : 0) * plane_in;
+#pragma unroll
+            for (int sg = 0; sg < NSG; ++sg) {
+              float4 v[MAXC][4];
+#pragma unroll
+              for (int k = 0; k < MAXC; ++k)
+                if (p_ok && goff[sg][k] >= 0) {
+                  const float4* p = reinterpret_cast<const float4*>(base + goff[sg][k]);
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) v[k][q] = __ldg(p + q);
+                }
+#pragma unroll
+              for (int k = 0; k < MAXC; ++k) {
+                if (goff[sg][k] == -1) continue;
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                  uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+                  if (p_ok && goff[sg][k] >= 0) {
+                    const float4 lo = v[k][2 * hf], hi = v[k][2 * hf + 1];
+                    const int c0 = 8 * hf;
+                    pk = make_uint4(pack_bf16(fmaf(lo.x, sc[c0], sh[c0]), fmaf(lo.y, sc[c0 + 1], sh[c0 + 1])),
+                                    pack_bf16(fmaf(lo.z, sc[c0 + 2], sh[c0 + 2]), fmaf(lo.w, sc[c0 + 3], sh[c0 + 3])),
+                                    pack_bf16(fmaf(hi.x, sc[c0 + 4], sh[c0 + 4]), fmaf(hi.y, sc[c0 + 5], sh[c0 + 5])),
+                                    pack_bf16(fmaf(hi.z, sc[c0 + 6], sh[c0 + 6]), fmaf(hi.w, sc[c0 + 7], sh[c0 + 7])));
+                  }
+                  *reinterpret_cast<uint4*>(dst0 + (size_t)(hf * NSG + sg) * SRB + (size_t)(ptid + k * PT) * 16) = pk;
+                }
+              }
+            }
+          } else {
+            float4 v[2][NSG][MAXC][CIN == 8 ? 2 : 1];
+            bool pok[2];
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              const int ip = SD * qd0 + pl.lo_d + 2 * P + hf;
+              pok[hf] = ip >= 0 && ip < g.inD;
+              const float* base = in_n + (size_t)(pok[hf] ? ip : 0) * plane_in;
+#pragma unroll
+              for (int sg = 0; sg < NSG; ++sg)
+#pragma unroll
+                for (int k = 0; k < MAXC; ++k)
+                  if (pok[hf] && goff[sg][k] >= 0) {
+                    if constexpr (CIN == 8) {
+                      const float4* p = reinterpret_cast<const float4*>(base + goff[sg][k]);
+                      v[hf][sg][k][0] = __ldg(p);
+                      v[hf][sg][k][1] = __ldg(p + 1);
+                    } else {
+                      v[hf][sg][k][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                      if (0 < wlim[k]) v[hf][sg][k][0].x = __ldg(base + goff[sg][k]);
+                      if (1 < wlim[k]) v[hf][sg][k][0].y = __ldg(base + goff[sg][k] + 1);
+                      if (2 < wlim[k]) v[hf][sg][k][0].z = __ldg(base + goff[sg][k] + 2);
+                    }
+                  }
+            }
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+              for (int sg = 0; sg < NSG; ++sg)
+#pragma unroll
+                for (int k = 0; k < MAXC; ++k) {
+                  if (goff[sg][k] == -1) continue;
+                  uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+                  if (pok[hf] && goff[sg][k] >= 0) {
+                    if constexpr (CIN == 8) {
+                      const float4 lo = v[hf][sg][k][0], hi = v[hf][sg][k][1];
+                      pk = make_uint4(pack_bf16(fmaf(lo.x, sc[0], sh[0]), fmaf(lo.y, sc[1], sh[1])),
+                                      pack_bf16(fmaf(lo.z, sc[2], sh[2]), fmaf(lo.w, sc[3], sh[3])),
+                                      pack_bf16(fmaf(hi.x, sc[4], sh[4]), fmaf(hi.y, sc[5], sh[5])),
+                                      pack_bf16(fmaf(hi.z, sc[6], sh[6]), fmaf(hi.w, sc[7], sh[7])));
+                    } else {
+                      const float4 t = v[hf][sg][k][0];
+                      const float f0 = 0 < wlim[k] ? fmaf(t.x, sc[0], sh[0]) : 0.f;
+                      const float f1 = 1 < wlim[k] ? fmaf(t.y, sc[0], sh[0]) : 0.f;
+                      const float f2 = 2 < wlim[k] ? fmaf(t.z, sc[0], sh[0]) : 0.f;
+                      pk = make_uint4(pack_bf16(f0, f1), pack_bf16(f2, 0.f), 0u, 0u);
+                    }
+                  }
+                  *reinterpret_cast<uint4*>(dst0 + (size_t)(hf * NSG + sg) * SRB + (size_t)(ptid + k * PT) * 16) = pk;
+                }
+          }
+          fence_async_smem();
+          mbar_arrive(smem_u32(&full_bar[slot]));
         }
       }
       pair_base += npairs;
@@ -416,7 +525,7 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
     // issues the tcgen05.mma / tcgen05.commit instructions, so operands stay in uniform registers.
     const int rb = warp - T2_MMA_WARP;
     const uint32_t ring16 = (smem_u32(ring) >> 4) + (uint32_t)rb * 128u, w16 = smem_u32(wts) >> 4;
-    const uint32_t lbo_field = ((uint32_t)SRB >> 4) << 16;
+    const uint32_t lbo_field = ((uint32_t)(NSG * SRB) >> 4) << 16;
     const uint32_t a_hi = (128u >> 4) | (1u << 14), b_hi = (256u >> 4) | (1u << 14);
     for (int col = blockIdx.x; col < ncols; col += gridDim.x) {
       const int dc = col % pl.ndchunks;
@@ -475,17 +584,23 @@ static constexpr int kT2SmemBudget = 212 * 1024;
 
 // gs[0..ng): the gathers of one layer pass that share their input (ng > 1: output-parity phases).
 // merged: gs[0] with every phase's taps (Tap::pad_ = phase).
+static inline int t2_ceil_div(int a, int b) { return a >= 0 ? (a + b - 1) / b : -((-a) / b); }
+
 static bool t2_build_plan(int cin, int cout, const Geom* gs, int ng, Geom& merged, T2Plan& pl) {
   if (ng < 1 || ng > T2_MAX_PH) return false;
-  if (cin != 1 && cin != 8) return false;
+  if (cin != 1 && cin != 8 && cin != 16) return false;
   if (cout != 1 && cout != 8 && cout != 16) return false;
+  const int sd = gs[0].sin;
+  if (sd != 1 && sd != 2) return false;
+  if (sd == 2 && (ng != 1 || cin != 8 || cout == 1)) return false;     // strided gathers: 8 input channels, one phase
+  if (cin == 16 && cout == 1) return false;
   merged = gs[0];
   int ntaps = 0;
   int lo[3] = {127, 127, 127}, hi[3] = {-127, -127, -127};
   int qmax[3] = {0, 0, 0};
   for (int p = 0; p < ng; ++p) {
     const Geom& g = gs[p];
-    if (g.sin != 1 || g.ntaps < 1 || g.sout != gs[0].sout) return false;
+    if (g.sin != sd || g.ntaps < 1 || g.sout != gs[0].sout) return false;
     if (g.inD != gs[0].inD || g.inH != gs[0].inH || g.inW != gs[0].inW) return false;
     if (g.qD > 32767 || g.qH > 32767 || g.qW > 32767) return false;
     for (int t = 0; t < g.ntaps; ++t) {
@@ -504,9 +619,12 @@ static bool t2_build_plan(int cin, int cout, const Geom* gs, int ng, Geom& merge
   }
   merged.ntaps = ntaps;
   pl.nph = ng;
+  pl.sd = sd;
+  pl.pps = cin == 16 ? 1 : 2;
+  pl.nsg = sd == 2 ? 4 : 1;
   pl.lo_d = lo[0]; pl.lo_h = lo[1]; pl.lo_w = lo[2];
   pl.span_d = hi[0] - lo[0]; pl.span_h = hi[1] - lo[1]; pl.span_w = hi[2] - lo[2];
-  if (pl.span_d > 2 || pl.span_h > 2 || pl.span_w > 2) return false;
+  if (pl.span_d > 4 || pl.span_h > 2 || pl.span_w > 2) return false;
   int lut[T2_MAX_PH][45];
   for (int p = 0; p < ng; ++p)
     for (int i = 0; i < 45; ++i) lut[p][i] = -1;
@@ -515,59 +633,73 @@ static bool t2_build_plan(int cin, int cout, const Geom* gs, int ng, Geom& merge
     lut[tp.pad_][(tp.dd - lo[0]) * 9 + (tp.dh - lo[1]) * 3 + (tp.dw - lo[2])] = tp.widx;
   }
 
-  pl.PW = cin == 1 ? qmax[2] : qmax[2] + pl.span_w;
+  // row frame: a tap (kh, kw) = (sd*mh + parity_h, sd*mw + parity_w) is the row shift mh*PW + mw in its sub-grid
+  const int sm_h = pl.span_h / sd, sm_w = pl.span_w / sd;
+  pl.PW = cin == 1 ? qmax[2] : qmax[2] + sm_w;
   pl.RTOT = qmax[1] * pl.PW;
   pl.qDmax = qmax[0];
-  pl.OB = cout == 1 ? 16 : 8;
-  pl.NPAIR = (pl.OB + pl.span_d + 1) / 2;
+  pl.OB = cout == 1 ? 16 : (sd == 2 ? 4 : 8);
+  const int wpl = sd * (pl.OB - 1) + pl.span_d + 1;      // input planes one block reads
+  pl.NPAIR = (wpl + pl.pps - 1) / pl.pps;
+  pl.ppb = sd * pl.OB / pl.pps;
   pl.ACCW = pl.OB * cout;
-  if (pl.NPAIR > T2_MAX_PAIR) return false;
+  if (pl.NPAIR > T2_MAX_PAIR || pl.ppb > pl.NPAIR) return false;
 
-  // MMA list + weight blocks (deduplicated: interior pairs share one shift-invariant block)
+  // MMA list + weight blocks (deduplicated: interior slots share one shift-invariant block)
   struct Key { int ph, rel, nj, dh, dw, off16; };
   Key keys[T2_MAX_BLK];
+  int m_sg[T2_MAX_MMA], m_mh[T2_MAX_MMA], m_mw[T2_MAX_MMA];
   int nblk = 0, nmma = 0, woff = 0;
   for (int ph = 0; ph < ng; ++ph)
     for (int p = 0; p <= pl.NPAIR; ++p) {
       if (nmma > 255) return false;
       pl.ph[ph].pair_begin[p] = (uint8_t)nmma;
       if (p == pl.NPAIR) break;
-      const int j0 = cout == 1 ? 0 : (2 * p - 2 > 0 ? 2 * p - 2 : 0);
-      const int j1 = cout == 1 ? pl.OB - 1 : (2 * p + 1 < pl.OB - 1 ? 2 * p + 1 : pl.OB - 1);
+      const int i_lo = pl.pps * p, i_hi = i_lo + pl.pps - 1;
+      int j0 = t2_ceil_div(i_lo - pl.span_d, sd), j1 = i_hi / sd;
+      if (j0 < 0) j0 = 0;
+      if (j1 > pl.OB - 1) j1 = pl.OB - 1;
+      if (cout == 1) { j0 = 0; j1 = pl.OB - 1; }
       if (j1 < j0) continue;
+      if (cout == 8) {                           // N = nj * 8 must be a multiple of 16; keep the column offset 16-aligned
+        j0 &= ~1;
+        if (((j1 - j0 + 1) & 1) != 0) ++j1;      // OB is even, so an even j1 is never the last plane
+      }
       const int nj = j1 - j0 + 1;
-      for (int dh = 0; dh <= pl.span_h; ++dh)
-        for (int dw = 0; dw <= (cin == 1 ? 0 : pl.span_w); ++dw) {
-          bool any = false;                       // does the block hold any tap?
-          for (int chunk = 0; chunk < 2 && !any; ++chunk)
-            for (int j = j0; j <= j1 && !any; ++j) {
-              const int ddr = 2 * p + chunk - j;
-              if (ddr < 0 || ddr > pl.span_d) continue;
-              for (int e = 0; e <= (cin == 1 ? pl.span_w : 0); ++e)
-                if (lut[ph][ddr * 9 + dh * 3 + (cin == 1 ? e : dw)] >= 0) any = true;
+      for (int sg = 0; sg < pl.nsg; ++sg)
+        for (int mh = 0; sd * mh + (sg >> 1) <= pl.span_h; ++mh)
+          for (int mw = 0; mw <= (cin == 1 ? 0 : sm_w) && sd * mw + (sg & 1) <= pl.span_w; ++mw) {
+            const int kh = sd * mh + (sg >> 1), kw = sd * mw + (sg & 1);
+            bool any = false;                     // does the block hold any tap?
+            for (int chunk = 0; chunk < 2 && !any; ++chunk)
+              for (int j = j0; j <= j1 && !any; ++j) {
+                const int kd = i_lo + (cin == 16 ? 0 : chunk) - sd * j;
+                if (kd < 0 || kd > pl.span_d) continue;
+                for (int e = 0; e <= (cin == 1 ? pl.span_w : 0); ++e)
+                  if (lut[ph][kd * 9 + kh * 3 + (cin == 1 ? e : kw)] >= 0) any = true;
+              }
+            if (!any) continue;
+            int found = -1;
+            for (int k = 0; k < nblk; ++k)
+              if (keys[k].ph == ph && keys[k].rel == i_lo - sd * j0 && keys[k].nj == nj && keys[k].dh == kh && keys[k].dw == kw)
+                found = k;
+            if (found < 0) {
+              if (nblk >= T2_MAX_BLK) return false;
+              found = nblk++;
+              keys[found] = Key{ph, i_lo - sd * j0, nj, kh, kw, woff >> 4};
+              pl.blk[found].i0 = (int8_t)i_lo; pl.blk[found].j0 = (int8_t)j0; pl.blk[found].nj = (int8_t)nj;
+              pl.blk[found].dh = (int8_t)kh; pl.blk[found].dw = (int8_t)kw; pl.blk[found].ph = (int8_t)ph;
+              pl.blk_off16[found] = (uint16_t)(woff >> 4);
+              woff += nj * cout * 32;
             }
-          if (!any) continue;
-          int found = -1;
-          for (int k = 0; k < nblk; ++k)
-            if (keys[k].ph == ph && keys[k].rel == 2 * p - j0 && keys[k].nj == nj && keys[k].dh == dh && keys[k].dw == dw)
-              found = k;
-          if (found < 0) {
-            if (nblk >= T2_MAX_BLK) return false;
-            found = nblk++;
-            keys[found] = Key{ph, 2 * p - j0, nj, dh, dw, woff >> 4};
-            pl.blk[found].i0 = (int8_t)(2 * p); pl.blk[found].j0 = (int8_t)j0; pl.blk[found].nj = (int8_t)nj;
-            pl.blk[found].dh = (int8_t)dh; pl.blk[found].dw = (int8_t)dw; pl.blk[found].ph = (int8_t)ph;
-            pl.blk_off16[found] = (uint16_t)(woff >> 4);
-            woff += nj * cout * 32;
+            if (nmma >= T2_MAX_MMA) return false;
+            T2Mma& m = pl.mma[nmma];
+            m_sg[nmma] = sg; m_mh[nmma] = mh; m_mw[nmma] = cin == 1 ? 0 : mw;
+            ++nmma;
+            m.b_lo = (uint32_t)keys[found].off16 | (8u << 16);          // LBO = 128 bytes between the two K chunks
+            m.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((nj * cout) >> 3) << 17) | ((128u >> 4) << 24);
+            m.dcol = (uint32_t)(j0 * cout);
           }
-          if (nmma >= T2_MAX_MMA) return false;
-          T2Mma& m = pl.mma[nmma++];
-          m.a_shift = (uint32_t)(dh * pl.PW + (cin == 1 ? 0 : dw));
-          if (getenv("VAEGAM_T2_EXPERIMENT_ALIGN")) m.a_shift &= ~7u;      // timing experiment only (wrong results)
-          m.b_lo = (uint32_t)keys[found].off16 | (8u << 16);          // LBO = 128 bytes between the two K chunks
-          m.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((nj * cout) >> 3) << 17) | ((128u >> 4) << 24);
-          m.dcol = (uint32_t)(j0 * cout);
-        }
     }
   pl.nmma = nmma;
   pl.nblk = nblk;
@@ -575,8 +707,8 @@ static bool t2_build_plan(int cin, int cout, const Geom* gs, int ng, Geom& merge
   if (pl.wbytes > 96 * 1024) return false;
 
   // rows per tile: as many 128-row blocks as TMEM (2 buffers), the producers' reach and shared memory allow
-  const int es = t2_epi_sets(cin, cout);
-  const int max_sr = t2_max_chunk(cin, es) * (12 - 4 * es) * 32;
+  const int es = t2_epi_sets(cin, cout, sd);
+  const int max_sr = t2_max_chunk(cin, es, sd) * (12 - 4 * es) * 32;
   int nrb_max = 512 / (2 * pl.ACCW);
   if (nrb_max > 4) nrb_max = 4;
   const int need = (pl.RTOT + 127) / 128;
@@ -585,12 +717,13 @@ static bool t2_build_plan(int cin, int cout, const Geom* gs, int ng, Geom& merge
   double best_eff = 0.0;
   for (int nrb = nrb_max; nrb >= 1; --nrb) {
     const int tr = 128 * nrb;
-    const int sr = (tr + pl.span_h * pl.PW + (cin == 1 ? 0 : pl.span_w) + 7) & ~7;
+    const int sr = (tr + sm_h * pl.PW + (cin == 1 ? 0 : sm_w) + 7) & ~7;
     if (sr > max_sr) continue;
+    const size_t slot = (size_t)2 * pl.nsg * sr * 16;
     int r = pl.NPAIR + 3;
     if (r > T2_MAX_RING) r = T2_MAX_RING;
-    while (r > pl.NPAIR + 1 && (size_t)r * 2 * sr * 16 + pl.wbytes > (size_t)kT2SmemBudget) --r;
-    if ((size_t)r * 2 * sr * 16 + pl.wbytes > (size_t)kT2SmemBudget) continue;
+    while (r > pl.NPAIR + 1 && (size_t)r * slot + pl.wbytes > (size_t)kT2SmemBudget) --r;
+    if ((size_t)r * slot + pl.wbytes > (size_t)kT2SmemBudget) continue;
     const int nt = (pl.RTOT + tr - 1) / tr;
     // useful rows per staged row: tile quantisation and the h-halo that every tile re-stages
     const double eff = (double)pl.RTOT / ((double)nt * sr);
@@ -599,8 +732,9 @@ static bool t2_build_plan(int cin, int cout, const Geom* gs, int ng, Geom& merge
   if (best < 1) return false;
   pl.nrb = best;
   pl.TR = 128 * best;
-  pl.SR = (pl.TR + pl.span_h * pl.PW + (cin == 1 ? 0 : pl.span_w) + 7) & ~7;
+  pl.SR = (pl.TR + sm_h * pl.PW + (cin == 1 ? 0 : sm_w) + 7) & ~7;
   pl.R = best_r;
+  for (int m = 0; m < nmma; ++m) pl.mma[m].a_shift = (uint32_t)(m_sg[m] * pl.SR + m_mh[m] * pl.PW + m_mw[m]);
   pl.ntiles = (pl.RTOT + pl.TR - 1) / pl.TR;
   int tc = 32;
   while (tc < 2 * pl.nrb * pl.ACCW) tc <<= 1;
@@ -632,21 +766,21 @@ int tc2_describe(int cin, int cout, const Geom* gs, int ng, char* buf, size_t ca
   if (!t2_build_plan(cin, cout, gs, ng, merged, pl)) return 0;
   const long long cols = (long long)merged.N * pl.ntiles * pl.ndchunks;
   return snprintf(buf, cap,
-                  "tc2 cin=%d cout=%d phases=%d q=(%d,%d,%d) taps=%d PW=%d RTOT=%d TR=%d ntiles=%d SR=%d OB=%d NPAIR=%d R=%d "
+                  "tc2 cin=%d cout=%d sin=%d phases=%d q=(%d,%d,%d) taps=%d PW=%d RTOT=%d TR=%d ntiles=%d SR=%d OB=%d NPAIR=%d R=%d "
                   "ACCW=%d tmem=%d nmma=%d nblk=%d wbytes=%d smem=%zu dchunk=%d ndchunks=%d cols=%lld",
-                  cin, cout, ng, pl.qDmax, pl.RTOT / pl.PW, merged.qW, merged.ntaps, pl.PW, pl.RTOT, pl.TR, pl.ntiles,
+                  cin, cout, pl.sd, ng, pl.qDmax, pl.RTOT / pl.PW, merged.qW, merged.ntaps, pl.PW, pl.RTOT, pl.TR, pl.ntiles,
                   pl.SR, pl.OB, pl.NPAIR, pl.R, pl.ACCW, pl.tmem_cols, pl.nmma, pl.nblk, pl.wbytes,
-                  (size_t)pl.R * 2 * pl.SR * 16 + pl.wbytes, pl.dchunk, pl.ndchunks, cols);
+                  (size_t)pl.R * 2 * pl.nsg * pl.SR * 16 + pl.wbytes, pl.dchunk, pl.ndchunks, cols);
 }
 
-template <int CIN, int COUT>
+template <int CIN, int COUT, int SD>
 static int launch_tc2_t(const Geom& g, const GatherArgs& a, const T2Plan& pl, cudaStream_t st) {
-  const size_t smem = (size_t)pl.R * 2 * pl.SR * 16 + pl.wbytes;
-  VG_CUDA(cudaFuncSetAttribute(tc2_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = (size_t)pl.R * 2 * pl.nsg * pl.SR * 16 + pl.wbytes;
+  VG_CUDA(cudaFuncSetAttribute(tc2_kernel<CIN, COUT, SD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long cols = (long long)g.N * pl.ntiles * pl.ndchunks;
   const int sms = vg_sm_count();
   const unsigned grid = (unsigned)(cols < sms ? cols : sms);
-  tc2_kernel<CIN, COUT><<<grid, T2_THREADS, smem, st>>>(g, a, pl);
+  tc2_kernel<CIN, COUT, SD><<<grid, T2_THREADS, smem, st>>>(g, a, pl);
   VG_LAUNCH_CHECK();
   return VG_OK;
 }
@@ -655,12 +789,19 @@ int launch_tc2_gather(int cin, int cout, const Geom* gs, int ng, const GatherArg
   T2Plan pl;
   Geom merged;
   if (!t2_build_plan(cin, cout, gs, ng, merged, pl)) { set_error("plane-folded tensor-core path: unsupported geometry"); return VG_EINVAL; }
-  if (cin == 1 && cout == 8) return launch_tc2_t<1, 8>(merged, a, pl, st);
-  if (cin == 1 && cout == 16) return launch_tc2_t<1, 16>(merged, a, pl, st);
-  if (cin == 8 && cout == 1) return launch_tc2_t<8, 1>(merged, a, pl, st);
-  if (cin == 8 && cout == 8) return launch_tc2_t<8, 8>(merged, a, pl, st);
-  if (cin == 8 && cout == 16) return launch_tc2_t<8, 16>(merged, a, pl, st);
-  set_error("plane-folded tensor-core path: unsupported channel pair (%d,%d)", cin, cout);
+  if (pl.sd == 2) {
+    if (cin == 8 && cout == 8) return launch_tc2_t<8, 8, 2>(merged, a, pl, st);
+    if (cin == 8 && cout == 16) return launch_tc2_t<8, 16, 2>(merged, a, pl, st);
+  } else {
+    if (cin == 1 && cout == 8) return launch_tc2_t<1, 8, 1>(merged, a, pl, st);
+    if (cin == 1 && cout == 16) return launch_tc2_t<1, 16, 1>(merged, a, pl, st);
+    if (cin == 8 && cout == 1) return launch_tc2_t<8, 1, 1>(merged, a, pl, st);
+    if (cin == 8 && cout == 8) return launch_tc2_t<8, 8, 1>(merged, a, pl, st);
+    if (cin == 8 && cout == 16) return launch_tc2_t<8, 16, 1>(merged, a, pl, st);
+    if (cin == 16 && cout == 8) return launch_tc2_t<16, 8, 1>(merged, a, pl, st);
+    if (cin == 16 && cout == 16) return launch_tc2_t<16, 16, 1>(merged, a, pl, st);
+  }
+  set_error("plane-folded tensor-core path: unsupported channel pair (%d,%d) at input stride %d", cin, cout, pl.sd);
   return VG_EINVAL;
 }
 

@@ -75,6 +75,7 @@ SIGNATURES = {
     "vg_profile_collect": (_LL, [C.c_char_p, _SZ]),
     "vg_set_conv_mode": (_I, [_I]),
     "vg_get_conv_mode": (_I, []),
+    "vg_set_conv_tuning": (_I, [C.c_char_p, _LL]),
     "vg_conv_describe": (_I, [C.POINTER(VgConvDesc), _I, C.c_char_p, _SZ]),
     "vg_conv_fwd": (_I, [C.POINTER(VgConvDesc), _P, _P, _P, _P, _P, _P, _I, _P, _P]),
     "vg_conv_dgrad": (_I, [C.POINTER(VgConvDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P]),
