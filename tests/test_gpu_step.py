@@ -235,7 +235,7 @@ def test_properties_at_baseline_batch():
         t.backward()
         reps.append((model._last.scalars.clone(), model._flat.grad32.clone()))
     assert rel_err(reps[0][0][:6].cpu(), reps[1][0][:6].cpu()) < 1e-5
-    assert rel_err(reps[0][1].cpu(), reps[1][1].cpu()) < 2e-4
+    assert rel_err(reps[0][1].cpu(), reps[1][1].cpu()) < 2e-3
 
 
 def test_ragged_last_batch_and_single_volume():

@@ -3,6 +3,8 @@
 // BatchNorm statistic groups -> gains -> fused reconstruction/likelihood/GLM pass, and the
 // mirror-image backward.  No host synchronisation, no allocation: every intermediate lives
 // in the caller's workspace, so the sequence can be captured into a CUDA graph.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "gp_core.h"
 
@@ -214,6 +216,53 @@ static int finalize_bn(const BnBuf& bn, const float* gamma, const float* beta, i
   return vg_bn_finalize(bn.stats, gamma, beta, groups, c, count, bn.scale, bn.shift, bn.istd, bn.mistd, st);
 }
 
+// Second stream for work that is off the critical path (the gain stage, every weight gradient): forked and
+// joined with events, so the step is still one ordered unit of work on the caller's stream (and capturable).
+// Disabled while per-operation profiling is on, so that the recorded times are those of un-overlapped kernels.
+constexpr int kSideEvents = 24;
+struct SideStream {
+  cudaStream_t s = nullptr;
+  cudaEvent_t ev[kSideEvents];
+  cudaEvent_t join = nullptr;
+  bool ok = false;
+};
+static SideStream& side_stream() {
+  static SideStream sd;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    const char* e = getenv("VAEGAM_SIDE_STREAM");
+    if (!(e && e[0] == '0') && cudaStreamCreateWithFlags(&sd.s, cudaStreamNonBlocking) == cudaSuccess) {
+      sd.ok = true;
+      for (int i = 0; i < kSideEvents; ++i) sd.ok = sd.ok && cudaEventCreateWithFlags(&sd.ev[i], cudaEventDisableTiming) == cudaSuccess;
+      sd.ok = sd.ok && cudaEventCreateWithFlags(&sd.join, cudaEventDisableTiming) == cudaSuccess;
+    }
+    if (!sd.ok) (void)cudaGetLastError();
+  }
+  return sd;
+}
+struct Fork {
+  SideStream& sd;
+  cudaStream_t st;
+  bool on;
+  int n = 0;
+  Fork(cudaStream_t main) : sd(side_stream()), st(main), on(sd.ok && !profiling()) {}
+  // stream for an off-critical-path launch that depends on everything enqueued on the main stream so far
+  cudaStream_t branch() {
+    if (!on) return st;
+    cudaEventRecord(sd.ev[n], st);
+    cudaStreamWaitEvent(sd.s, sd.ev[n], 0);
+    n = (n + 1) % kSideEvents;
+    return sd.s;
+  }
+  // the main stream waits for everything branched so far
+  void join() {
+    if (!on) return;
+    cudaEventRecord(sd.join, sd.s);
+    cudaStreamWaitEvent(st, sd.join, 0);
+  }
+};
+
 #define PF(idx) (reinterpret_cast<const float*>(io->params[idx]))
 #define GF(idx) (reinterpret_cast<float*>(io->grads[idx]))
 
@@ -378,18 +427,21 @@ extern "C" int vg_step_fwd(const VgStepConfig* cfg, const VgStepIO* io, void* wo
   VG_CUDA(cudaMemsetAsync(w.zero_begin, 0, w.zero_bytes, st));
   cast_eps_kernel<<<cdiv(VP, 256), 256, 0, st>>>(reinterpret_cast<const double*>(io->params[EPSILON]), w.eps32);
   VG_LAUNCH_CHECK();
+  Fork fk(st);
+  VgGainParams gp;
+  fill_gain_params(cfg, io, gp, nullptr);
+  { cudaStream_t gs = fk.branch();          // the gains depend on the covariates and parameters only
+  VG_PROF("gain.fwd", gs);
+  VG_TRY(vg_gain_fwd(&gp, io->covariates, io->eps_g, io->taps, B, cfg->m, io->g, w.kl_terms, io->beta_mean,
+                     io->beta_var, io->status, w.gain_ws, w.gain_ws_bytes, gs));
+  }
   VG_TRY(run_encoder(io, w.e, B, st));
   { VG_PROF("latent.fwd", st);
   VG_TRY(vg_latent_fwd(w.e.heads, io->eps_w, io->eps_d, B, io->z, w.klz, w.d_used, w.zcat,
                        io->status ? io->status + 8 : nullptr, st));
   }
   VG_TRY(run_decoder(io, w.d, w.zcat, NDEC * B, B, io->maps, VP, st));
-  VgGainParams gp;
-  fill_gain_params(cfg, io, gp, nullptr);
-  { VG_PROF("gain.fwd", st);
-  VG_TRY(vg_gain_fwd(&gp, io->covariates, io->eps_g, io->taps, B, cfg->m, io->g, w.kl_terms, io->beta_mean,
-                     io->beta_var, io->status, w.gain_ws, w.gain_ws_bytes, st));
-  }
+  fk.join();
   { VG_PROF("recon_loss.fwd", st);
   VG_TRY(vg_recon_loss_fwd(io->maps, io->g, io->x, w.eps32, io->glm_t, B, V, w.logp, w.norms,
                            cfg->want_maps ? io->cons : nullptr, cfg->want_maps ? io->x_rec : nullptr, w.recon_ws,
@@ -413,6 +465,7 @@ extern "C" int vg_step_bwd(const VgStepConfig* cfg, const VgStepIO* io, void* wo
   const EncWs& e = w.e;
   const DecWs& d = w.d;
 
+  Fork fk(st);
   // ---- objective
   { VG_PROF("recon_loss.bwd", st);
   VG_TRY(vg_recon_loss_bwd(io->maps, io->g, io->x, w.eps32, io->glm_t, w.norms, B, V, cfg->glm_reg_scale, w.dpre5,
@@ -422,16 +475,18 @@ extern "C" int vg_step_bwd(const VgStepConfig* cfg, const VgStepIO* io, void* wo
   VG_LAUNCH_CHECK();
   VgGainParams gp; VgGainGrads gg;
   fill_gain_params(cfg, io, gp, &gg);
-  { VG_PROF("gain.bwd", st);
+  { cudaStream_t gs = fk.branch();
+  VG_PROF("gain.bwd", gs);
   VG_TRY(vg_gain_bwd(&gp, &gg, io->covariates, io->eps_g, io->taps, w.dg, (double)cfg->gp_kl_scale, B, cfg->m,
-                     w.gain_ws, w.gain_ws_bytes, st));
+                     w.gain_ws, w.gain_ws_bytes, gs));
   }
 
   // ---- decoder (9B images, groups of B)
   VgConvDesc c1 = make_desc(kConvT[0], nd, B), c2 = make_desc(kConvT[1], nd, B), c3 = make_desc(kConvT[2], nd, B),
              c4 = make_desc(kConvT[3], nd, B), c5 = make_desc(kConvT[4], nd, B, 0, VP);
-  { VG_PROF("convt5.wgrad", st);
-  VG_TRY(vg_conv_wgrad(&c5, d.t4, w.dpre5, d.bnt5.scale, d.bnt5.shift, GF(CONVT5), GF(CONVT5 + 1), st));
+  { cudaStream_t ws = fk.branch();
+  VG_PROF("convt5.wgrad", ws);
+  VG_TRY(vg_conv_wgrad(&c5, d.t4, w.dpre5, d.bnt5.scale, d.bnt5.shift, GF(CONVT5), GF(CONVT5 + 1), ws));
   }
   { VG_PROF("convt5.dgrad", st);
   VG_TRY(vg_conv_dgrad(&c5, w.dpre5, PF(CONVT5), w.d_t4, nullptr, d.t4, d.bnt5.istd, d.bnt5.mistd, d.bnt5.sums, st));
@@ -440,14 +495,16 @@ extern "C" int vg_step_bwd(const VgStepConfig* cfg, const VgStepIO* io, void* wo
   VG_TRY(vg_bn_bwd_apply(w.d_t4, d.t4, d.bnt5.sums, d.bnt5.scale, d.bnt5.istd, d.bnt5.mistd, nd, B,
                          vol(kConvT[3].out), 8, (double)B * vol(kConvT[3].out), 1, w.d_t4, GF(BNT5), GF(BNT5 + 1), st));
   }
-  { VG_PROF("convt4.wgrad", st);
-  VG_TRY(vg_conv_wgrad(&c4, d.t3, w.d_t4, nullptr, nullptr, GF(CONVT4), GF(CONVT4 + 1), st));
+  { cudaStream_t ws = fk.branch();
+  VG_PROF("convt4.wgrad", ws);
+  VG_TRY(vg_conv_wgrad(&c4, d.t3, w.d_t4, nullptr, nullptr, GF(CONVT4), GF(CONVT4 + 1), ws));
   }
   { VG_PROF("convt4.dgrad", st);
   VG_TRY(vg_conv_dgrad(&c4, w.d_t4, PF(CONVT4), w.d_t3, d.t3, nullptr, nullptr, nullptr, nullptr, st));
   }
-  { VG_PROF("convt3.wgrad", st);
-  VG_TRY(vg_conv_wgrad(&c3, d.t2, w.d_t3, d.bnt3.scale, d.bnt3.shift, GF(CONVT3), GF(CONVT3 + 1), st));
+  { cudaStream_t ws = fk.branch();
+  VG_PROF("convt3.wgrad", ws);
+  VG_TRY(vg_conv_wgrad(&c3, d.t2, w.d_t3, d.bnt3.scale, d.bnt3.shift, GF(CONVT3), GF(CONVT3 + 1), ws));
   }
   { VG_PROF("convt3.dgrad", st);
   VG_TRY(vg_conv_dgrad(&c3, w.d_t3, PF(CONVT3), w.d_t2, nullptr, d.t2, d.bnt3.istd, d.bnt3.mistd, d.bnt3.sums, st));
@@ -456,14 +513,16 @@ extern "C" int vg_step_bwd(const VgStepConfig* cfg, const VgStepIO* io, void* wo
   VG_TRY(vg_bn_bwd_apply(w.d_t2, d.t2, d.bnt3.sums, d.bnt3.scale, d.bnt3.istd, d.bnt3.mistd, nd, B,
                          vol(kConvT[1].out), 16, (double)B * vol(kConvT[1].out), 1, w.d_t2, GF(BNT3), GF(BNT3 + 1), st));
   }
-  { VG_PROF("convt2.wgrad", st);
-  VG_TRY(vg_conv_wgrad(&c2, d.t1, w.d_t2, nullptr, nullptr, GF(CONVT2), GF(CONVT2 + 1), st));
+  { cudaStream_t ws = fk.branch();
+  VG_PROF("convt2.wgrad", ws);
+  VG_TRY(vg_conv_wgrad(&c2, d.t1, w.d_t2, nullptr, nullptr, GF(CONVT2), GF(CONVT2 + 1), ws));
   }
   { VG_PROF("convt2.dgrad", st);
   VG_TRY(vg_conv_dgrad(&c2, w.d_t2, PF(CONVT2), w.d_t1, d.t1, nullptr, nullptr, nullptr, nullptr, st));
   }
-  { VG_PROF("convt1.wgrad", st);
-  VG_TRY(vg_conv_wgrad(&c1, d.t0, w.d_t1, d.bnt1.scale, d.bnt1.shift, GF(CONVT1), GF(CONVT1 + 1), st));
+  { cudaStream_t ws = fk.branch();
+  VG_PROF("convt1.wgrad", ws);
+  VG_TRY(vg_conv_wgrad(&c1, d.t0, w.d_t1, d.bnt1.scale, d.bnt1.shift, GF(CONVT1), GF(CONVT1 + 1), ws));
   }
   { VG_PROF("convt1.dgrad", st);
   VG_TRY(vg_conv_dgrad(&c1, w.d_t1, PF(CONVT1), w.d_t0, nullptr, d.t0, d.bnt1.istd, d.bnt1.mistd, d.bnt1.sums, st));
@@ -534,8 +593,9 @@ extern "C" int vg_step_bwd(const VgStepConfig* cfg, const VgStepIO* io, void* wo
   VG_LAUNCH_CHECK();
   VgConvDesc d1 = make_desc(kConv[0], B, B), d2 = make_desc(kConv[1], B, B), d3 = make_desc(kConv[2], B, B),
              d4 = make_desc(kConv[3], B, B), d5 = make_desc(kConv[4], B, B);
-  { VG_PROF("conv5.wgrad", st);
-  VG_TRY(vg_conv_wgrad(&d5, e.a4, w.d_a5, e.bn5.scale, e.bn5.shift, GF(CONV5), GF(CONV5 + 1), st));
+  { cudaStream_t ws = fk.branch();
+  VG_PROF("conv5.wgrad", ws);
+  VG_TRY(vg_conv_wgrad(&d5, e.a4, w.d_a5, e.bn5.scale, e.bn5.shift, GF(CONV5), GF(CONV5 + 1), ws));
   }
   { VG_PROF("conv5.dgrad", st);
   VG_TRY(vg_conv_dgrad(&d5, w.d_a5, PF(CONV5), w.d_a4, nullptr, e.a4, e.bn5.istd, e.bn5.mistd, e.bn5.sums, st));
@@ -544,14 +604,16 @@ extern "C" int vg_step_bwd(const VgStepConfig* cfg, const VgStepIO* io, void* wo
   VG_TRY(vg_bn_bwd_apply(w.d_a4, e.a4, e.bn5.sums, e.bn5.scale, e.bn5.istd, e.bn5.mistd, B, B, vol(kConv[3].out), 16,
                          (double)B * vol(kConv[3].out), 1, w.d_a4, GF(BN5), GF(BN5 + 1), st));
   }
-  { VG_PROF("conv4.wgrad", st);
-  VG_TRY(vg_conv_wgrad(&d4, e.a3, w.d_a4, nullptr, nullptr, GF(CONV4), GF(CONV4 + 1), st));
+  { cudaStream_t ws = fk.branch();
+  VG_PROF("conv4.wgrad", ws);
+  VG_TRY(vg_conv_wgrad(&d4, e.a3, w.d_a4, nullptr, nullptr, GF(CONV4), GF(CONV4 + 1), ws));
   }
   { VG_PROF("conv4.dgrad", st);
   VG_TRY(vg_conv_dgrad(&d4, w.d_a4, PF(CONV4), w.d_a3, e.a3, nullptr, nullptr, nullptr, nullptr, st));
   }
-  { VG_PROF("conv3.wgrad", st);
-  VG_TRY(vg_conv_wgrad(&d3, e.a2, w.d_a3, e.bn3.scale, e.bn3.shift, GF(CONV3), GF(CONV3 + 1), st));
+  { cudaStream_t ws = fk.branch();
+  VG_PROF("conv3.wgrad", ws);
+  VG_TRY(vg_conv_wgrad(&d3, e.a2, w.d_a3, e.bn3.scale, e.bn3.shift, GF(CONV3), GF(CONV3 + 1), ws));
   }
   { VG_PROF("conv3.dgrad", st);
   VG_TRY(vg_conv_dgrad(&d3, w.d_a3, PF(CONV3), w.d_a2, nullptr, e.a2, e.bn3.istd, e.bn3.mistd, e.bn3.sums, st));
@@ -560,14 +622,16 @@ extern "C" int vg_step_bwd(const VgStepConfig* cfg, const VgStepIO* io, void* wo
   VG_TRY(vg_bn_bwd_apply(w.d_a2, e.a2, e.bn3.sums, e.bn3.scale, e.bn3.istd, e.bn3.mistd, B, B, vol(kConv[1].out), 8,
                          (double)B * vol(kConv[1].out), 1, w.d_a2, GF(BN3), GF(BN3 + 1), st));
   }
-  { VG_PROF("conv2.wgrad", st);
-  VG_TRY(vg_conv_wgrad(&d2, e.a1, w.d_a2, nullptr, nullptr, GF(CONV2), GF(CONV2 + 1), st));
+  { cudaStream_t ws = fk.branch();
+  VG_PROF("conv2.wgrad", ws);
+  VG_TRY(vg_conv_wgrad(&d2, e.a1, w.d_a2, nullptr, nullptr, GF(CONV2), GF(CONV2 + 1), ws));
   }
   { VG_PROF("conv2.dgrad", st);
   VG_TRY(vg_conv_dgrad(&d2, w.d_a2, PF(CONV2), w.d_a1, e.a1, nullptr, nullptr, nullptr, nullptr, st));
   }
-  { VG_PROF("conv1.wgrad", st);
-  VG_TRY(vg_conv_wgrad(&d1, io->x, w.d_a1, e.bn1.scale, e.bn1.shift, GF(CONV1), GF(CONV1 + 1), st));
+  { cudaStream_t ws = fk.branch();
+  VG_PROF("conv1.wgrad", ws);
+  VG_TRY(vg_conv_wgrad(&d1, io->x, w.d_a1, e.bn1.scale, e.bn1.shift, GF(CONV1), GF(CONV1 + 1), ws));
   }
   // bn1 sits on the network input: only its affine parameters need a gradient
   { VG_PROF("conv1.dgrad", st);
@@ -577,6 +641,7 @@ extern "C" int vg_step_bwd(const VgStepConfig* cfg, const VgStepIO* io, void* wo
   VG_TRY(vg_bn_bwd_apply(nullptr, io->x, e.bn1.sums, nullptr, nullptr, nullptr, B, B, V, 1, (double)B * V, 0, nullptr,
                          GF(BN1), GF(BN1 + 1), st));
   }
+  fk.join();
   return VG_OK;
 }
 
