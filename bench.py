@@ -48,14 +48,19 @@ _CONV = {  # name: (cin, cout, taps, out voxels, in voxels)
 }
 
 
-def conv_work(name):
-    """(flops, bytes) per image for one pass (fwd, dgrad or wgrad) of a conv layer."""
+def conv_work(name, kind="fwd"):
+    """(flops, bytes) per image for one pass (fwd, dgrad or wgrad) of a conv layer.  Algorithmic bytes (fp32
+    tensors): fwd x + y; wgrad x + dy; dgrad dy + dx + the saved tensor its fused epilogue reads
+    (ReLU mask or BatchNorm-backward statistics) — conv1.dgrad only produces the bn1 statistics (dy + x)."""
     cin, cout, taps, vo, vi = _CONV[name]
     if name.startswith("convt"):          # gather form: MACs = input voxels * taps * cin * cout
         flops = 2.0 * vi * taps * cin * cout
     else:
         flops = 2.0 * vo * taps * cin * cout
-    return flops, 4.0 * (vi * cin + vo * cout)
+    nbytes = 4.0 * (vi * cin + vo * cout)
+    if kind == "dgrad" and name != "conv1":
+        nbytes += 4.0 * vi * cin
+    return flops, nbytes
 
 
 def op_work(op, B):
@@ -63,7 +68,7 @@ def op_work(op, B):
     layer, _, kind = op.partition(".")
     if layer in _CONV:
         n = B if layer.startswith("conv") and not layer.startswith("convt") else 9 * B
-        f, b = conv_work(layer)
+        f, b = conv_work(layer, kind)
         return f * n, b * n
     if op == "recon_loss.fwd":
         return 30.0 * B * V, 4.0 * (10 * B * V + 9 * V)
@@ -391,8 +396,15 @@ def main():
         top = next((r for r in rows if "gbs" in r), None)
         if top:
             w = op_work(top["op"], B)
+            traffic = None
+            try:      # dram__bytes_read.sum + dram__bytes_write.sum of the same kernel from the committed ncu capture
+                tr = json.load(open(os.path.join(ROOT, "profiles", "r1_s3_ncu_traffic.json")))["ops"].get(top["op"])
+                if tr and B == BATCH:
+                    traffic = tr["dram_read_bytes"] + tr["dram_write_bytes"]
+            except Exception:
+                pass
             roof = {"kernel": top["op"], "bound": "hbm", "achieved": top["gbs"], "peak": hbm_peak, "unit": "GB/s",
-                    "frac": round(top["gbs"] / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
+                    "frac": round(top["gbs"] / hbm_peak, 4), "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes": w[1], "ms": top["ms_per_step"], "share_of_step": top["share"],
                     "tensor_frac": round(top["gflops"] / 1e3 / tf_peak, 5)}
         rl = [r for r in rows if r["op"].startswith("recon_loss")]
