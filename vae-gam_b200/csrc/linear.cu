@@ -7,7 +7,7 @@
 
 namespace vg {
 
-constexpr int TM = 64, TN = 64, TK = 16;
+constexpr int TM = 64, TN = 64, TK = 32;   // deep K tile: these GEMMs are latency-bound, few sequential K steps matter most
 
 struct GemmArgs {
   const float* A; long long as_m, as_k;
@@ -39,10 +39,10 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs a) {
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
   for (int k0 = kbeg; k0 < kend; k0 += TK) {
-    // A tile: TM x TK, 1024 elements, 4 per thread.  Pick the faster-varying thread index
-    // along whichever of (m, k) is contiguous in memory.
+    // A tile: TM x TK elements, TM*TK/256 per thread, all loads in flight together.  Pick the
+    // faster-varying thread index along whichever of (m, k) is contiguous in memory.
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < TM * TK / 256; ++r) {
       int e = tid + r * 256;
       int mm, kk;
       if (a.as_k == 1) { kk = e % TK; mm = e / TK; } else { mm = e % TM; kk = e / TM; }
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs a) {
       sA[kk][mm] = v;
     }
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < TN * TK / 256; ++r) {
       int e = tid + r * 256;
       int nn, kk;
       if (a.bs_k == 1) { kk = e % TK; nn = e / TK; } else { nn = e % TN; kk = e / TN; }

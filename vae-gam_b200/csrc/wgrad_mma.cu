@@ -56,13 +56,13 @@ __device__ __forceinline__ int fast_div(int e, uint32_t mul) { return mul ? (int
 // independent elements per thread in flight before the first is converted.  BIAS: also sum the raw values
 // of the voxels this tile OWNS (own*: global coordinate ranges) per channel — a thread always handles the
 // same 8-channel part (blockDim is a multiple of the parts per voxel), so the sums live in 8 registers.
-template <int C, bool BIAS>
+template <int C, bool BIAS, int UV>
 __device__ __forceinline__ void stage_box_bf16(__nv_bfloat16* dst, const float* __restrict__ src, int oD, int oH, int oW,
                                                int bh, int bw, int nvox, uint32_t mul_h, uint32_t mul_w, int gD, int gH,
                                                int gW, const float* sc, const float* sh, const int (&own)[6],
                                                float (&bs)[8]) {
   constexpr int PER = C >= 8 ? C / 8 : 1;        // 16-byte bf16 chunks per voxel
-  constexpr int U = C >= 8 ? 2 : 4;              // elements in flight per thread (registers are shared with the accumulators)
+  constexpr int U = C >= 8 ? UV : 4;             // elements in flight per thread (registers are shared with the accumulators)
   const int nel = nvox * PER;
   for (int e0 = threadIdx.x; e0 < nel; e0 += U * blockDim.x) {
     float4 va[U], vb[U];
@@ -139,6 +139,7 @@ wgrad_mma_kernel(const __grid_constant__ WmGeom g, const float* __restrict__ x, 
   __shared__ int s_tapoff[48];
   __shared__ float s_bias[16];
   constexpr int NT = CU / 8;                       // n8 tiles
+  constexpr int UV = MT * NT * 4 <= 16 ? 4 : 2;    // staged voxels in flight per thread: more when the accumulators are few
   constexpr int TPM = CS == 8 ? 2 : (CS == 16 ? 1 : 16);   // taps per m16 tile
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvw = (blockDim.x >> 5) / g.tg;        // warps sharing a tap group split the voxel chunks
@@ -197,11 +198,11 @@ wgrad_mma_kernel(const __grid_constant__ WmGeom g, const float* __restrict__ x, 
     if (MODE == 0) {
       // dY is the un-shifted tile: tiles partition the output grid
       const int own[6] = {q0d, q0d + g.tD, q0h, q0h + g.tH, q0w, q0w + g.tW};
-      stage_box_bf16<CS, false>(Ssh, xn, q0d * g.s, q0h * g.s, q0w * g.s, g.sH, g.sW, box_vox, g.mul_sH, g.mul_sW, g.xD, g.xH,
+      stage_box_bf16<CS, false, UV>(Ssh, xn, q0d * g.s, q0h * g.s, q0w * g.s, g.sH, g.sW, box_vox, g.mul_sH, g.mul_sW, g.xD, g.xH,
                                 g.xW, sc, sh, none, bsum);
-      if (dbias) stage_box_bf16<CU, true>(Sun, yn, q0d, q0h, q0w, g.tH, g.tW, tile_vox, g.mul_tH, g.mul_tW, g.yD, g.yH, g.yW,
+      if (dbias) stage_box_bf16<CU, true, UV>(Sun, yn, q0d, q0h, q0w, g.tH, g.tW, tile_vox, g.mul_tH, g.mul_tW, g.yD, g.yH, g.yW,
                                           nullptr, nullptr, own, bsum);
-      else stage_box_bf16<CU, false>(Sun, yn, q0d, q0h, q0w, g.tH, g.tW, tile_vox, g.mul_tH, g.mul_tW, g.yD, g.yH, g.yW,
+      else stage_box_bf16<CU, false, UV>(Sun, yn, q0d, q0h, q0w, g.tH, g.tW, tile_vox, g.mul_tH, g.mul_tW, g.yD, g.yH, g.yW,
                                      nullptr, nullptr, none, bsum);
     } else {
       // dY is the shifted box (boxes of neighbouring tiles overlap): a tile owns the outputs
@@ -209,11 +210,11 @@ wgrad_mma_kernel(const __grid_constant__ WmGeom g, const float* __restrict__ x, 
       const int own[6] = {td == 0 ? 0 : q0d * g.s - g.pD, td == g.nTd - 1 ? g.yD : (q0d + g.tD) * g.s - g.pD,
                           th == 0 ? 0 : q0h * g.s - g.pH, th == g.nTh - 1 ? g.yH : (q0h + g.tH) * g.s - g.pH,
                           tw == 0 ? 0 : q0w * g.s - g.pW, tw == g.nTw - 1 ? g.yW : (q0w + g.tW) * g.s - g.pW};
-      stage_box_bf16<CU, false>(Sun, xn, q0d, q0h, q0w, g.tH, g.tW, tile_vox, g.mul_tH, g.mul_tW, g.xD, g.xH, g.xW, sc, sh,
+      stage_box_bf16<CU, false, UV>(Sun, xn, q0d, q0h, q0w, g.tH, g.tW, tile_vox, g.mul_tH, g.mul_tW, g.xD, g.xH, g.xW, sc, sh,
                                 none, bsum);
-      if (dbias) stage_box_bf16<CS, true>(Ssh, yn, q0d * g.s - g.pD, q0h * g.s - g.pH, q0w * g.s - g.pW, g.sH, g.sW, box_vox,
+      if (dbias) stage_box_bf16<CS, true, UV>(Ssh, yn, q0d * g.s - g.pD, q0h * g.s - g.pH, q0w * g.s - g.pW, g.sH, g.sW, box_vox,
                                           g.mul_sH, g.mul_sW, g.yD, g.yH, g.yW, nullptr, nullptr, own, bsum);
-      else stage_box_bf16<CS, false>(Ssh, yn, q0d * g.s - g.pD, q0h * g.s - g.pH, q0w * g.s - g.pW, g.sH, g.sW, box_vox,
+      else stage_box_bf16<CS, false, UV>(Ssh, yn, q0d * g.s - g.pD, q0h * g.s - g.pH, q0w * g.s - g.pW, g.sH, g.sW, box_vox,
                                      g.mul_sH, g.mul_sW, g.yD, g.yH, g.yW, nullptr, nullptr, none, bsum);
     }
     // zero the un-shifted rows of the last chunk's padding (tile_vox .. 16*nchunks)
