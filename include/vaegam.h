@@ -208,10 +208,14 @@ int vg_gp_posterior(const float* xu, int m, const float* k_var, const float* ls,
  * maps (9,b,VP): decoder outputs (base, 8 covariate maps), every row padded to
  * VP = round_up(V,4) floats so rows are 16-byte aligned (V = 70315 is odd); g (8,b); x (b,V)
  * dense; eps (VP) fp32 copy of the fp64 epsilon parameter (.float() at :402); glm (8,VP) fp32
- * transposed GLM maps.  One HBM pass; partial sums are reduced deterministically in a second
+ * transposed GLM maps.  One HBM pass over warp items of 4 rows x 32 voxels dealt
+ * in equal spans to a persistent grid; partial sums are reduced deterministically in a second
  * tiny kernel.  dpre has the (9,b,VP) layout of maps; deps is (VP).
  * ---------------------------------------------------------------------------------- */
 size_t vg_recon_workspace_bytes(int b, long long v);
+/* Launch shape of both passes (warps per CTA x CTAs per SM x cp.async ring stages):
+ * 0: 4 x 5 x 2, 1 (default): 4 x 3 x 3, 2: 4 x 4 x 2. */
+void vg_recon_tune(int variant);
 /* logp (b), norms (8,b) = ||g_i D_i[b] - G_i||_2.  Optional cons (8,b,V) and x_rec (b,V)
  * (R5 side outputs, NULL in training). */
 int vg_recon_loss_fwd(const float* maps, const float* g, const float* x, const float* eps,

@@ -482,10 +482,12 @@ def test_gain_reports_non_pd(lib):
     assert status[1].item() != 0 and status[0].item() == 0
 
 
-@pytest.mark.parametrize("B", [1, 2, 5, 32])
-def test_fused_recon_loss(lib, B):
-    """vg_recon_loss_fwd/bwd vs the fp64 oracle (R1-R4 and the fused-pass gradients)."""
+@pytest.mark.parametrize("B,cps", [(1, 0), (2, 0), (5, 0), (5, 1), (5, 2), (32, 0), (32, 1), (32, 2), (33, 0)])
+def test_fused_recon_loss(lib, B, cps):
+    """vg_recon_loss_fwd/bwd vs the fp64 oracle (R1-R4 and the fused-pass gradients); cps = the
+    backward kernel's launch-shape variant (vg_recon_tune)."""
     native = nat()
+    lib.vg_recon_tune(cps)
     from oracle import ref_port as rp
     dev = "cuda"
     V, VP = native.V, native.VP
@@ -518,6 +520,7 @@ def test_fused_recon_loss(lib, B):
                                        native.ptr(norms), B, V, lam, native.ptr(dpre), native.ptr(dg), native.ptr(deps),
                                        native.ptr(ws), nbytes, st))
     torch.cuda.synchronize()
+    lib.vg_recon_tune(1)                                                        # back to the default
     assert rel_err(logp.cpu(), rl["logp"].detach()) < 2e-6
     assert rel_err(norms.cpu(), rl["glm_norms"].detach()) < 2e-6
     assert rel_err(cons.cpu(), rl["cons"].detach()) < 1e-6
