@@ -150,6 +150,39 @@ int vg_linear_bwd(const float* dy, const float* relu_out, const float* x, const 
                   float* dx, float* dw, float* db, int m, int n, int k, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Fused chains of small fully-connected layers (encoder heads fc2 -> fc31/32/33 -> fc41/42/43,
+ * vae_reg_GP.py:198-204,245-251; decoder stem fc5 -> fc6 -> fc7, :207-209,255-257): one launch
+ * per chain and direction, a CTA owns rows_per_cta batch rows and walks the layer list with the
+ * activations in shared memory.  buf[i]: (rows, width) row-major fp32 activations `act` and their
+ * gradients `grad`; layer l: buf[out] = act(buf[in] @ w^T + b), w (n,k) row-major (nn.Linear), k <= 224.
+ * Layers must be listed in a topological order; several layers may read the same buffer.
+ *   vg_mlp_fwd: reads the VG_MLP_INPUT buffers, writes every layer output to its `act`.
+ *   vg_mlp_bwd: reads every `act` (saved forward values) and the `grad` of VG_MLP_GRAD_IN buffers
+ *     (dLoss/d post-activation output), writes the `grad` of VG_MLP_GRAD_OUT buffers and
+ *     ACCUMULATES dw (n,k) / db (n) (fp32 RED; either may be NULL).
+ * ---------------------------------------------------------------------------------- */
+#define VG_MLP_MAX_LAYERS 8
+#define VG_MLP_MAX_BUFS 10
+#define VG_MLP_INPUT 1
+#define VG_MLP_GRAD_IN 2
+#define VG_MLP_GRAD_OUT 4
+typedef struct VgMlpLayer {
+  const float* w; const float* b; float* dw; float* db;
+  int32_t n, k, in, out, act, pad_;
+} VgMlpLayer;
+typedef struct VgMlpBuf {
+  float* act; float* grad;
+  int32_t width, role;
+} VgMlpBuf;
+typedef struct VgMlp {
+  int32_t nlayers, nbufs, rows, rows_per_cta;     /* rows_per_cta: 4 or 8 */
+  VgMlpLayer layer[VG_MLP_MAX_LAYERS];
+  VgMlpBuf buf[VG_MLP_MAX_BUFS];
+} VgMlp;
+int vg_mlp_fwd(const VgMlp* m, void* stream);
+int vg_mlp_bwd(const VgMlp* m, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Latent sample + KL (vae_reg_GP.py:321-325 LowRankMultivariateNormal(mu,u,d).rsample(),
  * :400 kl_divergence(latent_dist, z_prior); torch lowrank_multivariate_normal.py:214-223,
  * kl.py:342-372).  heads: (3, b, 32) = [mu | u | log d] (fc41/42/43 outputs, fc43 BEFORE exp).

@@ -63,12 +63,12 @@ def test_struct_sizes_match_c_layout(built_lib):
     src = r'''
 #include <stdio.h>
 #include "vaegam.h"
-int main(void){ printf("%zu %zu %zu %zu %zu\n", sizeof(VgConvDesc), sizeof(VgGainParams), sizeof(VgGainGrads),
-  sizeof(VgStepConfig), sizeof(VgStepIO)); return 0; }'''
+int main(void){ printf("%zu %zu %zu %zu %zu %zu\n", sizeof(VgConvDesc), sizeof(VgGainParams), sizeof(VgGainGrads),
+  sizeof(VgStepConfig), sizeof(VgStepIO), sizeof(VgMlp)); return 0; }'''
     d = tempfile.mkdtemp()
     open(os.path.join(d, "s.c"), "w").write(src)
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "s"), os.path.join(d, "s.c")], check=True)
     sizes = [int(v) for v in subprocess.run([os.path.join(d, "s")], capture_output=True, text=True).stdout.split()]
     n = built_lib
     assert sizes == [ctypes.sizeof(n.VgConvDesc), ctypes.sizeof(n.VgGainParams), ctypes.sizeof(n.VgGainGrads),
-                     ctypes.sizeof(n.VgStepConfig), ctypes.sizeof(n.VgStepIO)]
+                     ctypes.sizeof(n.VgStepConfig), ctypes.sizeof(n.VgStepIO), ctypes.sizeof(n.VgMlp)]

@@ -346,6 +346,76 @@ def test_linear_forward_backward(lib, m, n, k):
     assert rel_err(db.cpu(), br.grad.cpu()) < 1e-5
 
 
+def _mlp_case(native, chain, rows, dev, gen):
+    """Builds a VgMlp for one of the two chains of the step plus its torch twin."""
+    if chain == "enc_heads":      # fc2 -> fc31/32/33 -> fc41/42/43 (vae_reg_GP.py:245-251)
+        widths = [200, 100, 50, 50, 50, 32, 32, 32]
+        layers = [(100, 200, 0, 1, True), (50, 100, 1, 2, True), (50, 100, 1, 3, True), (50, 100, 1, 4, True),
+                  (32, 50, 2, 5, False), (32, 50, 3, 6, False), (32, 50, 4, 7, False)]
+        grad_in, rpc = [5, 6, 7], 4
+    else:                         # fc5 -> fc6 -> fc7 (vae_reg_GP.py:255-257)
+        widths = [41, 50, 100, 200]
+        layers = [(50, 41, 0, 1, True), (100, 50, 1, 2, True), (200, 100, 2, 3, True)]
+        grad_in, rpc = [3], 8
+    acts = [torch.randn(rows, w, device=dev, generator=gen) if i == 0 else torch.full((rows, w), float("nan"), device=dev)
+            for i, w in enumerate(widths)]
+    grads = [torch.randn(rows, w, device=dev, generator=gen) if i in grad_in else torch.full((rows, w), float("nan"), device=dev)
+             for i, w in enumerate(widths)]
+    ws = [torch.randn(n, k, device=dev, generator=gen) * (1.5 / k ** 0.5) for n, k, *_ in layers]
+    bs = [torch.randn(n, device=dev, generator=gen) * 0.3 for n, *_ in layers]
+    dws = [torch.randn_like(w) for w in ws]          # gradients are ACCUMULATED on top of these
+    dbs = [torch.randn_like(b) for b in bs]
+    m = native.VgMlp()
+    m.nlayers, m.nbufs, m.rows, m.rows_per_cta = len(layers), len(widths), rows, rpc
+    for i, w in enumerate(widths):
+        m.buf[i].act, m.buf[i].grad, m.buf[i].width = native.ptr(acts[i]), native.ptr(grads[i]), w
+        m.buf[i].role = (native.MLP_INPUT | native.MLP_GRAD_OUT if i == 0 else 0) | (native.MLP_GRAD_IN if i in grad_in else 0)
+    for l, (n, k, i, o, relu) in enumerate(layers):
+        L = m.layer[l]
+        L.w, L.b, L.dw, L.db = native.ptr(ws[l]), native.ptr(bs[l]), native.ptr(dws[l]), native.ptr(dbs[l])
+        L.n, L.k, L.in_, L.out, L.act = n, k, i, o, native.ACT_RELU if relu else native.ACT_NONE
+    return m, layers, grad_in, acts, grads, ws, bs, dws, dbs
+
+
+@pytest.mark.parametrize("chain,rows", [("enc_heads", 1), ("enc_heads", 5), ("enc_heads", 32), ("dec_stem", 9),
+                                        ("dec_stem", 45), ("dec_stem", 288)])
+def test_fused_mlp_chains(lib, chain, rows):
+    """vg_mlp_fwd / vg_mlp_bwd (the fused small fully-connected layers) vs torch fp32 autograd, including the
+    three-way fan-in at h2, ragged last row blocks and gradient accumulation into dw / db."""
+    native = nat()
+    dev = "cuda"
+    gen = torch.Generator(device=dev).manual_seed(rows)
+    m, layers, grad_in, acts, grads, ws, bs, dws, dbs = _mlp_case(native, chain, rows, dev, gen)
+    dw0, db0 = [t.clone() for t in dws], [t.clone() for t in dbs]
+    st = native.stream_ptr()
+    native.check(lib.vg_mlp_fwd(C.byref(m), st))
+    wr = [w.clone().requires_grad_(True) for w in ws]
+    br = [b.clone().requires_grad_(True) for b in bs]
+    x0 = acts[0].clone().requires_grad_(True)
+    ref = {0: x0}
+    for l, (n, k, i, o, relu) in enumerate(layers):
+        y = F.linear(ref[i], wr[l], br[l])
+        ref[o] = torch.relu(y) if relu else y
+    torch.cuda.synchronize()
+    for o in range(1, len(acts)):
+        assert rel_err(acts[o].cpu(), ref[o].detach().cpu()) < 1e-5, o
+    torch.autograd.backward([ref[o] for o in grad_in], [grads[o] for o in grad_in])
+    native.check(lib.vg_mlp_bwd(C.byref(m), st))
+    torch.cuda.synchronize()
+    assert rel_err(grads[0].cpu(), x0.grad.cpu()) < 1e-5
+    for l in range(len(layers)):
+        assert rel_err((dws[l] - dw0[l]).cpu(), wr[l].grad.cpu()) < 2e-5, l
+        assert rel_err((dbs[l] - db0[l]).cpu(), br[l].grad.cpu()) < 2e-5, l
+
+
+def test_fused_mlp_rejects_bad_wiring(lib):
+    native = nat()
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    m, *_keep = _mlp_case(native, "dec_stem", 8, "cuda", gen)
+    m.layer[1].k = 60                                   # does not match the width of its input buffer
+    assert lib.vg_mlp_fwd(C.byref(m), native.stream_ptr()) == native.VG_EINVAL
+
+
 @pytest.mark.parametrize("B,small_d", [(1, False), (4, False), (32, True), (70, False)])
 def test_latent_sample_kl(lib, B, small_d):
     native = nat()

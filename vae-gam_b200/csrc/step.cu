@@ -266,6 +266,51 @@ struct Fork {
 #define PF(idx) (reinterpret_cast<const float*>(io->params[idx]))
 #define GF(idx) (reinterpret_cast<float*>(io->grads[idx]))
 
+// The small fully-connected layers run as fused chains (csrc/mlp.cu): one launch per chain and direction.
+static void mlp_layer(const VgStepIO* io, bool grads, VgMlpLayer& l, int param, int n, int k, int in, int out, int act) {
+  l.w = PF(param); l.b = PF(param + 1);
+  l.dw = grads ? GF(param) : nullptr; l.db = grads ? GF(param + 1) : nullptr;
+  l.n = n; l.k = k; l.in = in; l.out = out; l.act = act; l.pad_ = 0;
+}
+static void mlp_buf(VgMlpBuf& b, float* act, float* grad, int width, int role) {
+  b.act = act; b.grad = grad; b.width = width; b.role = role;
+}
+// fc2 -> fc31/32/33 -> fc41/42/43 (vae_reg_GP.py:245-251); heads = [mu | u | log d]
+static VgMlp enc_head_mlp(const VgStepIO* io, const EncWs& e, int B, float* d_h1, float* dheads) {
+  const bool g = dheads != nullptr;
+  VgMlp m{};
+  m.nlayers = 7; m.nbufs = 8; m.rows = B; m.rows_per_cta = 4;
+  mlp_buf(m.buf[0], e.h1, d_h1, 200, VG_MLP_INPUT | (g ? VG_MLP_GRAD_OUT : 0));
+  mlp_buf(m.buf[1], e.h2, nullptr, 100, 0);
+  mlp_buf(m.buf[2], e.h31, nullptr, 50, 0);
+  mlp_buf(m.buf[3], e.h32, nullptr, 50, 0);
+  mlp_buf(m.buf[4], e.h33, nullptr, 50, 0);
+  for (int j = 0; j < 3; ++j)
+    mlp_buf(m.buf[5 + j], e.heads + (size_t)j * B * L, g ? dheads + (size_t)j * B * L : nullptr, L, g ? VG_MLP_GRAD_IN : 0);
+  mlp_layer(io, g, m.layer[0], FC2, 100, 200, 0, 1, VG_ACT_RELU);
+  mlp_layer(io, g, m.layer[1], FC31, 50, 100, 1, 2, VG_ACT_RELU);
+  mlp_layer(io, g, m.layer[2], FC32, 50, 100, 1, 3, VG_ACT_RELU);
+  mlp_layer(io, g, m.layer[3], FC33, 50, 100, 1, 4, VG_ACT_RELU);
+  mlp_layer(io, g, m.layer[4], FC41, L, 50, 2, 5, VG_ACT_NONE);
+  mlp_layer(io, g, m.layer[5], FC42, L, 50, 3, 6, VG_ACT_NONE);
+  mlp_layer(io, g, m.layer[6], FC43, L, 50, 4, 7, VG_ACT_NONE);
+  return m;
+}
+// fc5 -> fc6 -> fc7 (vae_reg_GP.py:255-257)
+static VgMlp dec_stem_mlp(const VgStepIO* io, const DecWs& d, const float* zcat, int nd, float* d_zcat, float* d_f7) {
+  const bool g = d_f7 != nullptr;
+  VgMlp m{};
+  m.nlayers = 3; m.nbufs = 4; m.rows = nd; m.rows_per_cta = 8;
+  mlp_buf(m.buf[0], const_cast<float*>(zcat), d_zcat, ZD, VG_MLP_INPUT | (g ? VG_MLP_GRAD_OUT : 0));
+  mlp_buf(m.buf[1], d.f5, nullptr, 50, 0);
+  mlp_buf(m.buf[2], d.f6, nullptr, 100, 0);
+  mlp_buf(m.buf[3], d.f7, d_f7, 200, g ? VG_MLP_GRAD_IN : 0);
+  mlp_layer(io, g, m.layer[0], FC5, 50, ZD, 0, 1, VG_ACT_RELU);
+  mlp_layer(io, g, m.layer[1], FC6, 100, 50, 1, 2, VG_ACT_RELU);
+  mlp_layer(io, g, m.layer[2], FC7, 200, 100, 2, 3, VG_ACT_RELU);
+  return m;
+}
+
 // ---- forward pieces ----------------------------------------------------------------
 static int run_encoder(const VgStepIO* io, const EncWs& e, int B, cudaStream_t st) {
   { VG_PROF("bn_stats", st);
@@ -301,26 +346,9 @@ static int run_encoder(const VgStepIO* io, const EncWs& e, int B, cudaStream_t s
   VG_TRY(vg_nhwc_to_nchw(e.a5, e.a5f, B, 16, 192, st));   // h.view(-1, 3072) is channel-major
   VG_TRY(vg_linear_fwd(e.a5f, PF(FC1), PF(FC1 + 1), e.h1, B, 200, 3072, VG_ACT_RELU, st));
   }
-  { VG_PROF("fc2.fwd", st);
-  VG_TRY(vg_linear_fwd(e.h1, PF(FC2), PF(FC2 + 1), e.h2, B, 100, 200, VG_ACT_RELU, st));
-  }
-  { VG_PROF("fc31.fwd", st);
-  VG_TRY(vg_linear_fwd(e.h2, PF(FC31), PF(FC31 + 1), e.h31, B, 50, 100, VG_ACT_RELU, st));
-  }
-  { VG_PROF("fc32.fwd", st);
-  VG_TRY(vg_linear_fwd(e.h2, PF(FC32), PF(FC32 + 1), e.h32, B, 50, 100, VG_ACT_RELU, st));
-  }
-  { VG_PROF("fc33.fwd", st);
-  VG_TRY(vg_linear_fwd(e.h2, PF(FC33), PF(FC33 + 1), e.h33, B, 50, 100, VG_ACT_RELU, st));
-  }
-  { VG_PROF("fc41.fwd", st);
-  VG_TRY(vg_linear_fwd(e.h31, PF(FC41), PF(FC41 + 1), e.heads, B, L, 50, VG_ACT_NONE, st));
-  }
-  { VG_PROF("fc42.fwd", st);
-  VG_TRY(vg_linear_fwd(e.h32, PF(FC42), PF(FC42 + 1), e.heads + (size_t)B * L, B, L, 50, VG_ACT_NONE, st));
-  }
-  { VG_PROF("fc43.fwd", st);
-  VG_TRY(vg_linear_fwd(e.h33, PF(FC43), PF(FC43 + 1), e.heads + (size_t)2 * B * L, B, L, 50, VG_ACT_NONE, st));
+  { VG_PROF("fc2-fc43.fwd", st);
+  const VgMlp m = enc_head_mlp(io, e, B, nullptr, nullptr);
+  VG_TRY(vg_mlp_fwd(&m, st));
   }
   return VG_OK;
 }
@@ -329,14 +357,9 @@ static int run_encoder(const VgStepIO* io, const EncWs& e, int B, cudaStream_t s
 static int run_decoder(const VgStepIO* io, const DecWs& d, const float* zcat, int nd, int group, float* out,
                        long long out_stride, cudaStream_t st) {
   const int groups = nd / group;
-  { VG_PROF("fc5.fwd", st);
-  VG_TRY(vg_linear_fwd(zcat, PF(FC5), PF(FC5 + 1), d.f5, nd, 50, ZD, VG_ACT_RELU, st));
-  }
-  { VG_PROF("fc6.fwd", st);
-  VG_TRY(vg_linear_fwd(d.f5, PF(FC6), PF(FC6 + 1), d.f6, nd, 100, 50, VG_ACT_RELU, st));
-  }
-  { VG_PROF("fc7.fwd", st);
-  VG_TRY(vg_linear_fwd(d.f6, PF(FC7), PF(FC7 + 1), d.f7, nd, 200, 100, VG_ACT_RELU, st));
+  { VG_PROF("fc5-fc7.fwd", st);
+  const VgMlp m = dec_stem_mlp(io, d, zcat, nd, nullptr, nullptr);
+  VG_TRY(vg_mlp_fwd(&m, st));
   }
   { VG_PROF("fc8.fwd", st);
   VG_TRY(vg_linear_fwd(d.f7, PF(FC8), PF(FC8 + 1), d.f8, nd, 3840, 200, VG_ACT_RELU, st));
@@ -535,14 +558,9 @@ extern "C" int vg_step_bwd(const VgStepConfig* cfg, const VgStepIO* io, void* wo
   VG_TRY(vg_nhwc_to_nchw(w.d_t0, w.d_f8, nd, 16, 240, st));     // gradient w.r.t. fc8 pre-activation
   VG_TRY(vg_linear_bwd(w.d_f8, nullptr, d.f7, PF(FC8), w.d_f7, GF(FC8), GF(FC8 + 1), nd, 3840, 200, st));
   }
-  { VG_PROF("fc7.bwd", st);
-  VG_TRY(vg_linear_bwd(w.d_f7, d.f7, d.f6, PF(FC7), w.d_f6, GF(FC7), GF(FC7 + 1), nd, 200, 100, st));
-  }
-  { VG_PROF("fc6.bwd", st);
-  VG_TRY(vg_linear_bwd(w.d_f6, d.f6, d.f5, PF(FC6), w.d_f5, GF(FC6), GF(FC6 + 1), nd, 100, 50, st));
-  }
-  { VG_PROF("fc5.bwd", st);
-  VG_TRY(vg_linear_bwd(w.d_f5, d.f5, w.zcat, PF(FC5), w.d_zcat, GF(FC5), GF(FC5 + 1), nd, 50, ZD, st));
+  { VG_PROF("fc5-fc7.bwd", st);
+  const VgMlp m = dec_stem_mlp(io, d, w.zcat, nd, w.d_zcat, w.d_f7);
+  VG_TRY(vg_mlp_bwd(&m, st));
   }
 
   // ---- latent
@@ -553,35 +571,9 @@ extern "C" int vg_step_bwd(const VgStepConfig* cfg, const VgStepIO* io, void* wo
   }
 
   // ---- encoder
-  float* d_h31 = w.d_h3;
-  float* d_h32 = w.d_h3 + (size_t)B * 50;
-  float* d_h33 = w.d_h3 + (size_t)2 * B * 50;
-  { VG_PROF("fc41.bwd", st);
-  VG_TRY(vg_linear_bwd(w.dheads, nullptr, e.h31, PF(FC41), d_h31, GF(FC41), GF(FC41 + 1), B, L, 50, st));
-  }
-  { VG_PROF("fc42.bwd", st);
-  VG_TRY(vg_linear_bwd(w.dheads + (size_t)B * L, nullptr, e.h32, PF(FC42), d_h32, GF(FC42), GF(FC42 + 1), B, L, 50, st));
-  }
-  { VG_PROF("fc43.bwd", st);
-  VG_TRY(vg_linear_bwd(w.dheads + (size_t)2 * B * L, nullptr, e.h33, PF(FC43), d_h33, GF(FC43), GF(FC43 + 1), B, L, 50, st));
-  }
-  // three branches fan into h2: reuse d_f5.. scratch?  keep explicit temporaries in d_a5f (B*3072 >= 3*B*100)
-  float* t31 = w.d_a5f;
-  float* t32 = w.d_a5f + (size_t)B * 100;
-  float* t33 = w.d_a5f + (size_t)2 * B * 100;
-  { VG_PROF("fc31.bwd", st);
-  VG_TRY(vg_linear_bwd(d_h31, e.h31, e.h2, PF(FC31), t31, GF(FC31), GF(FC31 + 1), B, 50, 100, st));
-  }
-  { VG_PROF("fc32.bwd", st);
-  VG_TRY(vg_linear_bwd(d_h32, e.h32, e.h2, PF(FC32), t32, GF(FC32), GF(FC32 + 1), B, 50, 100, st));
-  }
-  { VG_PROF("fc33.bwd", st);
-  VG_TRY(vg_linear_bwd(d_h33, e.h33, e.h2, PF(FC33), t33, GF(FC33), GF(FC33 + 1), B, 50, 100, st));
-  }
-  add3_kernel<<<cdiv(B * 100, 256), 256, 0, st>>>(w.d_h2, t31, t32, t33, B * 100);
-  VG_LAUNCH_CHECK();
-  { VG_PROF("fc2.bwd", st);
-  VG_TRY(vg_linear_bwd(w.d_h2, e.h2, e.h1, PF(FC2), w.d_h1, GF(FC2), GF(FC2 + 1), B, 100, 200, st));
+  { VG_PROF("fc2-fc43.bwd", st);
+  const VgMlp m = enc_head_mlp(io, e, B, w.d_h1, w.dheads);
+  VG_TRY(vg_mlp_bwd(&m, st));
   }
   { VG_PROF("fc1.bwd", st);
   VG_TRY(vg_linear_bwd(w.d_h1, e.h1, e.a5f, PF(FC1), w.d_a5f, GF(FC1), GF(FC1 + 1), B, 200, 3072, st));

@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libvaegam_sm100.so")
 
 VG_NUM_PARAMS = 97
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
+VG_OK, VG_EINVAL = 0, -1
 V = 41 * 49 * 35
 VP = (V + 3) // 4 * 4
 
@@ -46,6 +47,24 @@ class VgGainGrads(C.Structure):
 class VgStepConfig(C.Structure):
     _fields_ = [("b", C.c_int32), ("m", C.c_int32), ("neural_covariates", C.c_int32), ("want_maps", C.c_int32),
                 ("gp_kl_scale", C.c_float), ("glm_reg_scale", C.c_float)]
+
+
+class VgMlpLayer(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("b", C.c_void_p), ("dw", C.c_void_p), ("db", C.c_void_p),
+                ("n", C.c_int32), ("k", C.c_int32), ("in_", C.c_int32), ("out", C.c_int32), ("act", C.c_int32),
+                ("pad_", C.c_int32)]
+
+
+class VgMlpBuf(C.Structure):
+    _fields_ = [("act", C.c_void_p), ("grad", C.c_void_p), ("width", C.c_int32), ("role", C.c_int32)]
+
+
+class VgMlp(C.Structure):
+    _fields_ = [("nlayers", C.c_int32), ("nbufs", C.c_int32), ("rows", C.c_int32), ("rows_per_cta", C.c_int32),
+                ("layer", VgMlpLayer * 8), ("buf", VgMlpBuf * 10)]
+
+
+MLP_INPUT, MLP_GRAD_IN, MLP_GRAD_OUT = 1, 2, 4
 
 
 class VgStepIO(C.Structure):
@@ -87,6 +106,8 @@ SIGNATURES = {
     "vg_nhwc_to_nchw": (_I, [_P, _P, _I, _I, _LL, _P]),
     "vg_linear_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "vg_linear_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "vg_mlp_fwd": (_I, [C.POINTER(VgMlp), _P]),
+    "vg_mlp_bwd": (_I, [C.POINTER(VgMlp), _P]),
     "vg_latent_fwd": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P]),
     "vg_latent_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P]),
     "vg_gain_workspace_bytes": (_SZ, [_I, _I]),
