@@ -175,7 +175,7 @@ typedef struct VgMlpBuf {
   int32_t width, role;
 } VgMlpBuf;
 typedef struct VgMlp {
-  int32_t nlayers, nbufs, rows, rows_per_cta;     /* rows_per_cta: 4 or 8 */
+  int32_t nlayers, nbufs, rows, rows_per_cta;     /* rows_per_cta: 1, 2, 4 or 8 */
   VgMlpLayer layer[VG_MLP_MAX_LAYERS];
   VgMlpBuf buf[VG_MLP_MAX_BUFS];
 } VgMlp;

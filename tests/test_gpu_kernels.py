@@ -377,15 +377,16 @@ def _mlp_case(native, chain, rows, dev, gen):
     return m, layers, grad_in, acts, grads, ws, bs, dws, dbs
 
 
-@pytest.mark.parametrize("chain,rows", [("enc_heads", 1), ("enc_heads", 5), ("enc_heads", 32), ("dec_stem", 9),
-                                        ("dec_stem", 45), ("dec_stem", 288)])
-def test_fused_mlp_chains(lib, chain, rows):
+@pytest.mark.parametrize("chain,rows,rpc", [("enc_heads", 1, 1), ("enc_heads", 5, 4), ("enc_heads", 32, 1), ("enc_heads", 33, 2),
+                                            ("dec_stem", 9, 2), ("dec_stem", 45, 8), ("dec_stem", 288, 2), ("dec_stem", 288, 4)])
+def test_fused_mlp_chains(lib, chain, rows, rpc):
     """vg_mlp_fwd / vg_mlp_bwd (the fused small fully-connected layers) vs torch fp32 autograd, including the
     three-way fan-in at h2, ragged last row blocks and gradient accumulation into dw / db."""
     native = nat()
     dev = "cuda"
     gen = torch.Generator(device=dev).manual_seed(rows)
     m, layers, grad_in, acts, grads, ws, bs, dws, dbs = _mlp_case(native, chain, rows, dev, gen)
+    m.rows_per_cta = rpc
     dw0, db0 = [t.clone() for t in dws], [t.clone() for t in dbs]
     st = native.stream_ptr()
     native.check(lib.vg_mlp_fwd(C.byref(m), st))

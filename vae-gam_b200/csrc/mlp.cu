@@ -4,10 +4,11 @@
 //
 // These layers hold < 0.1 % of the step's FLOPs but were 23 dependent ~20 us GEMM launches (each a
 // handful of CTAs waiting on global-load latency).  Every batch row is independent through a chain,
-// so a CTA owns R rows and walks the whole layer list with the activations (and, backward, their
-// gradients) resident in shared memory; the weights (<= 80 KB per layer) stream from L2.
+// so a CTA owns R (1..8) rows and walks the whole layer list with the activations (and, backward, their
+// gradients) resident in shared memory.  All weights and biases of the chain (108 KB / 159 KB) are
+// copied into shared memory up front with one burst of cp.async, so no layer waits on L2 again.
 //   forward : y[r][n] = act(b[n] + sum_k x[r][k] W[n][k])   warp per 4 neurons, lanes along k
-//             (coalesced weight rows, every weight load of the group in flight at once)
+//             (conflict-free weight rows)
 //   backward: dym = dy * (y > 0);  dx[r][k] += sum_n dym[r][n] W[n][k]   thread per k, n split over
 //             thread groups (coalesced weight rows; fan-in of branches adds up in shared memory);
 //             dW[n][k] += sum_r dym[r][n] x[r][k], db[n] += sum_r dym[r][n]   fp32 RED to global
@@ -20,7 +21,33 @@ constexpr int MLP_THREADS = 256;
 constexpr int MLP_KSTEPS = 7;        // lanes along k: K <= 32 * 7 = 224
 constexpr int MLP_NB = 4;            // neurons per warp iteration
 
-struct MlpOffsets { int off[VG_MLP_MAX_BUFS + 1]; };
+struct MlpOffsets {
+  int off[VG_MLP_MAX_BUFS + 1];        // activation columns before buffer i (x rows_per_cta floats)
+  int woff[VG_MLP_MAX_LAYERS + 1];     // weight floats before layer l
+  int boff[VG_MLP_MAX_LAYERS + 1];     // bias floats before layer l
+};
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+// weights (parameter tensors are only 4-byte aligned inside the flat buffer) and biases -> shared memory
+__device__ __forceinline__ void stage_weights(const VgMlp& m, const MlpOffsets& o, float* sw, float* sb) {
+  for (int l = 0; l < m.nlayers; ++l) {
+    const VgMlpLayer& L = m.layer[l];
+    const int nw = L.n * L.k;
+    for (int i = threadIdx.x; i < nw; i += MLP_THREADS) cp_async4(sw + o.woff[l] + i, L.w + i);
+    for (int i = threadIdx.x; i < L.n; i += MLP_THREADS) {
+      if (L.b) cp_async4(sb + o.boff[l] + i, L.b + i);
+      else sb[o.boff[l] + i] = 0.f;
+    }
+  }
+}
 
 __device__ __forceinline__ float apply_act(float v, int act) { return act == VG_ACT_RELU ? fmaxf(v, 0.f) : v; }
 
@@ -35,7 +62,7 @@ __device__ __forceinline__ void dense_fwd(const float* __restrict__ sx, int K, c
 #pragma unroll
       for (int j = 0; j < MLP_NB; ++j) {
         const int k = lane + 32 * s;
-        w[s][j] = (k < K && n0 + j < N) ? __ldg(W + (size_t)(n0 + j) * K + k) : 0.f;
+        w[s][j] = (k < K && n0 + j < N) ? W[(n0 + j) * K + k] : 0.f;
       }
     float acc[MLP_NB][R];
 #pragma unroll
@@ -64,7 +91,7 @@ __device__ __forceinline__ void dense_fwd(const float* __restrict__ sx, int K, c
       }
     if (lane < MLP_NB * R) {
       const int j = lane / R, r = lane % R;
-      if (n0 + j < N) sy[r * N + n0 + j] = apply_act(mine + (b ? __ldg(b + n0 + j) : 0.f), act);
+      if (n0 + j < N) sy[r * N + n0 + j] = apply_act(mine + b[n0 + j], act);
     }
   }
 }
@@ -85,7 +112,7 @@ __device__ __forceinline__ void dense_dx(const float* __restrict__ sdym, int N, 
     for (int n0 = grp * U; n0 < N; n0 += groups * U) {
       float w[U];
 #pragma unroll
-      for (int j = 0; j < U; ++j) w[j] = n0 + j < N ? __ldg(W + (size_t)(n0 + j) * K + k) : 0.f;
+      for (int j = 0; j < U; ++j) w[j] = n0 + j < N ? W[(n0 + j) * K + k] : 0.f;
 #pragma unroll
       for (int j = 0; j < U; ++j)
         if (n0 + j < N) {
@@ -124,10 +151,12 @@ __device__ __forceinline__ void dense_dw(const float* __restrict__ sdym, int N, 
   }
 }
 
+// rows [row0, row0 + nrows) of a (rows, width) buffer -> shared memory (asynchronously), zero beyond nrows
 __device__ __forceinline__ void load_rows(float* dst, const float* src, int width, int row0, int nrows, int R) {
+  const int live = src ? nrows * width : 0;
   for (int i = threadIdx.x; i < R * width; i += MLP_THREADS) {
-    const int r = i / width;
-    dst[i] = (src && r < nrows) ? __ldg(src + (size_t)row0 * width + i) : 0.f;
+    if (i < live) cp_async4(dst + i, src + (size_t)row0 * width + i);
+    else dst[i] = 0.f;
   }
 }
 __device__ __forceinline__ void store_rows(float* dst, const float* src, int width, int row0, int nrows) {
@@ -137,14 +166,18 @@ __device__ __forceinline__ void store_rows(float* dst, const float* src, int wid
 template <int R>
 __global__ void __launch_bounds__(MLP_THREADS) mlp_fwd_kernel(const VgMlp m, const MlpOffsets o) {
   extern __shared__ float sm[];
+  float* sw = sm + R * o.off[m.nbufs];
+  float* sb = sw + o.woff[m.nlayers];
   const int row0 = blockIdx.x * R, nrows = min(R, m.rows - row0);
+  stage_weights(m, o, sw, sb);
   for (int i = 0; i < m.nbufs; ++i)
     if (m.buf[i].role & VG_MLP_INPUT) load_rows(sm + R * o.off[i], m.buf[i].act, m.buf[i].width, row0, nrows, R);
+  cp_async_commit_wait_all();
   __syncthreads();
   for (int l = 0; l < m.nlayers; ++l) {
     const VgMlpLayer& L = m.layer[l];
     float* sy = sm + R * o.off[L.out];
-    dense_fwd<R>(sm + R * o.off[L.in], L.k, L.w, L.b, L.n, sy, L.act);
+    dense_fwd<R>(sm + R * o.off[L.in], L.k, sw + o.woff[l], sb + o.boff[l], L.n, sy, L.act);
     __syncthreads();
     store_rows(m.buf[L.out].act, sy, L.n, row0, nrows);
   }
@@ -155,12 +188,16 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_bwd_kernel(const VgMlp m, con
   extern __shared__ float sm[];
   float* sact = sm;
   float* sgrad = sm + R * o.off[m.nbufs];
+  float* sw = sgrad + R * o.off[m.nbufs];
+  float* sb = sw + o.woff[m.nlayers];
   const int row0 = blockIdx.x * R, nrows = min(R, m.rows - row0);
+  stage_weights(m, o, sw, sb);
   for (int i = 0; i < m.nbufs; ++i) {
     load_rows(sact + R * o.off[i], m.buf[i].act, m.buf[i].width, row0, nrows, R);
     load_rows(sgrad + R * o.off[i], (m.buf[i].role & VG_MLP_GRAD_IN) ? m.buf[i].grad : nullptr, m.buf[i].width, row0,
               nrows, R);
   }
+  cp_async_commit_wait_all();
   __syncthreads();
   for (int l = m.nlayers - 1; l >= 0; --l) {
     const VgMlpLayer& L = m.layer[l];
@@ -173,7 +210,7 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_bwd_kernel(const VgMlp m, con
     }
     bool need_dx = (m.buf[L.in].role & VG_MLP_GRAD_OUT) != 0;
     for (int q = 0; q < l; ++q) need_dx = need_dx || m.layer[q].out == L.in;
-    if (need_dx) dense_dx<R>(dy, L.n, L.w, L.k, sgrad + R * o.off[L.in]);
+    if (need_dx) dense_dx<R>(dy, L.n, sw + o.woff[l], L.k, sgrad + R * o.off[L.in]);
     dense_dw<R>(dy, L.n, sact + R * o.off[L.in], L.k, L.dw, L.db);
     __syncthreads();
   }
@@ -184,15 +221,19 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_bwd_kernel(const VgMlp m, con
 static int check_mlp(const VgMlp* m, MlpOffsets& o, bool backward) {
   VG_CHECK_ARG(m && m->nlayers >= 1 && m->nlayers <= VG_MLP_MAX_LAYERS && m->nbufs >= 2 && m->nbufs <= VG_MLP_MAX_BUFS,
                "layer / buffer count");
-  VG_CHECK_ARG(m->rows > 0 && (m->rows_per_cta == 4 || m->rows_per_cta == 8), "rows, rows_per_cta (4 or 8)");
+  VG_CHECK_ARG(m->rows > 0 && (m->rows_per_cta == 1 || m->rows_per_cta == 2 || m->rows_per_cta == 4 || m->rows_per_cta == 8),
+               "rows, rows_per_cta (1, 2, 4 or 8)");
   o.off[0] = 0;
   for (int i = 0; i < m->nbufs; ++i) {
     VG_CHECK_ARG(m->buf[i].width > 0 && m->buf[i].act, "buffer width / activation pointer");
     if (backward && (m->buf[i].role & (VG_MLP_GRAD_IN | VG_MLP_GRAD_OUT))) VG_CHECK_ARG(m->buf[i].grad, "gradient pointer");
     o.off[i + 1] = o.off[i] + m->buf[i].width;
   }
+  o.woff[0] = o.boff[0] = 0;
   for (int l = 0; l < m->nlayers; ++l) {
     const VgMlpLayer& L = m->layer[l];
+    o.woff[l + 1] = o.woff[l] + L.n * L.k;
+    o.boff[l + 1] = o.boff[l] + L.n;
     VG_CHECK_ARG(L.w && L.in >= 0 && L.in < m->nbufs && L.out >= 0 && L.out < m->nbufs && L.in != L.out, "layer wiring");
     VG_CHECK_ARG(L.k == m->buf[L.in].width && L.n == m->buf[L.out].width, "layer shape vs buffer width");
     VG_CHECK_ARG(L.k <= 32 * MLP_KSTEPS && L.k <= MLP_THREADS, "layer input width > 224");
@@ -217,17 +258,27 @@ using namespace vg;
 extern "C" int vg_mlp_fwd(const VgMlp* m, void* stream) {
   MlpOffsets o;
   VG_TRY(check_mlp(m, o, false));
-  const size_t smem = (size_t)m->rows_per_cta * o.off[m->nbufs] * sizeof(float);
-  VG_CHECK_ARG(smem <= 200 * 1024, "activations of rows_per_cta rows exceed shared memory");
+  const size_t smem = ((size_t)m->rows_per_cta * o.off[m->nbufs] + o.woff[m->nlayers] + o.boff[m->nlayers]) * sizeof(float);
+  VG_CHECK_ARG(smem <= 224 * 1024, "weights + activations of rows_per_cta rows exceed shared memory");
   cudaStream_t st = as_stream(stream);
-  return m->rows_per_cta == 4 ? launch_mlp(mlp_fwd_kernel<4>, m, o, smem, st) : launch_mlp(mlp_fwd_kernel<8>, m, o, smem, st);
+  switch (m->rows_per_cta) {
+    case 1: return launch_mlp(mlp_fwd_kernel<1>, m, o, smem, st);
+    case 2: return launch_mlp(mlp_fwd_kernel<2>, m, o, smem, st);
+    case 4: return launch_mlp(mlp_fwd_kernel<4>, m, o, smem, st);
+    default: return launch_mlp(mlp_fwd_kernel<8>, m, o, smem, st);
+  }
 }
 
 extern "C" int vg_mlp_bwd(const VgMlp* m, void* stream) {
   MlpOffsets o;
   VG_TRY(check_mlp(m, o, true));
-  const size_t smem = (size_t)2 * m->rows_per_cta * o.off[m->nbufs] * sizeof(float);
-  VG_CHECK_ARG(smem <= 200 * 1024, "activations of rows_per_cta rows exceed shared memory");
+  const size_t smem = ((size_t)2 * m->rows_per_cta * o.off[m->nbufs] + o.woff[m->nlayers] + o.boff[m->nlayers]) * sizeof(float);
+  VG_CHECK_ARG(smem <= 224 * 1024, "weights + activations of rows_per_cta rows exceed shared memory");
   cudaStream_t st = as_stream(stream);
-  return m->rows_per_cta == 4 ? launch_mlp(mlp_bwd_kernel<4>, m, o, smem, st) : launch_mlp(mlp_bwd_kernel<8>, m, o, smem, st);
+  switch (m->rows_per_cta) {
+    case 1: return launch_mlp(mlp_bwd_kernel<1>, m, o, smem, st);
+    case 2: return launch_mlp(mlp_bwd_kernel<2>, m, o, smem, st);
+    case 4: return launch_mlp(mlp_bwd_kernel<4>, m, o, smem, st);
+    default: return launch_mlp(mlp_bwd_kernel<8>, m, o, smem, st);
+  }
 }

@@ -279,7 +279,7 @@ static void mlp_buf(VgMlpBuf& b, float* act, float* grad, int width, int role) {
 static VgMlp enc_head_mlp(const VgStepIO* io, const EncWs& e, int B, float* d_h1, float* dheads) {
   const bool g = dheads != nullptr;
   VgMlp m{};
-  m.nlayers = 7; m.nbufs = 8; m.rows = B; m.rows_per_cta = 4;
+  m.nlayers = 7; m.nbufs = 8; m.rows = B; m.rows_per_cta = B <= 64 ? 1 : (B <= 256 ? 2 : 4);   // >= ~32 CTAs
   mlp_buf(m.buf[0], e.h1, d_h1, 200, VG_MLP_INPUT | (g ? VG_MLP_GRAD_OUT : 0));
   mlp_buf(m.buf[1], e.h2, nullptr, 100, 0);
   mlp_buf(m.buf[2], e.h31, nullptr, 50, 0);
@@ -300,7 +300,7 @@ static VgMlp enc_head_mlp(const VgStepIO* io, const EncWs& e, int B, float* d_h1
 static VgMlp dec_stem_mlp(const VgStepIO* io, const DecWs& d, const float* zcat, int nd, float* d_zcat, float* d_f7) {
   const bool g = d_f7 != nullptr;
   VgMlp m{};
-  m.nlayers = 3; m.nbufs = 4; m.rows = nd; m.rows_per_cta = 8;
+  m.nlayers = 3; m.nbufs = 4; m.rows = nd; m.rows_per_cta = nd <= 320 ? 2 : (nd <= 1200 ? 4 : 8);   // ~one wave of CTAs
   mlp_buf(m.buf[0], const_cast<float*>(zcat), d_zcat, ZD, VG_MLP_INPUT | (g ? VG_MLP_GRAD_OUT : 0));
   mlp_buf(m.buf[1], d.f5, nullptr, 50, 0);
   mlp_buf(m.buf[2], d.f6, nullptr, 100, 0);
