@@ -22,7 +22,9 @@ struct GemmArgs {
   float* rowsum;                    // (m) += sum_k A_eff(m,k)   (bias gradient, fused into the dW GEMM) or null
 };
 
-__global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs a) {
+// AK / BK: the K index is the contiguous one of A / B (compile-time, so each tile load is one code path)
+template <bool AK, bool BK>
+__global__ void __launch_bounds__(256, 2) gemm_kernel(const GemmArgs a) {
   __shared__ float sA[TK][TM + 4];
   __shared__ float sB[TK][TN + 4];
   const int tid = threadIdx.x;
@@ -38,34 +40,53 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs a) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  for (int k0 = kbeg; k0 < kend; k0 += TK) {
-    // A tile: TM x TK elements, TM*TK/256 per thread, all loads in flight together.  Pick the
-    // faster-varying thread index along whichever of (m, k) is contiguous in memory.
+  // Register double buffering: the global loads of tile k0 + TK are in flight while tile k0 is multiplied
+  // (these GEMMs are a few CTAs deep in K, so the load latency of every K step used to be exposed).
+  // Element e of a tile: the faster-varying thread index runs along whichever of (m, k) is contiguous.
+  constexpr int NA = TM * TK / 256, NB = TN * TK / 256;
+  float ra[NA], rb[NB];
+  auto fetch = [&](int k0) {
 #pragma unroll
-    for (int r = 0; r < TM * TK / 256; ++r) {
-      int e = tid + r * 256;
+    for (int r = 0; r < NA; ++r) {
+      const int e = tid + r * 256;
       int mm, kk;
-      if (a.as_k == 1) { kk = e % TK; mm = e / TK; } else { mm = e % TM; kk = e / TM; }
-      int gm = m0 + mm, gk = k0 + kk;
+      if (AK) { kk = e % TK; mm = e / TK; } else { mm = e % TM; kk = e / TM; }
+      const int gm = m0 + mm, gk = k0 + kk;
       float v = 0.f;
       if (gm < a.m && gk < kend) {
         const long long off = gm * a.as_m + gk * a.as_k;
         v = __ldg(a.A + off);
         if (a.MA && !(__ldg(a.MA + off) > 0.f)) v = 0.f;
       }
-      sA[kk][mm] = v;
+      ra[r] = v;
     }
 #pragma unroll
-    for (int r = 0; r < TN * TK / 256; ++r) {
-      int e = tid + r * 256;
+    for (int r = 0; r < NB; ++r) {
+      const int e = tid + r * 256;
       int nn, kk;
-      if (a.bs_k == 1) { kk = e % TK; nn = e / TK; } else { nn = e % TN; kk = e / TN; }
-      int gn = n0 + nn, gk = k0 + kk;
-      float v = 0.f;
-      if (gn < a.n && gk < kend) v = __ldg(a.B + gk * a.bs_k + gn * a.bs_n);
-      sB[kk][nn] = v;
+      if (BK) { kk = e % TK; nn = e / TK; } else { nn = e % TN; kk = e / TN; }
+      const int gn = n0 + nn, gk = k0 + kk;
+      rb[r] = (gn < a.n && gk < kend) ? __ldg(a.B + gk * a.bs_k + gn * a.bs_n) : 0.f;
+    }
+  };
+  if (kbeg < kend) fetch(kbeg);
+  for (int k0 = kbeg; k0 < kend; k0 += TK) {
+#pragma unroll
+    for (int r = 0; r < NA; ++r) {
+      const int e = tid + r * 256;
+      int mm, kk;
+      if (AK) { kk = e % TK; mm = e / TK; } else { mm = e % TM; kk = e / TM; }
+      sA[kk][mm] = ra[r];
+    }
+#pragma unroll
+    for (int r = 0; r < NB; ++r) {
+      const int e = tid + r * 256;
+      int nn, kk;
+      if (BK) { kk = e % TK; nn = e / TK; } else { nn = e % TN; kk = e / TN; }
+      sB[kk][nn] = rb[r];
     }
     __syncthreads();
+    if (k0 + TK < kend) fetch(k0 + TK);
     if (a.rowsum && blockIdx.x == 0 && tx == 0) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -75,7 +96,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs a) {
         rs[i] += s;
       }
     }
-#pragma unroll
+#pragma unroll 8
     for (int kk = 0; kk < TK; ++kk) {
       float av[4], bv[4];
 #pragma unroll
@@ -145,7 +166,7 @@ __global__ void bias_act_kernel(float* __restrict__ y, const float* __restrict__
 static int pick_ksplit(int m, int n, int k) {
   const int blocks = cdiv(n, TN) * cdiv(m, TM);
   if (blocks >= 64 || k < 512) return 1;
-  int s = vg_sm_count() / blocks;
+  int s = 2 * vg_sm_count() / blocks;      // two resident CTAs per SM keep the K chains short
   const int maxs = k / 128;
   if (s > maxs) s = maxs;
   return s < 1 ? 1 : s;
@@ -154,7 +175,11 @@ static int pick_ksplit(int m, int n, int k) {
 static int gemm(GemmArgs a, cudaStream_t st) {
   if (a.ksplit < 1) a.ksplit = 1;
   dim3 grid(cdiv(a.n, TN), cdiv(a.m, TM), a.ksplit);
-  gemm_kernel<<<grid, 256, 0, st>>>(a);
+  const bool ak = a.as_k == 1, bk = a.bs_k == 1;
+  if (ak && bk) gemm_kernel<true, true><<<grid, 256, 0, st>>>(a);
+  else if (ak) gemm_kernel<true, false><<<grid, 256, 0, st>>>(a);
+  else if (bk) gemm_kernel<false, true><<<grid, 256, 0, st>>>(a);
+  else gemm_kernel<false, false><<<grid, 256, 0, st>>>(a);
   VG_LAUNCH_CHECK();
   return VG_OK;
 }
