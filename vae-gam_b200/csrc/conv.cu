@@ -372,12 +372,52 @@ static int launch_gather(int cin, int cout, const Geom& g, const GatherArgs& a, 
   return VG_EINVAL;
 }
 
+// Helper streams for the output-parity phases of a small stride-2 layer: the phases write disjoint
+// outputs (statistics are accumulated atomically), each is a latency-bound launch of a few CTAs, so they
+// run side by side: fork from the caller's stream with one event, join back with one event per phase.
+// Stream-capture safe (event record / wait only); VAEGAM_PHASE_STREAMS=0 serialises them.
+constexpr int kPhaseStreams = 7;
+struct PhaseStreams {
+  cudaStream_t s[kPhaseStreams];
+  cudaEvent_t fork, join[kPhaseStreams];
+  bool ok = false;
+};
+static PhaseStreams& phase_streams() {
+  static PhaseStreams ps;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    const char* e = getenv("VAEGAM_PHASE_STREAMS");
+    if (!(e && e[0] == '0')) {
+      ps.ok = cudaEventCreateWithFlags(&ps.fork, cudaEventDisableTiming) == cudaSuccess;
+      for (int i = 0; i < kPhaseStreams; ++i)
+        ps.ok = ps.ok && cudaStreamCreateWithFlags(&ps.s[i], cudaStreamNonBlocking) == cudaSuccess &&
+                cudaEventCreateWithFlags(&ps.join[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+    if (!ps.ok) (void)cudaGetLastError();
+  }
+  return ps;
+}
+
 // every gather of one layer pass: one fused multi-phase launch when the plane-folded kernel covers it
 static int launch_all(int cin, int cout, const Geom* gs, int ng, const GatherArgs& a, cudaStream_t st) {
   if (ng > 1 && conv_mode() == 1 && tc2_worthwhile(gs, ng) && tc2_supported(cin, cout, gs, ng))
     return launch_tc2_gather(cin, cout, gs, ng, a, st);
-  for (int i = 0; i < ng; ++i) VG_TRY(launch_gather(cin, cout, gs[i], a, st));
-  return VG_OK;
+  PhaseStreams& ps = phase_streams();
+  if (ng < 2 || ng > kPhaseStreams + 1 || !ps.ok) {
+    for (int i = 0; i < ng; ++i) VG_TRY(launch_gather(cin, cout, gs[i], a, st));
+    return VG_OK;
+  }
+  VG_CUDA(cudaEventRecord(ps.fork, st));
+  int rc = launch_gather(cin, cout, gs[0], a, st);
+  for (int i = 1; i < ng; ++i) {
+    cudaStream_t hs = ps.s[i - 1];
+    VG_CUDA(cudaStreamWaitEvent(hs, ps.fork, 0));
+    if (rc == VG_OK) rc = launch_gather(cin, cout, gs[i], a, hs);
+    VG_CUDA(cudaEventRecord(ps.join[i - 1], hs));          // always joined, also after a failed launch
+    VG_CUDA(cudaStreamWaitEvent(st, ps.join[i - 1], 0));
+  }
+  return rc;
 }
 
 }  // namespace vg

@@ -60,10 +60,12 @@ class FlatParams:
             raise ValueError(f"parameters missing from module: {missing}")
         self.params = [named_params[n] for n in self.names]
         self.device = device
+        self.version = 0
         self.rebuild()
 
     def rebuild(self):
         """(Re)pack the current parameter values into the flat buffers."""
+        self.version += 1          # pointer tables cached by StepEngine are rebuilt when this changes
         p32 = [p for p in self.params if p.dtype == torch.float32]
         p64 = [p for p in self.params if p.dtype == torch.float64]
         assert len(p32) + len(p64) == len(self.params)
@@ -178,13 +180,21 @@ class StepEngine:
         return sb
 
     def _bind_params(self, sb: StepBuffers, with_grads: bool):
-        for i, p in enumerate(self.flat.params):
+        """Parameter / gradient pointer tables of the IO struct.  The 2 x 97 pointers only change when the
+        flat buffers are re-packed (FlatParams.version) or a Parameter stops aliasing them, so the tables
+        are rebuilt only then: the first and last parameter's addresses are the cheap per-step check."""
+        ps = self.flat.params
+        key = (self.flat.version, ps[0].data_ptr(), ps[-1].data_ptr(), self.flat.grad32.data_ptr(),
+               self.flat.grad64.data_ptr())
+        if getattr(sb, "bound_key", None) == key:
+            return
+        for i, p in enumerate(ps):
             sb.io.params[i] = p.data_ptr()
-        if with_grads:
-            for i, n in enumerate(self.flat.names):
-                dt, off, k = self.flat.slices[n]
-                buf = self.flat.grad32 if dt == torch.float32 else self.flat.grad64
-                sb.io.grads[i] = buf.data_ptr() + off * buf.element_size()
+        for i, n in enumerate(self.flat.names):
+            dt, off, k = self.flat.slices[n]
+            buf = self.flat.grad32 if dt == torch.float32 else self.flat.grad64
+            sb.io.grads[i] = buf.data_ptr() + off * buf.element_size()
+        sb.bound_key = key
 
     def draw_noise(self, B: int, generator=None):
         """Same draws, same order as the reference on this device: eps_W (B,1), eps_D (B,32)
