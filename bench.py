@@ -420,7 +420,7 @@ def main():
             w = op_work(top["op"], B)
             traffic = None
             try:      # dram__bytes_read.sum + dram__bytes_write.sum of the same kernel from the committed ncu capture
-                tr = json.load(open(os.path.join(ROOT, "profiles", "r1_s3_ncu_traffic.json")))["ops"].get(top["op"])
+                tr = json.load(open(os.path.join(ROOT, "profiles", "r1_s5_ncu_traffic.json")))["ops"].get(top["op"])
                 if tr and B == BATCH:
                     traffic = tr["dram_read_bytes"] + tr["dram_write_bytes"]
             except Exception:
@@ -437,6 +437,7 @@ def main():
     if rank != 0:
         if world > 1:
             dist.barrier()
+            dist.destroy_process_group()
         return
     total_vols = args.steps * B * world
     value = total_vols / (ms * 1e-3)
@@ -466,6 +467,7 @@ def main():
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
