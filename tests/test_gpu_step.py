@@ -180,6 +180,97 @@ def test_drop_in_training_loop_decreases_loss(tmp_path):
     assert not torch.equal(before, other.epsilon.detach())
 
 
+def _nifti_experiment(tmp_path, n_subjects=2, n_vols=5):
+    """A tiny cohort backed by real 4-D NIfTI files (BASELINE config 5 needs reference images for affine / header)."""
+    import nibabel as nib
+    import pandas as pd
+    from vaegam import synthetic as syn
+    coh = syn.make_cohort(n_subjects, "checker", seed=3, n_vols=n_vols)
+    vols = coh.volumes().numpy() * 3284.5                                     # the loader divides by 3284.5
+    tab = coh.table.copy()
+    sidx = coh.subject_index()
+    paths = []
+    for s, name in enumerate(tab["subjid"].unique().tolist()):
+        v4 = np.moveaxis(vols[sidx == s], 0, -1).astype(np.float32)           # (41,49,35,T)
+        path = str(tmp_path / f"{name}.nii.gz")
+        nib.save(nib.Nifti1Image(v4, np.diag([3.0, 3.0, 3.5, 1.0])), path)
+        paths.append(path)
+    tab["nii_path"] = [paths[s] for s in sidx]
+    tab["volume #"] = np.concatenate([np.arange(n_vols)] * n_subjects)
+    csv = str(tmp_path / "train.csv")
+    tab.to_csv(csv)
+    glm = str(tmp_path / "glm.csv")
+    pd.DataFrame(syn.glm_maps_uniform(), columns=syn.GLM_COLS).to_csv(glm)
+    return csv, glm, coh
+
+
+def test_recons_only_path_config5(tmp_path):
+    """BASELINE config 5 (`--recons_only`, reference multsubj_reg_run_GP.py:84-93 + build_model_recons.py):
+    checkpoint -> project_latent, plot_GPs, per-volume reconstructions and subject / grand averages.
+    The files hold what forward(return_latent_rec=True) returns for the same draws, and the averages computed from
+    the device-side sums equal the reference's procedure (re-reading every file)."""
+    import DataClass_GP as data
+    import build_model_recons as recon
+    import nibabel as nib
+    import pandas as pd
+    import vae_reg_GP
+    from vaegam.step import IMG_KEYS
+    csv, glm, coh = _nifti_experiment(tmp_path)
+    torch.manual_seed(5)
+    model = vae_reg_GP.VAE(save_dir=str(tmp_path), glm_maps=glm, csv_files=[csv, csv])
+    model.save_state("ck.tar")
+    torch.manual_seed(6)
+    m2 = vae_reg_GP.VAE(save_dir=str(tmp_path), glm_maps=glm, csv_files=[csv, csv])
+    m2.load_state(str(tmp_path / "ck.tar"))
+    loaders = data.setup_data_loaders(batch_size=4, train_csv=csv, test_csv=csv)
+    n = len(loaders['UnShuffled_train'].dataset)
+
+    latent = m2.project_latent(loaders, save_dir=str(tmp_path), title="t", split=5)
+    assert latent.shape == (n, 32) and np.isfinite(latent).all()
+    assert np.loadtxt(str(tmp_path / "000_latent_means.csv"), delimiter=",").shape == (n, 32)
+    m2.plot_GPs(csv_file=csv, save_dir=str(tmp_path))
+    gp_csv = pd.read_csv(str(tmp_path / "000_GP_plots" / "000_GP_x_full.csv"))
+    assert len(gp_csv) == n and (gp_csv["vars"] > 0).all() and gp_csv["xq"].is_monotonic_increasing
+
+    torch.manual_seed(11)
+    recon.mk_single_volumes(loaders['UnShuffled_train'], m2, csv, str(tmp_path))
+    torch.manual_seed(11)                                  # same draws, same batches -> the same maps
+    expect = {k: [] for k in IMG_KEYS}
+    for sample in loaders['UnShuffled_train']:
+        ids, cov, x = m2._batch(sample)
+        with torch.no_grad():
+            _, z, imgs = m2.forward(ids, cov, x, 'reconstruction', return_latent_rec=True, train_mode=False)
+        assert z.shape == (ids.shape[0], 32)
+        for k in IMG_KEYS:
+            expect[k].append(imgs[k])
+    expect = {k: np.concatenate(v) for k, v in expect.items()}
+    subjs = pd.read_csv(csv).subjid.unique().tolist()
+    root = tmp_path / "reconstructions" / "000_model_recons"
+    row = 0
+    for s in subjs:
+        for t in range(5):
+            for k in IMG_KEYS:
+                img = nib.load(str(root / s / f"vol_{float(t)}" / f"recon_{k}.nii"))
+                got = np.asarray(img.dataobj)
+                assert got.shape == (41, 49, 35) and np.allclose(img.affine, np.diag([3.0, 3.0, 3.5, 1.0]))
+                # BatchNorm statistics are accumulated with fp64 atomics: repeat runs agree to rounding, not bit for bit
+                assert np.allclose(got.reshape(-1), expect[k][row], rtol=1e-4, atol=1e-5), (s, t, k)
+            row += 1
+
+    recon.mk_avg_maps(csv, m2, str(tmp_path), mk_motion_maps=True)           # device-side sums
+    avg = tmp_path / "reconstructions" / "000_avg_model_recons"
+    fast = {(s, k): np.asarray(nib.load(str(avg / s / f"{k}_avg.nii")).dataobj) for s in subjs for k in IMG_KEYS}
+    fast_grand = {k: np.asarray(nib.load(str(avg / f"{k}_avg.nii")).dataobj) for k in IMG_KEYS}
+    m2._recon_avg = None                                                       # the reference's procedure
+    recon.mk_avg_maps(csv, m2, str(tmp_path), mk_motion_maps=True)
+    for k in IMG_KEYS:
+        for i, s in enumerate(subjs):
+            slow = np.asarray(nib.load(str(avg / s / f"{k}_avg.nii")).dataobj)
+            assert np.allclose(fast[(s, k)], slow, rtol=1e-12, atol=1e-14)
+            assert np.allclose(slow.reshape(-1), expect[k][5 * i:5 * i + 5].astype(np.float64).mean(0), rtol=1e-4, atol=1e-5)
+        assert np.allclose(fast_grand[k], np.asarray(nib.load(str(avg / f"{k}_avg.nii")).dataobj), rtol=1e-12, atol=1e-14)
+
+
 def test_properties_at_baseline_batch():
     """B=32 (BASELINE config batch): determinism, term identity, API consistency."""
     from oracle import ref_port as rp

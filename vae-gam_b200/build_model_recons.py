@@ -35,6 +35,20 @@ def mk_avg_maps(csv_file, model, save_dir, mk_motion_maps=False):
     ref_niis = dset.nii_path.unique().tolist()
     subjs = dset.subjid.unique().tolist()
     maps = _ALL_MAPS if mk_motion_maps else [_ALL_MAPS[i] for i in (0, 1, 2, 9)]
+    dev = getattr(model, "_recon_avg", None)
+    if dev is not None and dev["epoch"] == model.epoch and \
+            dev["save_dirs"] == [os.path.join(single, s) for s in subjs] and float(dev["counts"].min()) > 0:
+        # per-subject sums accumulated on the device by VAE.reconstruct: no file is read back
+        from vaegam.step import IMG_KEYS
+        means = (dev["sums"] / dev["counts"][:, None, None]).cpu().numpy()          # (S, 10, V) fp64
+        for key in maps:
+            k = IMG_KEYS.index(key)
+            for i, s in enumerate(subjs):
+                out = os.path.join(avg, s)
+                os.makedirs(out, exist_ok=True)
+                _save_map(means[i, k].reshape(41, 49, 35), ref_niis[i], out, key)
+            _save_map(means[:, k].mean(0).reshape(41, 49, 35), ref_niis[0], avg, key)
+        return
     for key in maps:
         grand = np.zeros((41, 49, 35), np.float64)
         for i, s in enumerate(subjs):

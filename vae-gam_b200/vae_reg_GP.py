@@ -400,26 +400,63 @@ class VAE(nn.Module):
         return latent
 
     def reconstruct(self, loader, ref_niis, save_dirs):
-        """Per-volume NIfTI maps for every key of `imgs` (reference vae_reg_GP.py:585-620)."""
+        """Per-volume NIfTI maps for every key of `imgs` (reference vae_reg_GP.py:585-620), same file tree.
+
+        B200-first: the 10 maps of a batch are the optional outputs of the fused
+        reconstruction pass and stay on the device as one (10, B, V) block; per-subject sums are
+        accumulated there (fp64 index_add) so that `build_model_recons.mk_avg_maps` does not have to
+        read the 10 x N files back; one asynchronous D2H per batch into alternating pinned buffers,
+        and the files of batch i are written by a small thread pool while batch i+1 computes."""
         import nibabel as nib
+        from concurrent.futures import ThreadPoolExecutor
+        eng = self._get_engine()
+        n_subj = len(save_dirs)
+        sums = torch.zeros(n_subj, len(IMG_KEYS), IMG_DIM, dtype=torch.float64, device=self.device)
+        counts = torch.zeros(n_subj, dtype=torch.float64, device=self.device)
         ref_cache = {}
-        with torch.no_grad():
-            for sample in loader:
+        pinned = [None, None]
+        pending = [[], []]
+        copied = [torch.cuda.Event(), torch.cuda.Event()]
+
+        def write_volume(arr10, s, vol):
+            vol_dir = os.path.join(save_dirs[s], 'vol_{}'.format(vol))
+            os.makedirs(vol_dir, exist_ok=True)
+            aff, hdr = ref_cache[s]
+            for k, key in enumerate(IMG_KEYS):
+                nib.save(nib.Nifti1Image(arr10[k].reshape(IMG_SHAPE), aff, hdr),
+                         os.path.join(vol_dir, 'recon_{}.nii'.format(key)))
+
+        with torch.no_grad(), ThreadPoolExecutor(max_workers=4) as pool:
+            for it, sample in enumerate(loader):
                 ids, covariates, x = self._batch(sample)
+                B = ids.shape[0]
                 vol_num, subjidx = sample['vol_num'].tolist(), sample['subjid'].tolist()
-                _, _, imgs = self.forward(ids, covariates, x, 'reconstruction', return_latent_rec=True,
-                                          train_mode=False)
-                for key, arr in imgs.items():
-                    for b in range(ids.shape[0]):
-                        s = subjidx[b]
-                        vol_dir = os.path.join(save_dirs[s], 'vol_{}'.format(vol_num[b]))
-                        os.makedirs(vol_dir, exist_ok=True)
-                        if s not in ref_cache:
-                            ref = nib.load(ref_niis[s])
-                            ref_cache[s] = (ref.affine, ref.header)
-                        aff, hdr = ref_cache[s]
-                        nib.save(nib.Nifti1Image(arr[b].reshape(IMG_SHAPE), aff, hdr),
-                                 os.path.join(vol_dir, 'recon_{}.nii'.format(key)))
+                for s in set(subjidx):
+                    if s not in ref_cache:
+                        ref = nib.load(ref_niis[s])
+                        ref_cache[s] = (ref.affine, ref.header)
+                _, sb = run_step(eng, x.reshape(B, -1), covariates, None, True)
+                self._last = sb
+                stack = torch.cat([sb.maps[0, :, :IMG_DIM].unsqueeze(0), sb.cons, sb.x_rec.unsqueeze(0)])   # (10,B,V)
+                per_vol = stack.permute(1, 0, 2)                                                          # (B,10,V)
+                sums.index_add_(0, ids.to(self.device), per_vol.double())
+                counts.index_add_(0, ids.to(self.device), torch.ones(B, dtype=torch.float64, device=self.device))
+                slot = it % 2
+                for f in pending[slot]:
+                    f.result()                        # the files that read this pinned buffer are written
+                if pinned[slot] is None or pinned[slot].shape[0] < B:
+                    pinned[slot] = torch.empty(max(B, loader.batch_size or B), len(IMG_KEYS), IMG_DIM).pin_memory()
+                host = pinned[slot][:B]
+                host.copy_(per_vol, non_blocking=True)
+                copied[slot].record()
+                copied[slot].synchronize()
+                arr = host.numpy()
+                pending[slot] = [pool.submit(write_volume, arr[b], subjidx[b], vol_num[b]) for b in range(B)]
+            for fs in pending:
+                for f in fs:
+                    f.result()
+        self.check_status()
+        self._recon_avg = {"epoch": self.epoch, "save_dirs": list(save_dirs), "sums": sums, "counts": counts}
 
     def plot_GPs(self, csv_file='', save_dir=''):
         """Posterior gain mean / variance over all rows of the CSV, one sorted CSV (+ PDF when

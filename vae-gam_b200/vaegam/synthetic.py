@@ -152,13 +152,13 @@ class Cohort:
         if self.signal == "blob":  # HRF-shaped response per subject run
             taps = torch.from_numpy(hrf_taps().astype(np.float32))
             tv = task.clone()
-            n = N_VOLS
-            for s0 in range(0, len(task), n):
-                seg = task[s0:s0 + n]
+            starts = [0] + [i for i in range(1, len(sidx)) if sidx[i] != sidx[i - 1]] + [len(sidx)]
+            for s0, s1 in zip(starts[:-1], starts[1:]):      # one run per subject
+                seg = task[s0:s1]
                 full = torch.zeros(len(seg))
-                for k in range(len(taps)):
+                for k in range(min(len(taps), len(seg))):
                     full[k:] += taps[k] * seg[:len(seg) - k]
-                tv[s0:s0 + n] = full
+                tv[s0:s1] = full
             task = tv
         out = torch.empty((len(idx), IMG_DIM), dtype=torch.float32)
         anat_cache = {}
