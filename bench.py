@@ -431,8 +431,9 @@ def main():
                     "tensor_frac": round(top["gflops"] / 1e3 / tf_peak, 5)}
         rl = [r for r in rows if r["op"].startswith("recon_loss")]
         kernels["fused_loss"] = [{"op": r["op"], "gbs": r.get("gbs"), "frac_hbm": round(r.get("gbs", 0) / hbm_peak, 4)} for r in rl]
-        fl = fused_loss_roofline(device)
-        kernels["fused_loss_b128_alone"] = {k: dict(v, frac_hbm=round(v["gbs"] / hbm_peak, 4)) for k, v in fl.items()}
+        for bb in (128, 512):       # alone, inputs (0.36 / 1.4 GB) larger than L2: the stage's own roofline figure
+            fl = fused_loss_roofline(device, B=bb)
+            kernels[f"fused_loss_b{bb}_alone"] = {k: dict(v, frac_hbm=round(v["gbs"] / hbm_peak, 4)) for k, v in fl.items()}
 
     if rank != 0:
         if world > 1:

@@ -247,7 +247,7 @@ int vg_gp_posterior(const float* xu, int m, const float* k_var, const float* ls,
  * ---------------------------------------------------------------------------------- */
 size_t vg_recon_workspace_bytes(int b, long long v);
 /* Launch shape of both passes (warps per CTA x CTAs per SM x cp.async ring stages):
- * 0: 4 x 5 x 2, 1 (default): 4 x 3 x 3, 2: 4 x 4 x 2. */
+ * 0: 4 x 5 x 2, 1: 4 x 3 x 3, 2: 4 x 4 x 2, 3 (default, also for any other value): 8 x 2 x 3. */
 void vg_recon_tune(int variant);
 /* logp (b), norms (8,b) = ||g_i D_i[b] - G_i||_2.  Optional cons (8,b,V) and x_rec (b,V)
  * (R5 side outputs, NULL in training). */

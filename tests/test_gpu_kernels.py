@@ -553,7 +553,7 @@ def test_gain_reports_non_pd(lib):
     assert status[1].item() != 0 and status[0].item() == 0
 
 
-@pytest.mark.parametrize("B,cps", [(1, 0), (2, 0), (5, 0), (5, 1), (5, 2), (32, 0), (32, 1), (32, 2), (33, 0)])
+@pytest.mark.parametrize("B,cps", [(1, 3), (2, 3), (5, 0), (5, 1), (5, 2), (5, 3), (32, 0), (32, 1), (32, 2), (32, 3), (33, 3)])
 def test_fused_recon_loss(lib, B, cps):
     """vg_recon_loss_fwd/bwd vs the fp64 oracle (R1-R4 and the fused-pass gradients); cps = the
     backward kernel's launch-shape variant (vg_recon_tune)."""
@@ -591,7 +591,7 @@ def test_fused_recon_loss(lib, B, cps):
                                        native.ptr(norms), B, V, lam, native.ptr(dpre), native.ptr(dg), native.ptr(deps),
                                        native.ptr(ws), nbytes, st))
     torch.cuda.synchronize()
-    lib.vg_recon_tune(1)                                                        # back to the default
+    lib.vg_recon_tune(-1)                                                       # back to the default
     assert rel_err(logp.cpu(), rl["logp"].detach()) < 2e-6
     assert rel_err(norms.cpu(), rl["glm_norms"].detach()) < 2e-6
     assert rel_err(cons.cpu(), rl["cons"].detach()) < 1e-6

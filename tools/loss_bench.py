@@ -11,7 +11,7 @@ iters = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 batches = [int(a) for a in sys.argv[2:]] or [32, 128, 512]
 lib = native.load()
 for B in batches:
-    for cps in (0, 1, 2):
+    for cps in (1, 2, 3):
         lib.vg_recon_tune(cps)
         print(B, cps, bench.fused_loss_roofline(torch.device("cuda", 0), B=B, iters=iters), flush=True)
-lib.vg_recon_tune(1)
+lib.vg_recon_tune(-1)

@@ -73,11 +73,11 @@ struct ReconArgs {
 
 // Launch shape: warps per CTA, CTAs per SM, ring depth (shared memory: warps*32*stages*144 B per CTA).
 struct Shape { int warps, ctas, stages; };
-constexpr int NVARIANT = 3;
-// vg_recon_tune(variant): 0 = 4 warps x 5 CTAs/SM x 2 stages, 1 = 4 x 3 x 3 (default), 2 = 4 x 4 x 2.
-static int g_variant = 1;
+constexpr int NVARIANT = 4;
+// vg_recon_tune(variant): 0 = 4 warps x 5 CTAs/SM x 2 stages, 1 = 4 x 3 x 3, 2 = 4 x 4 x 2, 3 = 8 x 2 x 3 (default; anything else selects it).
+static int g_variant = 3;
 static inline Shape shape_of(int variant) {
-  return variant == 1 ? Shape{4, 3, 3} : variant == 2 ? Shape{4, 4, 2} : Shape{4, 5, 2};
+  return variant == 1 ? Shape{4, 3, 3} : variant == 2 ? Shape{4, 4, 2} : variant == 3 ? Shape{8, 2, 3} : Shape{4, 5, 2};
 }
 static inline size_t ring_bytes(const Shape& sh) { return (size_t)sh.stages * RING_VECS * sh.warps * 32 * sizeof(float4); }
 
@@ -484,7 +484,7 @@ static int launch_bwd(const ReconArgs& a, int grid, const float* norms, float la
 
 using namespace vg;
 
-extern "C" void vg_recon_tune(int variant) { g_variant = (variant >= 0 && variant < NVARIANT) ? variant : 1; }
+extern "C" void vg_recon_tune(int variant) { g_variant = (variant >= 0 && variant < NVARIANT) ? variant : 3; }
 
 extern "C" size_t vg_recon_workspace_bytes(int b, long long v) {
   if (b <= 0 || v <= 0) return 256;
@@ -512,6 +512,7 @@ extern "C" int vg_recon_loss_fwd(const float* maps, const float* g, const float*
   float* ws = (float*)workspace;
   if (variant == 1) VG_TRY((launch_fwd<4, 3, 3>(a, p.grid, ws, cons, x_rec, st)));
   else if (variant == 2) VG_TRY((launch_fwd<4, 4, 2>(a, p.grid, ws, cons, x_rec, st)));
+  else if (variant == 3) VG_TRY((launch_fwd<8, 2, 3>(a, p.grid, ws, cons, x_rec, st)));
   else VG_TRY((launch_fwd<4, 5, 2>(a, p.grid, ws, cons, x_rec, st)));
   recon_finalize<<<cdiv(b * 9 * 32, 256), 256, 0, st>>>(ws, b, p.n_c8, p.span, p.n_items, sh.warps, 9, 1, logp, norms);
   VG_LAUNCH_CHECK();
@@ -534,6 +535,7 @@ extern "C" int vg_recon_loss_bwd(const float* maps, const float* g, const float*
   VG_CUDA(cudaMemsetAsync(deps, 0, (size_t)a.vp * sizeof(float), st));
   if (variant == 1) VG_TRY((launch_bwd<4, 3, 3>(a, p.grid, norms, lam, dpre, ws, deps, st)));
   else if (variant == 2) VG_TRY((launch_bwd<4, 4, 2>(a, p.grid, norms, lam, dpre, ws, deps, st)));
+  else if (variant == 3) VG_TRY((launch_bwd<8, 2, 3>(a, p.grid, norms, lam, dpre, ws, deps, st)));
   else VG_TRY((launch_bwd<4, 5, 2>(a, p.grid, norms, lam, dpre, ws, deps, st)));
   recon_finalize<<<cdiv(b * KCOV * 32, 256), 256, 0, st>>>(ws, b, p.n_c8, p.span, p.n_items, sh.warps, KCOV, 0, dg,
                                                            nullptr);
