@@ -180,6 +180,47 @@ def test_drop_in_training_loop_decreases_loss(tmp_path):
     assert not torch.equal(before, other.epsilon.detach())
 
 
+def test_cuda_graph_step_matches_eager_step(tmp_path):
+    """VAE.train_batch (one CUDA-graph launch per step after two eager warm-up steps) against the eager
+    forward / backward / optimizer.step sequence: same batches, same injected noise, 6 steps."""
+    import vae_reg_GP
+    from vaegam import synthetic as syn
+    tr, te, glm, coh = syn.write_experiment(str(tmp_path), n_subjects=1, config="checker", glm="uniform")
+    B = 8
+    x = coh.volumes(rows=range(6 * B)).cuda()
+    cov = torch.from_numpy(coh.covariates()[:6 * B]).cuda()
+    ids = torch.zeros(B, dtype=torch.int64, device="cuda")
+    models = []
+    for graph in (False, False, True):
+        torch.manual_seed(3)
+        m = vae_reg_GP.VAE(save_dir=str(tmp_path), glm_maps=glm, csv_files=[tr, te])
+        m.use_cuda_graph = graph
+        models.append(m)
+    eager, eager2, graphed = models
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    losses = {0: [], 1: [], 2: []}
+    for step in range(6):
+        noise = eager._get_engine().draw_noise(B, generator=gen)
+        xb, cb = x[step * B:(step + 1) * B], cov[step * B:(step + 1) * B]
+        for k, m in enumerate(models):
+            losses[k].append(float(m.train_batch(ids, cb, xb, _noise=noise).item()))
+            m.check_status()
+    assert graphed._graph_steps[B].graph is not None          # steps 3.. were graph replays
+    assert np.allclose(losses[0], losses[2], rtol=2e-4), (losses[0], losses[2])
+    assert losses[0][-1] != losses[0][0]
+    # Parameters after six Adam steps of 1e-3: Adam turns gradients whose sign is accumulation-order noise
+    # (statistics and weight gradients use atomics) into full-size steps, so two EAGER runs already differ;
+    # the graph run must sit within that run-to-run spread.
+    for (n, p), (_, p2), (_, q) in zip(eager.named_parameters(), eager2.named_parameters(), graphed.named_parameters()):
+        noise_floor = float((p.detach().double() - p2.detach().double()).abs().mean())
+        d = (p.detach().double() - q.detach().double()).abs()
+        assert float(d.max()) <= 1.3e-2, (n, float(d.max()))      # two opposite 6-step Adam walks
+        assert float(d.mean()) <= 3.0 * noise_floor + 2e-5, (n, float(d.mean()), noise_floor)
+    assert eager.optimizer._host_steps == graphed.optimizer._host_steps == 6
+    sd = graphed.optimizer.state_dict()                            # the device-side step count stays in sync
+    assert int(float(sd["state"][0]["step"])) == 6
+
+
 def _nifti_experiment(tmp_path, n_subjects=2, n_vols=5):
     """A tiny cohort backed by real 4-D NIfTI files (BASELINE config 5 needs reference images for affine / header)."""
     import nibabel as nib

@@ -33,7 +33,7 @@ from torch import nn
 import gp
 import utils
 from vaegam import native
-from vaegam.step import FlatAdam, FlatParams, GP_KEYS, IMG_KEYS, StepEngine, run_step
+from vaegam.step import FlatAdam, FlatParams, GP_KEYS, GraphStep, IMG_KEYS, StepEngine, run_step
 
 IMG_SHAPE = (41, 49, 35)
 IMG_DIM = int(np.prod(IMG_SHAPE))
@@ -123,6 +123,9 @@ class VAE(nn.Module):
         # TensorBoard hooks inside forward(): every `log_every` training steps (0 = never)
         self.log_every = int(os.environ.get("VAEGAM_TB_EVERY", "0"))
         self._step_counter = 0
+        # whole-step CUDA graphs in train_batch / train_epoch (VAEGAM_CUDA_GRAPH=0 switches them off)
+        self.use_cuda_graph = os.environ.get("VAEGAM_CUDA_GRAPH", "1") != "0"
+        self._graph_steps = {}
         self._engine = None
         self._flat = None
         self._last = None
@@ -293,17 +296,45 @@ class VAE(nn.Module):
         dev = self.device
         return sample['subjid'].to(dev), sample['covariates'].to(dev), sample['volume'].to(dev)
 
+    def train_batch(self, ids, covariates, x, _noise=None, reducer=None):
+        """forward + backward + Adam step for one minibatch (the body of the reference's train_epoch loop,
+        vae_reg_GP.py:421-429) as ONE CUDA-graph launch per step after two eager warm-up steps; returns the
+        loss tensor (shape (1,), no autograd graph).  Falls back to the eager three-call sequence when graphs
+        are switched off (`self.use_cuda_graph = False` / VAEGAM_CUDA_GRAPH=0) or when this step logs to
+        TensorBoard.  `reducer` (vaegam.dp.GradientAllReduce) puts the NCCL gradient all-reduce between
+        backward and Adam — inside the graph too."""
+        eng = self._get_engine()
+        B = ids.shape[0]
+        log_now = self.log_every > 0 and (self._step_counter % self.log_every == 0)
+        if not self.use_cuda_graph or log_now:
+            loss = self.forward(ids, covariates, x, 'train', train_mode=True, _noise=_noise)
+            self.optimizer.zero_grad()
+            loss.backward()
+            if reducer is not None:
+                reducer()
+            self.optimizer.step()
+            return loss.detach()
+        self._step_counter += 1
+        gs = self._graph_steps.get(B)
+        if gs is None or gs.version != self._flat.version or gs.engine is not eng or gs.opt is not self.optimizer \
+                or gs.reducer is not reducer:
+            gs = GraphStep(eng, self.optimizer, B, reducer)
+            self._graph_steps[B] = gs
+        gs.opt.grad_scale = self.optimizer.grad_scale
+        loss = gs.run(x.to(self.device), covariates.to(self.device), _noise)
+        self._last = gs.sb
+        for p in self._flat.params:         # gradients live in the flat buffer; nothing is left in .grad
+            p.grad = None
+        return loss
+
     def train_epoch(self, train_loader):
         self.train()
         train_loss = 0.0
         for sample in train_loader:
             ids, covariates, x = self._batch(sample)
-            loss = self.forward(ids, covariates, x, 'train', train_mode=True)
+            loss = self.train_batch(ids, covariates, x)
             train_loss += loss.item()
             self.check_status()
-            self.optimizer.zero_grad()
-            loss.backward()
-            self.optimizer.step()
         train_loss /= len(train_loader.dataset)
         print('Epoch: {} Average loss: {:.4f}'.format(self.epoch, train_loss))
         self.epoch += 1

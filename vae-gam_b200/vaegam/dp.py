@@ -82,6 +82,14 @@ class GradientAllReduce:
             done.record()
         self._pending = done
 
+    def inline(self):
+        """All-reduce on the CURRENT stream (no side stream, no events): the form a CUDA-graph capture of the
+        whole step records (vaegam.step.GraphStep)."""
+        if self.world == 1:
+            return
+        for b in (self.flat.grad32, self.flat.grad64):
+            dist.all_reduce(b, group=self.group)
+
     def finish(self):
         if self._pending is not None:
             torch.cuda.current_stream().wait_event(self._pending)
@@ -93,7 +101,10 @@ class GradientAllReduce:
 
 
 def train_step(model, reducer: GradientAllReduce, ids, covariates, x, noise=None):
-    """forward + backward + gradient all-reduce + fused Adam; returns the local loss tensor."""
+    """forward + backward + gradient all-reduce + fused Adam; returns the local loss tensor.  With
+    `model.use_cuda_graph` the whole sequence (all-reduce included) is one CUDA-graph launch per step."""
+    if getattr(model, "use_cuda_graph", False):
+        return model.train_batch(ids, covariates, x, _noise=noise, reducer=reducer)
     loss = model.forward(ids, covariates, x, 'train', train_mode=False, _noise=noise)
     model.optimizer.zero_grad()
     loss.backward()

@@ -293,6 +293,83 @@ def run_step(engine: StepEngine, x, covariates, noise=None, want_maps=False):
     return tot, holder[0]
 
 
+class GraphStep:
+    """One whole training step — vg_step_fwd, gradient zeroing, vg_step_bwd, fused Adam — captured once
+    per minibatch size as a CUDA graph and replayed.  The native calls are allocation-free,
+    sync-free and fork / join their helper streams with events only, so the ~130 launches of a step become
+    one `cudaGraphLaunch`; inputs are copied into static buffers and the noise is drawn eagerly into static
+    buffers with the same calls, in the same order, as `StepEngine.draw_noise` (same RNG stream as the eager
+    path and as the reference).  The graph holds raw pointers into the flat parameter / gradient / Adam
+    buffers: it is rebuilt when they are re-packed (FlatParams.version)."""
+
+    WARMUP = 2      # eager steps before capture: every lazily created stream / event / attribute exists by then
+    replayed_launches = 0   # kernels launched through graph replays (vg_launch_count only sees host-side launches)
+
+    def __init__(self, engine: StepEngine, optimizer: "FlatAdam", B: int, reducer=None):
+        dev = engine.device
+        self.engine, self.opt, self.B = engine, optimizer, B
+        self.reducer = reducer          # vaegam.dp.GradientAllReduce (or None): NCCL all-reduce inside the graph
+        self.failed = False
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.x = torch.zeros(B, V, **f32)
+        self.cov = torch.zeros(B, 8, **f32)
+        self.noise = {"eps_w": torch.zeros(B, 1, **f32), "eps_d": torch.zeros(B, NUM_LATENTS, **f32),
+                      "eps_g": torch.zeros(8, B, **f32)}
+        self.loss = torch.zeros(1, **f32)
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.calls = 0
+        self.version = engine.flat.version
+        self.sb: Optional[StepBuffers] = None
+
+    def _body(self):
+        eng = self.engine
+        sb = eng.forward(self.x, self.cov, self.noise, False)
+        eng.backward(sb)
+        if self.reducer is not None:
+            self.reducer.inline()       # sum over ranks on this stream; 1/world is folded into Adam's grad_scale
+        self.opt.launch()
+        self.loss.copy_(sb.scalars[:1])
+        self.sb = sb
+
+    def draw(self, generator=None):
+        n = self.noise
+        n["eps_w"].normal_(generator=generator)
+        n["eps_d"].normal_(generator=generator)
+        for i in range(8):
+            n["eps_g"][i].normal_(generator=generator)
+
+    def run(self, x, covariates, noise=None) -> torch.Tensor:
+        B = self.B
+        self.x.copy_(x.reshape(B, V), non_blocking=True)
+        self.cov.copy_(covariates, non_blocking=True)
+        if noise is None:
+            self.draw()
+        else:
+            for k in ("eps_w", "eps_d", "eps_g"):
+                self.noise[k].copy_(noise[k])
+        self.calls += 1
+        if self.graph is None and not self.failed and self.calls > self.WARMUP:
+            try:
+                g = torch.cuda.CUDAGraph()
+                n0 = native.launch_count()
+                with torch.cuda.graph(g):
+                    self._body()
+                self.launches_per_replay = native.launch_count() - n0
+                self.graph = g          # capture only records; the replay below is this call's step
+            except RuntimeError as e:   # e.g. a collective that cannot be captured: stay on the eager path
+                import warnings
+                warnings.warn(f"whole-step CUDA graph capture failed, running eagerly: {e}")
+                self.failed = True
+                torch.cuda.synchronize()
+        if self.graph is not None:
+            self.graph.replay()
+            GraphStep.replayed_launches += self.launches_per_replay
+        else:
+            self._body()
+        self.opt._host_steps += 1
+        return self.loss
+
+
 class FlatAdam(torch.optim.Adam):
     """torch.optim.Adam whose step() is ONE fused native kernel over the flat buffers
     (vg_adam_step).  State tensors (`exp_avg`, `exp_avg_sq`, `step`) are views of flat
@@ -355,7 +432,6 @@ class FlatAdam(torch.optim.Adam):
         if closure is not None:
             raise NotImplementedError("closure is not supported")
         f = self.flat
-        lib = native.load()
         # gradients normally ARE views of the flat gradient buffer (see _StepFn.backward);
         # anything else (user-modified .grad) is gathered into it first.
         for n, p in zip(f.names, f.params):
@@ -364,6 +440,15 @@ class FlatAdam(torch.optim.Adam):
                 gv.zero_()
             elif p.grad.data_ptr() != gv.data_ptr():
                 gv.copy_(p.grad)
+        self.launch()
+        self._host_steps += 1
+
+    @torch.no_grad()
+    def launch(self):
+        """The fused Adam kernel over the flat buffers as they are (graph-capturable: the step count lives on
+        the device)."""
+        f = self.flat
+        lib = native.load()
         g = self.param_groups[0]
         b1, b2 = g["betas"]
         native.check(lib.vg_adam_step(native.ptr(f.flat32), native.ptr(f.grad32), native.ptr(self.m32),
@@ -371,4 +456,3 @@ class FlatAdam(torch.optim.Adam):
                                       native.ptr(self.m64), native.ptr(self.v64), f.n64, float(g["lr"]), float(b1),
                                       float(b2), float(g["eps"]), float(self.grad_scale),
                                       native.ptr(self.step_count), native.stream_ptr()), "vg_adam_step")
-        self._host_steps += 1
