@@ -232,6 +232,23 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def finish(model, world):
+    """Multi-rank exit: drop the captured CUDA graphs (they hold NCCL work) before the ranks part, then leave
+    without running communicator destructors — tearing NCCL down under live graphs can block."""
+    if world <= 1:
+        return
+    import gc
+    import torch.distributed as dist
+    model._graph_steps.clear()
+    gc.collect()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -435,9 +452,7 @@ def main():
             kernels[f"fused_loss_b{bb}_alone"] = {k: dict(v, frac_hbm=round(v["gbs"] / hbm_peak, 4)) for k, v in fl.items()}
 
     if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
+        finish(model, world)
         return
     total_vols = args.steps * B * world
     value = total_vols / (ms * 1e-3)
@@ -468,9 +483,7 @@ def main():
         line["cpu_baseline"] = {"value": val, "unit": "volumes/s", "cores": threads, "kind": "port",
                                 "sample": f"3 steps of B={BATCH} after 1 warm-up ({sec:.2f} s/step)"}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    finish(model, world)
 
 
 if __name__ == "__main__":
