@@ -3,7 +3,8 @@
 Parity status: PINNED.  `tests/test_oracle_vs_golden.py` checks this port against
 golden vectors produced by the unmodified reference (`tests/golden/make_golden.py`,
 run in the build container where `/root/reference` is mounted), and
-`tests/test_oracle_vs_reference.py` re-checks it live whenever the reference is present.
+`tests/test_host_logic.py` re-checks initial values, utils and checkpoint interchange live against the
+reference whenever it is present.
 
 Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s CPU-baseline legs may
 import this module.  The product (`vae-gam_b200/`) never does.
