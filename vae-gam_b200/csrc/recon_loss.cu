@@ -501,7 +501,7 @@ extern "C" size_t vg_recon_workspace_bytes(int b, long long v) {
 extern "C" int vg_recon_loss_fwd(const float* maps, const float* g, const float* x, const float* eps,
                                  const float* glm, int b, long long v, float* logp, float* norms, float* cons,
                                  float* x_rec, void* workspace, size_t workspace_bytes, void* stream) {
-  VG_CHECK_ARG(maps && g && x && eps && glm && logp && norms && b > 0 && v > 0, "bad arguments");
+  VG_CHECK_ARG(maps && g && x && eps && glm && logp && norms && b > 0 && v >= 256, "bad arguments (v >= 256)");
   VG_CHECK_ARG(workspace && workspace_bytes >= vg_recon_workspace_bytes(b, v), "workspace too small");
   const int variant = g_variant;
   const Shape sh = shape_of(variant);
@@ -523,7 +523,7 @@ extern "C" int vg_recon_loss_bwd(const float* maps, const float* g, const float*
                                  const float* glm, const float* norms, int b, long long v, float lam,
                                  float* dpre, float* dg, float* deps, void* workspace, size_t workspace_bytes,
                                  void* stream) {
-  VG_CHECK_ARG(maps && g && x && eps && glm && norms && dpre && dg && deps && b > 0 && v > 0, "bad arguments");
+  VG_CHECK_ARG(maps && g && x && eps && glm && norms && dpre && dg && deps && b > 0 && v >= 256, "bad arguments (v >= 256)");
   VG_CHECK_ARG(workspace && workspace_bytes >= vg_recon_workspace_bytes(b, v), "workspace too small");
   const int variant = g_variant;
   const Shape sh = shape_of(variant);

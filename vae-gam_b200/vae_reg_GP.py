@@ -193,12 +193,24 @@ class VAE(nn.Module):
             self._pack()
         if self._engine is None:
             xu = [self.gp_params[k]['xu'] for k in _GP_COVS]
-            self._engine = StepEngine(self._flat, xu, self.glm_maps, self.inducing_pts, float(self.gp_kl_scale),
-                                      float(self.glm_reg_scale), self.neural_covariates, self.device)
-        self._engine.gp_kl_scale = float(self.gp_kl_scale)
-        self._engine.glm_reg_scale = float(self.glm_reg_scale)
+            self._engine = StepEngine(self._flat, xu, self.glm_maps, self.inducing_pts, self._as_float("gp_kl_scale"),
+                                      self._as_float("glm_reg_scale"), self.neural_covariates, self.device)
+        self._engine.gp_kl_scale = self._as_float("gp_kl_scale")
+        self._engine.glm_reg_scale = self._as_float("glm_reg_scale")
         self._engine.neural_covariates = bool(self.neural_covariates)
         return self._engine
+
+    def _as_float(self, attr):
+        """Host value of a loss weight.  `gp_kl_scale` is a device tensor like the reference's (vae_reg_GP.py:64)
+        and float() of it synchronises the device, so the conversion is cached per object identity: it is
+        redone only when the attribute is re-assigned (ctor, load_state, user code)."""
+        obj = getattr(self, attr)
+        cache = self.__dict__.setdefault("_float_cache", {})
+        hit = cache.get(attr)
+        if hit is None or hit[0] is not obj:
+            hit = (obj, float(obj))
+            cache[attr] = hit
+        return hit[1]
 
     # ------------------------------------------------------------------ public pieces
     def encode(self, x):

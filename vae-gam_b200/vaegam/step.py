@@ -320,6 +320,15 @@ class GraphStep:
         self.calls = 0
         self.version = engine.flat.version
         self.sb: Optional[StepBuffers] = None
+        self.baked = None
+
+    def signature(self):
+        """Every host-side scalar the captured kernels received by value: a change (learning-rate schedule,
+        loss weights, gradient scale) needs a new capture."""
+        g = self.opt.param_groups[0]
+        e = self.engine
+        return (e.gp_kl_scale, e.glm_reg_scale, e.neural_covariates, e.m, float(g["lr"]), tuple(g["betas"]),
+                float(g["eps"]), float(self.opt.grad_scale))
 
     def _body(self):
         eng = self.engine
@@ -348,6 +357,8 @@ class GraphStep:
             for k in ("eps_w", "eps_d", "eps_g"):
                 self.noise[k].copy_(noise[k])
         self.calls += 1
+        if self.graph is not None and self.baked != self.signature():
+            self.graph = None           # a by-value kernel argument changed: capture again
         if self.graph is None and not self.failed and self.calls > self.WARMUP:
             try:
                 g = torch.cuda.CUDAGraph()
@@ -356,6 +367,7 @@ class GraphStep:
                     self._body()
                 self.launches_per_replay = native.launch_count() - n0
                 self.graph = g          # capture only records; the replay below is this call's step
+                self.baked = self.signature()
             except RuntimeError as e:   # e.g. a collective that cannot be captured: stay on the eager path
                 import warnings
                 warnings.warn(f"whole-step CUDA graph capture failed, running eagerly: {e}")
