@@ -249,6 +249,10 @@ size_t vg_recon_workspace_bytes(int b, long long v);
 /* Launch shape of both passes (warps per CTA x CTAs per SM x cp.async ring stages):
  * 0: 4 x 5 x 2, 1: 4 x 3 x 3, 2: 4 x 4 x 2, 3 (default, also for any other value): 8 x 2 x 3. */
 void vg_recon_tune(int variant);
+/* Work decomposition a launch with this (b, v, variant) uses (host-side, no device needed):
+ * out[0..5] = row groups of 4, warp items (4 rows x 32 voxels) per row group, items, items per CTA, CTAs,
+ * warps per CTA. */
+int vg_recon_plan(int b, long long v, int variant, int* out);
 /* logp (b), norms (8,b) = ||g_i D_i[b] - G_i||_2.  Optional cons (8,b,V) and x_rec (b,V)
  * (R5 side outputs, NULL in training). */
 int vg_recon_loss_fwd(const float* maps, const float* g, const float* x, const float* eps,

@@ -72,3 +72,52 @@ int main(void){ printf("%zu %zu %zu %zu %zu %zu\n", sizeof(VgConvDesc), sizeof(V
     n = built_lib
     assert sizes == [ctypes.sizeof(n.VgConvDesc), ctypes.sizeof(n.VgGainParams), ctypes.sizeof(n.VgGainGrads),
                      ctypes.sizeof(n.VgStepConfig), ctypes.sizeof(n.VgStepIO), ctypes.sizeof(n.VgMlp)]
+
+
+def test_fused_loss_work_decomposition(built_lib):
+    """Host side of the fused reconstruction pass (csrc/recon_loss.cu: make_plan / recon_finalize): for every
+    launch shape the spans tile the (row group, column) items exactly once, a CTA's span crosses at most one
+    row-group boundary (it writes two partial segments), and the finalize ranges visit every span of a row group."""
+    lib = built_lib.load()
+    out = (ctypes.c_int * 6)()
+    V = 41 * 49 * 35
+    for variant in (0, 1, 2, 3):
+        for b in (1, 2, 3, 4, 5, 31, 32, 33, 128, 129, 512, 4096):
+            for v in (V, 256, 1000, 8 * 32 * 4 * 3 + 1):
+                assert lib.vg_recon_plan(b, v, variant, out) == 0
+                n_rg, n_c8, n_items, span, grid, warps = list(out)
+                assert n_rg == -(-b // 4) and n_c8 == -(-(-(-v // 4)) // 8) and n_items == n_rg * n_c8
+                assert span % warps == 0 and (span <= n_c8 or n_c8 < warps) and grid == -(-n_items // span)
+                assert (grid - 1) * span < n_items <= grid * span
+                if n_c8 < warps:
+                    continue
+                for c in range(0, grid, max(1, grid // 50)):          # a CTA's items span <= 2 row groups
+                    first, last = c * span, min((c + 1) * span, n_items) - 1
+                    assert last // n_c8 - first // n_c8 <= 1
+                for rg in range(0, n_rg, max(1, n_rg // 50)):         # finalize: CTAs meeting row group rg, segment 0 / 1
+                    c_lo, c_hi = (rg * n_c8) // span, (min((rg + 1) * n_c8, n_items) - 1) // span
+                    assert 0 <= c_lo <= c_hi < grid
+                    for c in (c_lo, c_hi):
+                        assert rg - (c * span) // n_c8 in (0, 1)
+                    # CTAs outside [c_lo, c_hi] hold no item of this row group
+                    if c_lo > 0:
+                        assert (c_lo * span - 1) // n_c8 < rg
+                    if c_hi + 1 < grid:
+                        assert ((c_hi + 1) * span) // n_c8 > rg
+    assert lib.vg_recon_plan(4, 100, 3, out) != 0                     # fewer than 256 voxels is rejected
+
+
+def test_fused_mlp_validation_without_gpu(built_lib):
+    """vg_mlp_fwd / vg_mlp_bwd reject malformed chains before any device work."""
+    n = built_lib
+    lib = n.load()
+    m = n.VgMlp()
+    assert lib.vg_mlp_fwd(ctypes.byref(m), None) == n.VG_EINVAL                       # empty
+    m.nlayers, m.nbufs, m.rows, m.rows_per_cta = 1, 2, 8, 3
+    assert lib.vg_mlp_fwd(ctypes.byref(m), None) == n.VG_EINVAL                       # rows_per_cta not in {1,2,4,8}
+    m.rows_per_cta = 4
+    m.buf[0].width, m.buf[1].width = 300, 10
+    m.buf[0].act = m.buf[1].act = 16                                                  # non-null placeholders, never dereferenced
+    m.layer[0].w, m.layer[0].n, m.layer[0].k, m.layer[0].in_, m.layer[0].out = 16, 10, 300, 0, 1
+    assert lib.vg_mlp_fwd(ctypes.byref(m), None) == n.VG_EINVAL                       # k > 224
+    assert b"224" in lib.vg_last_error()

@@ -49,10 +49,6 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -485,6 +481,16 @@ static int launch_bwd(const ReconArgs& a, int grid, const float* norms, float la
 using namespace vg;
 
 extern "C" void vg_recon_tune(int variant) { g_variant = (variant >= 0 && variant < NVARIANT) ? variant : 3; }
+
+// the work decomposition of a launch, for host-side inspection and tests: out = {row groups, warp items per
+// row group, items, items per CTA (span), CTAs, warps per CTA}
+extern "C" int vg_recon_plan(int b, long long v, int variant, int* out) {
+  VG_CHECK_ARG(out && b > 0 && v >= 256, "bad arguments (v >= 256)");
+  const Shape sh = shape_of((variant >= 0 && variant < NVARIANT) ? variant : 3);
+  const ReconPlan p = make_plan(b, v, sh);
+  out[0] = p.n_rg; out[1] = p.n_c8; out[2] = p.n_items; out[3] = p.span; out[4] = p.grid; out[5] = sh.warps;
+  return VG_OK;
+}
 
 extern "C" size_t vg_recon_workspace_bytes(int b, long long v) {
   if (b <= 0 || v <= 0) return 256;

@@ -189,11 +189,6 @@ __global__ void relu_mask_kernel(float* __restrict__ d, const float* __restrict_
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     if (!(a[i] > 0.f)) d[i] = 0.f;
 }
-__global__ void add3_kernel(float* __restrict__ dst, const float* __restrict__ a, const float* __restrict__ b,
-                            const float* __restrict__ c, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = a[i] + b[i] + c[i];
-}
 // out = [tot, neg_elbo, gp_kl, glm_reg, mean logp, mean klz, 0, 0]   (vae_reg_GP.py:400-410)
 __global__ void scalars_kernel(const float* __restrict__ logp, const float* __restrict__ klz,
                                const float* __restrict__ norms, const double* __restrict__ kl_terms, int B,

@@ -116,6 +116,7 @@ SIGNATURES = {
     "vg_gp_posterior": (_I, [_P, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P]),
     "vg_recon_workspace_bytes": (_SZ, [_I, _LL]),
     "vg_recon_tune": (None, [_I]),
+    "vg_recon_plan": (_I, [_I, _LL, _I, C.POINTER(C.c_int)]),
     "vg_recon_loss_fwd": (_I, [_P, _P, _P, _P, _P, _I, _LL, _P, _P, _P, _P, _P, _SZ, _P]),
     "vg_recon_loss_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _LL, _F, _P, _P, _P, _P, _SZ, _P]),
     "vg_adam_step": (_I, [_P, _P, _P, _P, _LL, _P, _P, _P, _P, _LL, _D, _D, _D, _D, _D, _P, _P]),
