@@ -462,8 +462,10 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if conv_mode == 1 else "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world,
                    "parallelism": f"dp{world} (one minibatch per rank, NCCL grad all-reduce)",
-                   "launch": "whole step (fwd + bwd + all-reduce + Adam) replayed as one CUDA graph; captured during "
-                             f"warm-up, {GRAPH_SETTLE} extra untimed replays before the timed region",
+                   "launch": (("whole step (fwd + bwd + all-reduce + Adam) replayed as one CUDA graph; captured during "
+                               f"warm-up, {GRAPH_SETTLE} extra untimed replays before the timed region")
+                              if any(gs.graph is not None for gs in model._graph_steps.values())
+                              else "eager launches (CUDA graph off, not captured, or running under a profiler)"),
                    "l2": "inputs cycle through a 386 MB HBM-resident cohort and the step's 1.8 GB activation "
                          "working set, both larger than the 126 MB L2",
                    "gain_stage": "fp64", "other_stages": "fp32",

@@ -15,6 +15,7 @@ if has bench; then
   echo "bench rc=$?"; head -c 300 gpurun_out/${tag}_bench.json; echo
 fi
 if has launches; then
+  export VAEGAM_CUDA_GRAPH=0      # ncu follows eager launches; the graph replays the same kernels
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv \
      --log-file gpurun_out/${tag}_launches.csv python tools/profile_step.py 3 > gpurun_out/${tag}_ncu1.log 2>&1
   echo "ncu launches rc=$?"

@@ -293,6 +293,13 @@ def run_step(engine: StepEngine, x, covariates, noise=None, want_maps=False):
     return tot, holder[0]
 
 
+def _under_profiler() -> bool:
+    """Nsight Compute / Systems inject themselves through the environment; kernel-replay profiling cannot
+    follow launches made during stream capture, so the whole-step graph is not used under them."""
+    import os
+    return any(("NSIGHT" in k) or ("INJECTION" in k) or ("COMPUTE_PROFILER" in k) for k in os.environ)
+
+
 class GraphStep:
     """One whole training step — vg_step_fwd, gradient zeroing, vg_step_bwd, fused Adam — captured once
     per minibatch size as a CUDA graph and replayed.  The native calls are allocation-free,
@@ -309,7 +316,7 @@ class GraphStep:
         dev = engine.device
         self.engine, self.opt, self.B = engine, optimizer, B
         self.reducer = reducer          # vaegam.dp.GradientAllReduce (or None): NCCL all-reduce inside the graph
-        self.failed = False
+        self.failed = _under_profiler() # True: stay on the eager path
         f32 = dict(dtype=torch.float32, device=dev)
         self.x = torch.zeros(B, V, **f32)
         self.cov = torch.zeros(B, 8, **f32)
