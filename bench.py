@@ -479,6 +479,10 @@ def main():
                 "input_pipeline": "loader thread gathers each batch into pinned host slots; H2D of step i+1 on a copy "
                                   "stream during step i"},
         "roofline": roof, "kernels": kernels,
+        # layer-by-layer fp32 activation traffic of a whole step, ~52.7 MB forward x 3 per volume
+        "step_hbm_ceiling": {"algorithmic_bytes_per_volume": 158.1e6, "peak_gbs": hbm_peak,
+                             "ceiling_volumes_per_s_per_gpu": round(hbm_peak * 1e9 / 158.1e6, 1),
+                             "frac": round(value / world / (hbm_peak * 1e9 / 158.1e6), 4)},
     }
     if not args.no_cpu_baseline and world == 1:
         val, threads, sec = cpu_baseline(steps=3, warmup=1)
