@@ -207,3 +207,29 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp_, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, os.path.join(dp_, f)
+
+
+def test_lsq_glm_maps_match_the_reference_formula(tmp_path):
+    """vaegam.glm_maps (streamed G'Y / G'G accumulation) against the reference's dense numpy evaluation
+    (get_beta_map_regularizer.py:94-107 + utils.scale_beta_maps), and the CSV it writes is what the VAE reads."""
+    from vaegam import glm_maps, synthetic as syn
+    rng = np.random.default_rng(0)
+    n, v = 60, 501
+    y = rng.random((n, v)).astype(np.float32)
+    gamma = rng.standard_normal((n, 7))
+    sex_map = rng.standard_normal(v)
+    pinv = np.linalg.inv(gamma.T @ gamma) @ gamma.T                       # the reference's pseudo_inv
+    want = np.concatenate([pinv @ y.astype(np.float64), sex_map[None]], 0)
+    want = want / want.max(axis=1, keepdims=True)
+    blocks = [(torch.from_numpy(y[i:i + 17]), torch.from_numpy(gamma[i:i + 17])) for i in range(0, n, 17)]
+    got = glm_maps.lsq_beta_maps(blocks, torch.from_numpy(sex_map))
+    assert got.shape == (v, 8) and np.allclose(got, want.T, rtol=1e-9, atol=1e-12)
+    path = glm_maps.write_glm_csv(str(tmp_path / "scld_GLM_beta_maps.csv"), got)
+    back = pd.read_csv(path).to_numpy()
+    assert back.shape == (v, 9) and np.allclose(back[:, 1:], got)          # index column + 8 maps
+    with pytest.raises(ValueError):
+        glm_maps.lsq_beta_maps([(torch.zeros(3, 5), torch.zeros(3, 6))])
+    # the synthetic cohort's maps go through the same code (BASELINE config 3)
+    coh = syn.make_cohort(2, "v1", seed=1, n_vols=40)
+    maps = syn.glm_maps_lsq(coh, block=17)
+    assert maps.shape == (41 * 49 * 35, 8) and np.isfinite(maps).all() and np.allclose(maps.max(0)[:7], 1.0)

@@ -189,22 +189,34 @@ def glm_maps_uniform(seed: int = 7) -> np.ndarray:
     return np.random.default_rng(seed).random((IMG_DIM, 8))
 
 
-def glm_maps_lsq(cohort: Cohort, max_rows: int = 392) -> np.ndarray:
+def glm_maps_lsq(cohort: Cohort, max_rows: int = 392, device="cpu", block: int = 98) -> np.ndarray:
     """Least-squares beta maps, max-scaled (get_beta_map_regularizer.py:94-103,
     utils.py:170-178): beta = (G'G)^-1 G' Y with G = [task, 6 motion]; sex map
-    = mean(sex==1) - mean(sex==0)."""
+    = mean(sex==1) - mean(sex==0).  Streams the volumes in blocks (vaegam.glm_maps)."""
+    from . import glm_maps
     n = min(len(cohort), max_rows)
-    rows = np.arange(n)
-    y = cohort.volumes(rows=rows).reshape(n, -1).double().numpy()
     cov = cohort.covariates()[:n].astype(np.float64)
-    g = cov[:, :7]
-    beta = np.linalg.inv(g.T @ g) @ g.T @ y                     # (7,V)
     sex = cov[:, 7] > 0.5
+    sums = {True: None, False: None}
+
+    def blocks():
+        for r0 in range(0, n, block):
+            rows = np.arange(r0, min(n, r0 + block))
+            y = cohort.volumes(device=device, rows=rows).reshape(len(rows), -1)
+            for flag in (True, False):
+                sel = torch.from_numpy(sex[rows] == flag).to(y.device)
+                if bool(sel.any()):
+                    part = y[sel].double().sum(0)
+                    sums[flag] = part if sums[flag] is None else sums[flag] + part
+            yield y, torch.from_numpy(cov[rows, :7])
+
+    beta_only = glm_maps.lsq_beta_maps(blocks(), None, scale=False)      # (V, 8), sex column zero
     if sex.any() and (~sex).any():
-        smap = y[sex].mean(0) - y[~sex].mean(0)
+        smap = (sums[True] / int(sex.sum()) - sums[False] / int((~sex).sum())).cpu().numpy()
     else:
         smap = np.zeros(IMG_DIM)
-    maps = np.concatenate([beta, smap[None]], 0)
+    maps = beta_only.T.copy()
+    maps[7] = smap
     for i in range(maps.shape[0]):
         mx = maps[i].max()
         if mx != 0:
