@@ -294,10 +294,24 @@ def run_step(engine: StepEngine, x, covariates, noise=None, want_maps=False):
 
 
 def _under_profiler() -> bool:
-    """Nsight Compute / Systems inject themselves through the environment; kernel-replay profiling cannot
-    follow launches made during stream capture, so the whole-step graph is not used under them."""
+    """Nsight Compute / Systems inject a library into the process; kernel-replay profiling cannot follow
+    launches made during stream capture, so the whole-step graph is not used under them.  (Image-level
+    variables such as NV_CUDA_NSIGHT_COMPUTE_VERSION say nothing: only injection hooks count.)"""
     import os
-    return any(("NSIGHT" in k) or ("INJECTION" in k) or ("COMPUTE_PROFILER" in k) for k in os.environ)
+    if any(k in os.environ for k in ("CUDA_INJECTION64_PATH", "CUDA_INJECTION32_PATH", "NV_NSIGHT_INJECTION_PORT_BASE",
+                                     "NV_NSIGHT_INJECTION_TRANSPORT_TYPE", "NV_COMPUTE_PROFILER_PERFWORKS_DIR", "NVTX_INJECTION64_PATH",
+                                     "NSYS_PROFILING_SESSION_ID")):
+        return True
+    try:
+        with open("/proc/self/maps") as f:
+            for line in f:
+                low = line.lower()
+                if "injection" in low and (".so" in low) and ("nsight" in low or "cuda-injection" in low or "nsys" in low
+                                                              or "target" in low):
+                    return True
+    except OSError:
+        pass
+    return False
 
 
 class GraphStep:
