@@ -400,7 +400,7 @@ class GraphStep:
         else:
             self._body()
         self.opt._host_steps += 1
-        return self.loss
+        return self.loss.clone()        # the static buffer is overwritten by the next step
 
 
 class FlatAdam(torch.optim.Adam):
