@@ -69,24 +69,42 @@ typedef struct VgConvDesc {
   int32_t out[3];          /* output grid (D,H,W) — must satisfy the PyTorch size formula */
   int32_t n;               /* images */
   int32_t group_size;      /* images per BatchNorm statistics group (n % group_size == 0) */
+  int32_t arith;           /* VG_ARITH_*: arithmetic of THIS call (0 = the process default below) */
   int64_t x_img_stride;    /* floats between consecutive images of x / dx; 0 = dense (D*H*W*cin) */
   int64_t y_img_stride;    /* floats between consecutive images of y / dy; 0 = dense (D*H*W*cout) */
 } VgConvDesc;
 
-/* Arithmetic of the convolution forward / data-gradient kernels:
- *   1 (default): bf16 operands on the tcgen05 tensor cores with fp32 accumulation in TMEM, for
- *      every geometry the implicit-GEMM kernel covers (unit input stride, 8 or 16 input
- *      channels); the remaining layers use the fp32 kernel;
- *   0: fp32 CUDA-core kernels everywhere ("check mode", 1e-5 parity with PyTorch fp32).
- * Initial value from the environment variable VAEGAM_CONV_MODE ("0"/"fp32" or "1"). */
-int vg_set_conv_mode(int mode);
+/* Arithmetic of the convolution kernels.  Every call carries its own choice — VgConvDesc.arith for
+ * the per-layer entry points, VgStepConfig.arith for the whole-step ones — so callers that state it
+ * are independent of any process state:
+ *   VG_ARITH_FP32 : fp32 CUDA-core kernels everywhere ("check mode", 1e-5 parity with PyTorch fp32);
+ *   VG_ARITH_BF16 : bf16 operands on the tcgen05 tensor cores with fp32 accumulation in TMEM for
+ *      every geometry the implicit-GEMM kernels cover, mma.sync bf16 weight gradients; the
+ *      remaining geometries use the fp32 kernels;
+ *   VG_ARITH_MIXED (whole-step entry points; per-layer calls treat it as BF16): BF16 for the decoder
+ *      and for every backward pass, FP32 for the five forward convolutions of the ENCODER.  The
+ *      encoder's forward rounding is what dominates the gradient deviation of the BF16 mode
+ *      (tools/precision_study.py: 25 % -> 2 % on the encoder's weight gradients at B = 32) while
+ *      the encoder is 9 % of the convolution work;
+ *   VG_ARITH_DEFAULT (0, what a zero-initialised struct says): the process default, which is
+ *      read once from the environment variable VAEGAM_CONV_MODE ("0"/"fp32", "1"/"bf16",
+ *      "2"/"mixed"; unset = mixed) and can be changed with vg_set_conv_mode(0 | 1 | 2).
+ * vg_set_conv_mode / vg_set_conv_tuning / vg_recon_tune only move such process DEFAULTS and
+ * benchmarking knobs; no entry point keeps per-call state in the library. */
+#define VG_ARITH_DEFAULT 0
+#define VG_ARITH_FP32 1
+#define VG_ARITH_BF16 2
+#define VG_ARITH_MIXED 3
+int vg_set_conv_mode(int mode);     /* 0 fp32, 1 bf16, 2 mixed */
 int vg_get_conv_mode(void);
-/* Dispatch tuning.  "t2_min_voxels": output voxels per launch from which the persistent plane-folded
- * tcgen05 kernel is preferred over the per-tile kernels (default 400000; env VAEGAM_T2_MIN_VOXELS). */
+/* Dispatch tuning (benchmarking knob, process default).  "t2_min_voxels": output voxels per launch from
+ * which the persistent plane-folded tcgen05 kernel is preferred over the per-tile kernels (default
+ * 400000; env VAEGAM_T2_MIN_VOXELS). */
 int vg_set_conv_tuning(const char* key, long long value);
 
-/* Host-side description of the launches a layer maps to in the current mode (kind 0: forward,
- * 1: data gradient), one text line per launch; returns the number of launches. */
+/* Host-side description of the launches a layer maps to under d->arith (kind 0: forward,
+ * 1: data gradient), one text line per launch ("tc2 ..." plane-folded tcgen05, "tc1 ..." per-tile
+ * tcgen05, "fp32 ..." CUDA cores); returns the number of launches. */
 int vg_conv_describe(const VgConvDesc* d, int kind, char* buf, size_t cap);
 
 /* y = act(conv(x * in_scale[g,ci] + in_shift[g,ci]) + bias); zero padding is applied
@@ -271,10 +289,15 @@ int vg_recon_loss_bwd(const float* maps, const float* g, const float* x, const f
  * Fused Adam over a flat parameter buffer (torch.optim.Adam defaults, vae_reg_GP.py:179,429).
  * fp32 segment [0,n32) and fp64 segment (epsilon).  step_count: device int64 incremented here.
  * grad_scale multiplies the gradient (1/world_size after the NCCL sum).
+ * skip_flags (n_flags device ints, may be NULL): when any of them is non-zero the whole update
+ * (parameters, moments and step count) is skipped on the device.  The step passes VgStepIO.status,
+ * so a minibatch that met a non-positive-definite covariance leaves the parameters untouched, as
+ * the reference does by raising inside forward (vae_reg_GP.py:368, gp.py:51) before backward()/step().
  * ---------------------------------------------------------------------------------- */
 int vg_adam_step(float* p32, const float* g32, float* m32, float* v32, long long n32, double* p64,
                  const double* g64, double* m64, double* v64, long long n64, double lr, double beta1,
-                 double beta2, double eps, double grad_scale, long long* step_count, void* stream);
+                 double beta2, double eps, double grad_scale, long long* step_count,
+                 const int32_t* skip_flags, int n_flags, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Whole training step (vae_reg_GP.py:307-413 forward, :427-428 backward) chained on one
@@ -288,6 +311,8 @@ typedef struct VgStepConfig {
   int32_t want_maps;         /* also emit cons / x_rec (return_latent_rec) */
   float gp_kl_scale;
   float glm_reg_scale;
+  int32_t arith;             /* VG_ARITH_* for every convolution of this call (0 = process default) */
+  int32_t reserved[3];       /* zero */
 } VgStepConfig;
 
 size_t vg_step_workspace_bytes(const VgStepConfig* cfg);
@@ -322,16 +347,30 @@ typedef struct VgStepIO {
 int vg_step_fwd(const VgStepConfig* cfg, const VgStepIO* io, void* workspace,
                 size_t workspace_bytes, void* stream);
 /* Gradients of out_scalars[0] are ACCUMULATED into io->grads (caller zeroes).  Must follow
- * vg_step_fwd with the same cfg/io/workspace.  If stream2 != NULL the gain backward runs on
- * it concurrently (fork/join through events; still capturable). */
+ * vg_step_fwd with the same cfg/io/workspace.  Weight gradients and the gain backward run on a
+ * helper stream (fork / join through events; still capturable). */
 int vg_step_bwd(const VgStepConfig* cfg, const VgStepIO* io, void* workspace,
                 size_t workspace_bytes, void* stream);
+/* The same backward in three phases, for data-parallel training that overlaps the gradient
+ * all-reduce with the rest of the backward (the reference has no collective; its step is
+ * vae_reg_GP.py:427-429).  Phases must be called in order 0, 1, 2 on `stream`:
+ *   0: objective + the whole decoder      -> grads of epsilon, fc5..fc8, convt1..5, bnt1/3/5 complete
+ *   1: latent + encoder fully connected   -> grads of fc1..fc43 complete
+ *   2: encoder convolutions + gain stage  -> grads of conv1..5, bn1/3/5 and all gain parameters complete
+ * If ready_stream != NULL it is made to wait (events only) for every kernel that writes this
+ * phase's gradients, helper-stream kernels included, WITHOUT joining them into `stream`: the
+ * caller enqueues the phase's all-reduce on ready_stream and joins ready_stream into `stream`
+ * before the optimizer step.  vg_step_bwd == phases 0, 1, 2 with ready_stream NULL. */
+#define VG_BWD_PHASES 3
+int vg_step_bwd_phase(const VgStepConfig* cfg, const VgStepIO* io, void* workspace,
+                      size_t workspace_bytes, int phase, void* ready_stream, void* stream);
 /* Encoder only (VAE.encode, vae_reg_GP.py:236-252): heads (3,b,32) = [mu | u | log d]. */
 int vg_encode_fwd(const VgStepConfig* cfg, const VgStepIO* io, float* heads, void* workspace,
                   size_t workspace_bytes, void* stream);
-/* Decoder only (VAE.decode, :254-264) for n rows of zcat (n,41) treated as ONE BatchNorm batch. */
+/* Decoder only (VAE.decode, :254-264) for n rows of zcat (n,41) treated as ONE BatchNorm batch;
+ * arith: VG_ARITH_* (MIXED = BF16 here: the decoder is never the fp32 part). */
 size_t vg_decode_workspace_bytes(int n);
-int vg_decode_fwd(const VgStepIO* io, const float* zcat, int n, float* out, void* workspace,
+int vg_decode_fwd(const VgStepIO* io, const float* zcat, int n, int arith, float* out, void* workspace,
                   size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus

@@ -233,3 +233,137 @@ def test_lsq_glm_maps_match_the_reference_formula(tmp_path):
     coh = syn.make_cohort(2, "v1", seed=1, n_vols=40)
     maps = syn.glm_maps_lsq(coh, block=17)
     assert maps.shape == (41 * 49 * 35, 8) and np.isfinite(maps).all() and np.allclose(maps.max(0)[:7], 1.0)
+
+
+# ----------------------------------------------------------------------------- round 2 additions
+def test_load_state_with_other_inducing_points_repacks(experiment):
+    """a checkpoint trained with another num_inducing_pts replaces Parameter objects; the flat
+    buffers, the optimizer and the engine must be rebuilt around the NEW objects (reference load_state:
+    vae_reg_GP.py:473-539)."""
+    d = experiment[0]
+    small = make_model(experiment, seed=5, num_inducing_pts=4)
+    small.save_state("ck_m4.tar")
+    big = make_model(experiment, seed=6, num_inducing_pts=6)
+    big.load_state(os.path.join(d, "ck_m4.tar"))
+    assert big.inducing_pts == 4 and tuple(big.qu_m_x.shape) == (1, 4) and tuple(big.qu_S_x.shape) == (4, 4)
+    named = dict(big.named_parameters())
+    assert big._flat.is_packed()
+    for n, p in zip(big._flat.names, big._flat.params):
+        assert p is named[n], n                                   # the flat table lists the live objects
+    owned = {id(p) for g in big.optimizer.param_groups for p in g["params"]}
+    assert all(id(p) in owned for p in named.values())            # and the optimizer owns all of them
+    assert big._flat.n32 == small._flat.n32 and big.optimizer.m32.numel() == big._flat.n32
+    for (n, a), (_, b) in zip(small.named_parameters(), big.named_parameters()):
+        assert torch.equal(a.detach(), b.detach()), n
+    assert big.gp_params['x']['qu_m'] is big.qu_m_x
+
+
+def test_numpy_aliases_and_nibabel_are_not_shadowed():
+    """`np.float` exists after importing the package (reference build_model_recons.py:74,85) and `nibabel`
+    resolves to a real installation when there is one, else to the bundled codec — never to a directory shim."""
+    import importlib.util
+    import sys
+    import vaegam  # noqa: F401
+    assert np.float is float and np.int is int
+    from vaegam.nib_compat import nib
+    spec_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "vae-gam_b200", "nibabel")
+    assert not os.path.exists(spec_dir)
+    assert hasattr(nib, "load") and hasattr(nib, "Nifti1Image") and hasattr(nib, "save")
+    assert sys.modules["nibabel"] is nib
+
+
+def test_nifti_qform_only_header(tmp_path):
+    """Files that carry only a qform (sform_code == 0) get their affine from the quaternion (NIfTI-1 method 2)."""
+    import struct
+    from vaegam import nifti
+    a = np.arange(2 * 3 * 4, dtype=np.float32).reshape(2, 3, 4)
+    p = str(tmp_path / "q.nii")
+    nifti.save(nifti.Nifti1Image(a, np.eye(4)), p)
+    raw = bytearray(open(p, "rb").read())
+    # 90 degree rotation about z: quaternion (a, b, c, d) = (cos45, 0, 0, sin45); pixdim (2, 3, 4); qfac -1
+    struct.pack_into("<8f", raw, 76, -1.0, 2.0, 3.0, 4.0, 1.0, 1.0, 1.0, 1.0)
+    struct.pack_into("<hh", raw, 252, 1, 0)                       # qform_code = 1, sform_code = 0
+    struct.pack_into("<6f", raw, 256, 0.0, 0.0, float(np.sqrt(0.5)), 10.0, 20.0, 30.0)
+    open(p, "wb").write(bytes(raw))
+    img = nifti.load(p)
+    want = np.array([[0, -3, 0, 10], [2, 0, 0, 20], [0, 0, -4, 30], [0, 0, 0, 1]], dtype=np.float64)
+    assert np.allclose(img.affine, want, atol=1e-6)
+    assert np.array_equal(np.asarray(img.dataobj), a)
+
+
+def test_launcher_resolves_the_drop_in_modules(tmp_path, capsys):
+    """run_reference.py executes an unmodified reference script with the drop-in directory FIRST on sys.path
+    (python <script> would put the script's own directory first and import the reference's PyTorch modules)."""
+    import shutil
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "vae-gam_b200")
+    src = "/root/reference" if HAVE_REF else pkg
+    work = tmp_path / "VAE-GAM"
+    work.mkdir()
+    for f in ("multsubj_reg_run_GP.py", "build_model_recons.py", "vae_reg_GP.py", "utils.py"):
+        shutil.copy(os.path.join(src, f), str(work / f))          # decoys next to the script, as in a checkout
+    probe = ("import sys, runpy\n"
+             "sys.argv = ['x', %r, '--help']\n"
+             "try:\n    runpy.run_path(%r, run_name='__main__')\nexcept SystemExit as e:\n    assert e.code in (0, None), e.code\n"
+             "import vae_reg_GP, DataClass_GP, build_model_recons, utils\n"
+             "print('RESOLVED', vae_reg_GP.__file__, DataClass_GP.__file__, build_model_recons.__file__, utils.__file__)\n"
+             % (str(work / "multsubj_reg_run_GP.py"), os.path.join(pkg, "run_reference.py")))
+    env = dict(os.environ, PYTHONPATH="")
+    out = subprocess.run([sys.executable, "-c", probe], capture_output=True, text=True, env=env, cwd=str(tmp_path))
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("RESOLVED")][0]
+    for path in line.split()[1:]:
+        assert os.path.dirname(os.path.abspath(path)) == pkg, line
+    assert "--num_inducing_pts" in out.stdout                      # the reference's own argparse help was printed
+
+
+def test_resident_loader_matches_dataloader_batches(experiment):
+    """GPU-resident loader (here on the CPU device): same contract and, for a given torch seed, the same
+    shuffled batches as torch's DataLoader — so switching it on does not change a run."""
+    import DataClass_GP as data
+    d, tr, te, glm, coh = experiment
+    torch.manual_seed(21)
+    std = data.setup_data_loaders(batch_size=40, train_csv=tr, test_csv=te, resident=False)
+    a = [b for b in std['Shuffled_train']]
+    torch.manual_seed(21)
+    res = data.setup_data_loaders(batch_size=40, train_csv=tr, test_csv=te, resident=True, device="cpu")
+    assert isinstance(res['Shuffled_train'], data.ResidentLoader)
+    b = [x for x in res['Shuffled_train']]
+    assert len(a) == len(b) == len(res['Shuffled_train']) == 5 and len(res['test'].dataset) == 98
+    assert res['UnShuffled_train'].batch_size == 40
+    for x, y in zip(a, b):
+        for k in ('volume', 'covariates', 'subjid', 'vol_num'):
+            assert x[k].dtype == y[k].dtype and x[k].shape == y[k].shape and torch.equal(x[k], y[k]), k
+    assert b[-1]['volume'].shape[0] == 2 * 98 - 4 * 40            # ragged last batch
+    # rank shards: disjoint, equal, and their union is one epoch's permutation
+    r0 = data.setup_data_loaders(batch_size=49, train_csv=tr, test_csv=te, resident=True, device="cpu", rank=0, world=2)
+    r1 = data.setup_data_loaders(batch_size=49, train_csv=tr, test_csv=te, resident=True, device="cpu", rank=1, world=2)
+    torch.manual_seed(3)                                          # every rank seeds the same way (as torchrun ranks do)
+    v0 = torch.cat([x['vol_num'] + 1000 * x['subjid'] for x in r0['Shuffled_train']])
+    torch.manual_seed(3)
+    v1 = torch.cat([x['vol_num'] + 1000 * x['subjid'] for x in r1['Shuffled_train']])
+    assert v0.numel() == v1.numel() == 98 and len(set(v0.tolist()) & set(v1.tolist())) == 0
+
+
+def test_gradient_buckets_partition_the_flat_buffers(experiment):
+    """The three all-reduce buckets (vaegam.dp) are contiguous views that tile the flat gradient buffers exactly,
+    in backward-completion order: decoder tail, encoder FC middle, gains + encoder convolutions head."""
+    from vaegam import dp
+    m = make_model(experiment)
+    red = dp.GradientAllReduce(m._flat, m.optimizer, overlap=False)
+    b = red.buckets()
+    f = m._flat
+    assert len(b) == 3 and b[0][0] is f.grad64
+    tail, mid, head = b[0][1], b[1][0], b[2][0]
+    assert head.data_ptr() == f.grad32.data_ptr()
+    assert mid.data_ptr() == head.data_ptr() + 4 * head.numel()
+    assert tail.data_ptr() == mid.data_ptr() + 4 * mid.numel()
+    assert head.numel() + mid.numel() + tail.numel() == f.n32
+    where = lambda n: f.slices[n][1]
+    assert where("fc1.weight") == head.numel() and where("fc5.weight") == head.numel() + mid.numel()
+    for n in ("conv1.weight", "bn5.bias", "sa_task", "qu_S_zrot"):
+        assert where(n) < head.numel()
+    for n in ("fc8.weight", "convt5.bias", "bnt1.weight"):
+        assert where(n) >= head.numel() + mid.numel()

@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pandas as pd
 
-import nibabel as nib
+from vaegam.nib_compat import nib
 
 _ALL_MAPS = ['base', 'task', 'full_rec', 'x_mot', 'y_mot', 'z_mot', 'pitch_mot', 'roll_mot', 'yaw_mot', 'sex']
 

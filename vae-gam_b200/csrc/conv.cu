@@ -337,14 +337,26 @@ static int launch_gather_t(const Geom& g, const GatherArgs& a, cudaStream_t st) 
   return VG_OK;
 }
 
+// Process default of the arithmetic mode (0 fp32 CUDA cores, 1 bf16 tcgen05, 2 mixed: bf16 tcgen05 with the
+// encoder's forward convolutions in fp32).  Only consulted when a descriptor / step config says VG_ARITH_DEFAULT.
 static int g_conv_mode = -1;
 int conv_mode() {
   if (g_conv_mode < 0) {
     const char* e = getenv("VAEGAM_CONV_MODE");
-    g_conv_mode = (e && (e[0] == '0' || e[0] == 'f')) ? 0 : 1;     // "0" / "fp32" -> CUDA cores
+    if (e && (e[0] == '0' || e[0] == 'f')) g_conv_mode = 0;        // "0" / "fp32" -> CUDA cores
+    else if (e && (e[0] == '1' || e[0] == 'b')) g_conv_mode = 1;   // "1" / "bf16" -> tensor cores everywhere
+    else g_conv_mode = 2;
   }
   return g_conv_mode;
 }
+// VG_ARITH_* of a descriptor / step config -> 0 (fp32), 1 (bf16 tensor cores) or 2 (mixed, step level only)
+int resolve_arith(int arith) {
+  if (arith == VG_ARITH_FP32) return 0;
+  if (arith == VG_ARITH_BF16) return 1;
+  if (arith == VG_ARITH_MIXED) return 2;
+  return conv_mode();
+}
+static inline bool desc_tc(const VgConvDesc* d) { return resolve_arith(d->arith) != 0; }
 
 // The plane-folded kernel is persistent with a per-CTA set-up (weight blocks, TMEM): worth it from a few
 // hundred thousand output voxels per launch
@@ -352,13 +364,13 @@ static long long g_t2_min_voxels = -1;
 static bool tc2_worthwhile(const Geom* gs, int ng) {
   long long vox = 0;
   for (int i = 0; i < ng; ++i) vox += (long long)gs[i].N * gs[i].qD * gs[i].qH * gs[i].qW;
-  if (g_t2_min_voxels < 0) { const char* e = getenv("VAEGAM_T2_MIN_VOXELS"); g_t2_min_voxels = e ? atoll(e) : 400000; }
+  if (g_t2_min_voxels < 0) { const char* e = getenv("VAEGAM_T2_MIN_VOXELS"); g_t2_min_voxels = e ? atoll(e) : 400000; }   // process default
   return vox >= g_t2_min_voxels;
 }
 
-static int launch_gather(int cin, int cout, const Geom& g, const GatherArgs& a, cudaStream_t st) {
-  if (conv_mode() == 1 && tc2_worthwhile(&g, 1) && tc2_supported(cin, cout, &g, 1)) return launch_tc2_gather(cin, cout, &g, 1, a, st);
-  if (conv_mode() == 1 && tc_supported(cin, cout, g)) return launch_tc_gather(cin, cout, g, a, st);
+static int launch_gather(bool tc, int cin, int cout, const Geom& g, const GatherArgs& a, cudaStream_t st) {
+  if (tc && tc2_worthwhile(&g, 1) && tc2_supported(cin, cout, &g, 1)) return launch_tc2_gather(cin, cout, &g, 1, a, st);
+  if (tc && tc_supported(cin, cout, g)) return launch_tc_gather(cin, cout, g, a, st);
   if (cin == 1 && cout == 8) return launch_gather_t<1, 8, 4>(g, a, st);
   if (cin == 8 && cout == 1) return launch_gather_t<8, 1, 4>(g, a, st);
   if (cin == 8 && cout == 8) return launch_gather_t<8, 8, 4>(g, a, st);
@@ -382,9 +394,16 @@ struct PhaseStreams {
   cudaEvent_t fork, join[kPhaseStreams];
   bool ok = false;
 };
+// One set per host thread and device: entry points called from different threads or for different devices
+// never share a stream or an event.
 static PhaseStreams& phase_streams() {
-  static PhaseStreams ps;
-  static bool tried = false;
+  constexpr int kMaxDev = 16;
+  static thread_local PhaseStreams per_dev[kMaxDev];
+  static thread_local bool tried_dev[kMaxDev] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) { (void)cudaGetLastError(); dev = 0; }
+  PhaseStreams& ps = per_dev[dev];
+  bool& tried = tried_dev[dev];
   if (!tried) {
     tried = true;
     const char* e = getenv("VAEGAM_PHASE_STREAMS");
@@ -400,20 +419,20 @@ static PhaseStreams& phase_streams() {
 }
 
 // every gather of one layer pass: one fused multi-phase launch when the plane-folded kernel covers it
-static int launch_all(int cin, int cout, const Geom* gs, int ng, const GatherArgs& a, cudaStream_t st) {
-  if (ng > 1 && conv_mode() == 1 && tc2_worthwhile(gs, ng) && tc2_supported(cin, cout, gs, ng))
+static int launch_all(bool tc, int cin, int cout, const Geom* gs, int ng, const GatherArgs& a, cudaStream_t st) {
+  if (ng > 1 && tc && tc2_worthwhile(gs, ng) && tc2_supported(cin, cout, gs, ng))
     return launch_tc2_gather(cin, cout, gs, ng, a, st);
   PhaseStreams& ps = phase_streams();
   if (ng < 2 || ng > kPhaseStreams + 1 || !ps.ok) {
-    for (int i = 0; i < ng; ++i) VG_TRY(launch_gather(cin, cout, gs[i], a, st));
+    for (int i = 0; i < ng; ++i) VG_TRY(launch_gather(tc, cin, cout, gs[i], a, st));
     return VG_OK;
   }
   VG_CUDA(cudaEventRecord(ps.fork, st));
-  int rc = launch_gather(cin, cout, gs[0], a, st);
+  int rc = launch_gather(tc, cin, cout, gs[0], a, st);
   for (int i = 1; i < ng; ++i) {
     cudaStream_t hs = ps.s[i - 1];
     VG_CUDA(cudaStreamWaitEvent(hs, ps.fork, 0));
-    if (rc == VG_OK) rc = launch_gather(cin, cout, gs[i], a, hs);
+    if (rc == VG_OK) rc = launch_gather(tc, cin, cout, gs[i], a, hs);
     VG_CUDA(cudaEventRecord(ps.join[i - 1], hs));          // always joined, also after a failed launch
     VG_CUDA(cudaStreamWaitEvent(st, ps.join[i - 1], 0));
   }
@@ -425,7 +444,7 @@ static int launch_all(int cin, int cout, const Geom* gs, int ng, const GatherArg
 using namespace vg;
 
 extern "C" int vg_set_conv_mode(int mode) {
-  VG_CHECK_ARG(mode == 0 || mode == 1, "mode must be 0 (fp32 CUDA cores) or 1 (bf16 tcgen05)");
+  VG_CHECK_ARG(mode >= 0 && mode <= 2, "mode must be 0 (fp32 CUDA cores), 1 (bf16 tcgen05) or 2 (mixed)");
   g_conv_mode = mode;
   return VG_OK;
 }
@@ -445,18 +464,19 @@ extern "C" int vg_conv_describe(const VgConvDesc* d, int kind, char* buf, size_t
   Geom gs[8];
   const int ng = build_geoms(d, kind, gs);
   const int cin = kind == 0 ? d->cin : d->cout, cout = kind == 0 ? d->cout : d->cin;
+  const bool use_tc = desc_tc(d);
   size_t off = 0;
   buf[0] = 0;
-  if (ng > 1 && conv_mode() == 1 && tc2_worthwhile(gs, ng) && tc2_supported(cin, cout, gs, ng)) {
+  if (ng > 1 && use_tc && tc2_worthwhile(gs, ng) && tc2_supported(cin, cout, gs, ng)) {
     const int n = tc2_describe(cin, cout, gs, ng, buf, cap);
     if (n > 0 && (size_t)n + 2 < cap) { buf[n] = '\n'; buf[n + 1] = 0; }
     return 1;
   }
   for (int i = 0; i < ng && off + 8 < cap; ++i) {
     int n = 0;
-    if (conv_mode() == 1 && tc2_worthwhile(&gs[i], 1)) n = tc2_describe(cin, cout, &gs[i], 1, buf + off, cap - off);
+    if (use_tc && tc2_worthwhile(&gs[i], 1)) n = tc2_describe(cin, cout, &gs[i], 1, buf + off, cap - off);
     if (n <= 0) {
-      const bool tc = conv_mode() == 1 && tc_supported(cin, cout, gs[i]);
+      const bool tc = use_tc && tc_supported(cin, cout, gs[i]);
       n = snprintf(buf + off, cap - off, "%s cin=%d cout=%d q=(%d,%d,%d) taps=%d", tc ? "tc1" : "fp32", cin, cout,
                    gs[i].qD, gs[i].qH, gs[i].qW, gs[i].ntaps);
     }
@@ -476,7 +496,7 @@ extern "C" int vg_conv_fwd(const VgConvDesc* d, const float* x, const float* w, 
   GatherArgs a{};
   a.in = x; a.w = w; a.bias = bias; a.in_scale = in_scale; a.in_shift = in_shift;
   a.out = y; a.act = act; a.stats = out_stats;
-  return launch_all(d->cin, d->cout, gs, ng, a, as_stream(stream));
+  return launch_all(desc_tc(d), d->cin, d->cout, gs, ng, a, as_stream(stream));
 }
 
 extern "C" int vg_conv_dgrad(const VgConvDesc* d, const float* dy, const float* w, float* dx,
@@ -493,7 +513,7 @@ extern "C" int vg_conv_dgrad(const VgConvDesc* d, const float* dy, const float* 
   if (mask_act) { a.aux = mask_act; a.aux_mode = 1; }
   if (bn_x) { a.aux = bn_x; a.aux_mode = 2; a.aux_istd = bn_istd; a.aux_mistd = bn_mistd; a.aux_sums = bn_sums; }
   // the gather reads dy (cout channels) and produces cin channels
-  return launch_all(d->cout, d->cin, gs, ng, a, as_stream(stream));
+  return launch_all(desc_tc(d), d->cout, d->cin, gs, ng, a, as_stream(stream));
 }
 
 namespace vg {
@@ -508,7 +528,7 @@ extern "C" int vg_conv_wgrad(const VgConvDesc* d, const float* x, const float* d
                              const float* in_shift, float* dw, float* dbias, void* stream) {
   VG_TRY(check_desc(d));
   VG_CHECK_ARG(x && dy && dw, "null tensor");
-  if (conv_mode() == 1) {
+  if (desc_tc(d)) {
     const int rc = wgrad_mma(d, x, dy, in_scale, in_shift, dw, dbias, as_stream(stream));   // bias gradient fused
     if (rc <= 0) return rc;
   }

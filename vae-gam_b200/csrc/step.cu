@@ -6,6 +6,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "conv_geom.cuh"
 #include "gp_core.h"
 
 namespace vg {
@@ -43,8 +44,10 @@ static const LayerShape kConvT[5] = {
     {1, 8, 1, {3, 3, 3}, 1, {0, 0, 0}, {0, 0, 0}, {39, 47, 33}, {41, 49, 35}},
 };
 
-static VgConvDesc make_desc(const LayerShape& s, int n, int group, long long xs = 0, long long ys = 0) {
+// arith: VG_ARITH_FP32 / VG_ARITH_BF16 of this layer's calls (already resolved from the step config)
+static VgConvDesc make_desc(const LayerShape& s, int n, int group, int arith, long long xs = 0, long long ys = 0) {
   VgConvDesc d{};
+  d.arith = arith;
   d.transposed = s.transposed; d.cin = s.cin; d.cout = s.cout; d.stride = s.stride;
   for (int i = 0; i < 3; ++i) { d.k[i] = s.k[i]; d.pad[i] = s.pad[i]; d.opad[i] = s.opad[i]; d.in[i] = s.in[i]; d.out[i] = s.out[i]; }
   d.n = n; d.group_size = group; d.x_img_stride = xs; d.y_img_stride = ys;
@@ -214,23 +217,31 @@ static int finalize_bn(const BnBuf& bn, const float* gamma, const float* beta, i
 // Second stream for work that is off the critical path (the gain stage, every weight gradient): forked and
 // joined with events, so the step is still one ordered unit of work on the caller's stream (and capturable).
 // Disabled while per-operation profiling is on, so that the recorded times are those of un-overlapped kernels.
+// One set of helper stream + events per host thread and per device: no state is shared between callers.
 constexpr int kSideEvents = 24;
 struct SideStream {
   cudaStream_t s = nullptr;
   cudaEvent_t ev[kSideEvents];
-  cudaEvent_t join = nullptr;
-  bool ok = false;
+  cudaEvent_t join = nullptr, ready_main = nullptr, ready_side = nullptr;
+  bool ok = false, tried = false;
+  bool forked = false;      // a branch of this thread's step has not been joined into the main stream yet
+  int n = 0;
 };
 static SideStream& side_stream() {
-  static SideStream sd;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  constexpr int kMaxDev = 16;
+  static thread_local SideStream per_dev[kMaxDev];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) { (void)cudaGetLastError(); dev = 0; }
+  SideStream& sd = per_dev[dev];
+  if (!sd.tried) {
+    sd.tried = true;
     const char* e = getenv("VAEGAM_SIDE_STREAM");
     if (!(e && e[0] == '0') && cudaStreamCreateWithFlags(&sd.s, cudaStreamNonBlocking) == cudaSuccess) {
       sd.ok = true;
       for (int i = 0; i < kSideEvents; ++i) sd.ok = sd.ok && cudaEventCreateWithFlags(&sd.ev[i], cudaEventDisableTiming) == cudaSuccess;
       sd.ok = sd.ok && cudaEventCreateWithFlags(&sd.join, cudaEventDisableTiming) == cudaSuccess;
+      sd.ok = sd.ok && cudaEventCreateWithFlags(&sd.ready_main, cudaEventDisableTiming) == cudaSuccess;
+      sd.ok = sd.ok && cudaEventCreateWithFlags(&sd.ready_side, cudaEventDisableTiming) == cudaSuccess;
     }
     if (!sd.ok) (void)cudaGetLastError();
   }
@@ -240,21 +251,41 @@ struct Fork {
   SideStream& sd;
   cudaStream_t st;
   bool on;
-  int n = 0;
+  bool keep_open = false;   // phased backward: the branch stays open across calls, the last phase joins it
+  int err = VG_OK;          // first CUDA error of a record / wait (returned by join())
   Fork(cudaStream_t main) : sd(side_stream()), st(main), on(sd.ok && !profiling()) {}
+  // an early return between branch() and join() must not leave the helper stream un-joined (stream capture)
+  ~Fork() { if (!keep_open) (void)join(); }
+  void note(cudaError_t e, const char* what) {
+    if (e != cudaSuccess && err == VG_OK) { set_error("step helper stream: %s: %s", what, cudaGetErrorString(e)); err = VG_ECUDA; }
+  }
   // stream for an off-critical-path launch that depends on everything enqueued on the main stream so far
   cudaStream_t branch() {
     if (!on) return st;
-    cudaEventRecord(sd.ev[n], st);
-    cudaStreamWaitEvent(sd.s, sd.ev[n], 0);
-    n = (n + 1) % kSideEvents;
-    return sd.s;
+    note(cudaEventRecord(sd.ev[sd.n], st), "cudaEventRecord");
+    note(cudaStreamWaitEvent(sd.s, sd.ev[sd.n], 0), "cudaStreamWaitEvent");
+    sd.n = (sd.n + 1) % kSideEvents;
+    sd.forked = true;
+    return err == VG_OK ? sd.s : st;
   }
-  // the main stream waits for everything branched so far
-  void join() {
-    if (!on) return;
-    cudaEventRecord(sd.join, sd.s);
-    cudaStreamWaitEvent(st, sd.join, 0);
+  // the main stream waits for everything branched so far (by this or an earlier phase)
+  int join() {
+    if (on && sd.forked) {
+      note(cudaEventRecord(sd.join, sd.s), "cudaEventRecord");
+      note(cudaStreamWaitEvent(st, sd.join, 0), "cudaStreamWaitEvent");
+      sd.forked = false;
+    }
+    return err;
+  }
+  // `rs` waits for everything enqueued so far on the main AND the helper stream; neither is joined
+  int make_ready(cudaStream_t rs) {
+    note(cudaEventRecord(sd.ready_main, st), "cudaEventRecord");
+    note(cudaStreamWaitEvent(rs, sd.ready_main, 0), "cudaStreamWaitEvent");
+    if (on && sd.forked) {
+      note(cudaEventRecord(sd.ready_side, sd.s), "cudaEventRecord");
+      note(cudaStreamWaitEvent(rs, sd.ready_side, 0), "cudaStreamWaitEvent");
+    }
+    return err;
   }
 };
 
@@ -307,15 +338,15 @@ static VgMlp dec_stem_mlp(const VgStepIO* io, const DecWs& d, const float* zcat,
 }
 
 // ---- forward pieces ----------------------------------------------------------------
-static int run_encoder(const VgStepIO* io, const EncWs& e, int B, cudaStream_t st) {
+static int run_encoder(const VgStepIO* io, const EncWs& e, int B, int arith, cudaStream_t st) {
   { VG_PROF("bn_stats", st);
   VG_TRY(vg_bn_stats(io->x, B, B, V, 1, e.bn1.stats, st));
   }
   { VG_PROF("bn1.bn_finalize", st);
   VG_TRY(finalize_bn(e.bn1, PF(BN1), PF(BN1 + 1), 1, 1, (double)B * V, st));
   }
-  VgConvDesc d1 = make_desc(kConv[0], B, B), d2 = make_desc(kConv[1], B, B), d3 = make_desc(kConv[2], B, B),
-             d4 = make_desc(kConv[3], B, B), d5 = make_desc(kConv[4], B, B);
+  VgConvDesc d1 = make_desc(kConv[0], B, B, arith), d2 = make_desc(kConv[1], B, B, arith), d3 = make_desc(kConv[2], B, B, arith),
+             d4 = make_desc(kConv[3], B, B, arith), d5 = make_desc(kConv[4], B, B, arith);
   { VG_PROF("conv1.fwd", st);
   VG_TRY(vg_conv_fwd(&d1, io->x, PF(CONV1), PF(CONV1 + 1), e.bn1.scale, e.bn1.shift, e.a1, VG_ACT_RELU, nullptr, st));
   }
@@ -350,7 +381,7 @@ static int run_encoder(const VgStepIO* io, const EncWs& e, int B, cudaStream_t s
 
 // nd images in groups of `group` share BatchNorm statistics; out rows have stride out_stride
 static int run_decoder(const VgStepIO* io, const DecWs& d, const float* zcat, int nd, int group, float* out,
-                       long long out_stride, cudaStream_t st) {
+                       long long out_stride, int arith, cudaStream_t st) {
   const int groups = nd / group;
   { VG_PROF("fc5-fc7.fwd", st);
   const VgMlp m = dec_stem_mlp(io, d, zcat, nd, nullptr, nullptr);
@@ -366,9 +397,9 @@ static int run_decoder(const VgStepIO* io, const DecWs& d, const float* zcat, in
   { VG_PROF("bnt1.bn_finalize", st);
   VG_TRY(finalize_bn(d.bnt1, PF(BNT1), PF(BNT1 + 1), groups, 16, (double)group * 240, st));
   }
-  VgConvDesc c1 = make_desc(kConvT[0], nd, group), c2 = make_desc(kConvT[1], nd, group),
-             c3 = make_desc(kConvT[2], nd, group), c4 = make_desc(kConvT[3], nd, group),
-             c5 = make_desc(kConvT[4], nd, group, 0, out_stride);
+  VgConvDesc c1 = make_desc(kConvT[0], nd, group, arith), c2 = make_desc(kConvT[1], nd, group, arith),
+             c3 = make_desc(kConvT[2], nd, group, arith), c4 = make_desc(kConvT[3], nd, group, arith),
+             c5 = make_desc(kConvT[4], nd, group, arith, 0, out_stride);
   { VG_PROF("convt1.fwd", st);
   VG_TRY(vg_conv_fwd(&c1, d.t0, PF(CONVT1), PF(CONVT1 + 1), d.bnt1.scale, d.bnt1.shift, d.t1, VG_ACT_RELU, nullptr, st));
   }
@@ -414,8 +445,20 @@ static void fill_gain_params(const VgStepConfig* cfg, const VgStepIO* io, VgGain
   }
 }
 
+// Arithmetic of the step's convolutions from VgStepConfig.arith (include/vaegam.h):
+// encoder forward | everything else
+struct StepArith { int enc_fwd, rest; };
+static StepArith step_arith(const VgStepConfig* cfg) {
+  const int m = resolve_arith(cfg->arith);     // 0 fp32, 1 bf16, 2 mixed
+  StepArith a;
+  a.rest = m == 0 ? VG_ARITH_FP32 : VG_ARITH_BF16;
+  a.enc_fwd = m == 1 ? VG_ARITH_BF16 : VG_ARITH_FP32;
+  return a;
+}
+
 static int check_cfg(const VgStepConfig* cfg, const VgStepIO* io) {
   VG_CHECK_ARG(cfg && io, "null config / io");
+  VG_CHECK_ARG(cfg->arith >= VG_ARITH_DEFAULT && cfg->arith <= VG_ARITH_MIXED, "arith must be a VG_ARITH_* value");
   VG_CHECK_ARG(cfg->b > 0 && cfg->b <= 4096, "batch out of range");
   VG_CHECK_ARG(cfg->m >= 2 && cfg->m <= kMaxInducing, "inducing points must be in [2,16]");
   for (int i = 0; i < VG_NUM_PARAMS; ++i) VG_CHECK_ARG(io->params[i] != nullptr, "null parameter pointer");
@@ -453,13 +496,14 @@ extern "C" int vg_step_fwd(const VgStepConfig* cfg, const VgStepIO* io, void* wo
   VG_TRY(vg_gain_fwd(&gp, io->covariates, io->eps_g, io->taps, B, cfg->m, io->g, w.kl_terms, io->beta_mean,
                      io->beta_var, io->status, w.gain_ws, w.gain_ws_bytes, gs));
   }
-  VG_TRY(run_encoder(io, w.e, B, st));
+  const StepArith ar = step_arith(cfg);
+  VG_TRY(run_encoder(io, w.e, B, ar.enc_fwd, st));
   { VG_PROF("latent.fwd", st);
   VG_TRY(vg_latent_fwd(w.e.heads, io->eps_w, io->eps_d, B, io->z, w.klz, w.d_used, w.zcat,
                        io->status ? io->status + 8 : nullptr, st));
   }
-  VG_TRY(run_decoder(io, w.d, w.zcat, NDEC * B, B, io->maps, VP, st));
-  fk.join();
+  VG_TRY(run_decoder(io, w.d, w.zcat, NDEC * B, B, io->maps, VP, ar.rest, st));
+  VG_TRY(fk.join());
   { VG_PROF("recon_loss.fwd", st);
   VG_TRY(vg_recon_loss_fwd(io->maps, io->g, io->x, w.eps32, io->glm_t, B, V, w.logp, w.norms,
                            cfg->want_maps ? io->cons : nullptr, cfg->want_maps ? io->x_rec : nullptr, w.recon_ws,
@@ -471,19 +515,22 @@ extern "C" int vg_step_fwd(const VgStepConfig* cfg, const VgStepIO* io, void* wo
   return VG_OK;
 }
 
-extern "C" int vg_step_bwd(const VgStepConfig* cfg, const VgStepIO* io, void* workspace, size_t workspace_bytes,
-                           void* stream) {
+// phases: 1 << phase bits of what to run (see vg_step_bwd_phase in include/vaegam.h)
+static int step_bwd_impl(const VgStepConfig* cfg, const VgStepIO* io, void* workspace, size_t workspace_bytes,
+                         unsigned phases, cudaStream_t ready, cudaStream_t st) {
   VG_TRY(check_cfg(cfg, io));
   VG_CHECK_ARG(workspace && workspace_bytes >= vg_step_workspace_bytes(cfg), "workspace too small");
   for (int i = 0; i < VG_NUM_PARAMS; ++i) VG_CHECK_ARG(io->grads[i] != nullptr, "null gradient pointer");
-  cudaStream_t st = as_stream(stream);
   const int B = cfg->b, nd = NDEC * B;
   StepWs w;
   carve_step((char*)workspace, B, cfg->m, true, w);
   const EncWs& e = w.e;
   const DecWs& d = w.d;
+  const int ar = step_arith(cfg).rest;       // every backward pass uses the step's main arithmetic
 
   Fork fk(st);
+  fk.keep_open = (phases & 4u) == 0;         // the last phase joins the helper stream
+  if (phases & 1u) {
   // ---- objective
   { VG_PROF("recon_loss.bwd", st);
   VG_TRY(vg_recon_loss_bwd(io->maps, io->g, io->x, w.eps32, io->glm_t, w.norms, B, V, cfg->glm_reg_scale, w.dpre5,
@@ -500,8 +547,8 @@ extern "C" int vg_step_bwd(const VgStepConfig* cfg, const VgStepIO* io, void* wo
   }
 
   // ---- decoder (9B images, groups of B)
-  VgConvDesc c1 = make_desc(kConvT[0], nd, B), c2 = make_desc(kConvT[1], nd, B), c3 = make_desc(kConvT[2], nd, B),
-             c4 = make_desc(kConvT[3], nd, B), c5 = make_desc(kConvT[4], nd, B, 0, VP);
+  VgConvDesc c1 = make_desc(kConvT[0], nd, B, ar), c2 = make_desc(kConvT[1], nd, B, ar), c3 = make_desc(kConvT[2], nd, B, ar),
+             c4 = make_desc(kConvT[3], nd, B, ar), c5 = make_desc(kConvT[4], nd, B, ar, 0, VP);
   { cudaStream_t ws = fk.branch();
   VG_PROF("convt5.wgrad", ws);
   VG_TRY(vg_conv_wgrad(&c5, d.t4, w.dpre5, d.bnt5.scale, d.bnt5.shift, GF(CONVT5), GF(CONVT5 + 1), ws));
@@ -558,6 +605,8 @@ extern "C" int vg_step_bwd(const VgStepConfig* cfg, const VgStepIO* io, void* wo
   VG_TRY(vg_mlp_bwd(&m, st));
   }
 
+  }
+  if (phases & 2u) {
   // ---- latent
   fill_kernel<<<cdiv(B, 128), 128, 0, st>>>(w.dklz, B, 1.f / (float)B);   // tot = -mean(logp - klz)
   VG_LAUNCH_CHECK();
@@ -573,13 +622,15 @@ extern "C" int vg_step_bwd(const VgStepConfig* cfg, const VgStepIO* io, void* wo
   { VG_PROF("fc1.bwd", st);
   VG_TRY(vg_linear_bwd(w.d_h1, e.h1, e.a5f, PF(FC1), w.d_a5f, GF(FC1), GF(FC1 + 1), B, 200, 3072, st));
   }
+  }
+  if (phases & 4u) {
   { VG_PROF("layout", st);
   VG_TRY(vg_nchw_to_nhwc(w.d_a5f, w.d_a5, B, 16, 192, st));
   }
   relu_mask_kernel<<<cdiv((long long)B * 3072, 256), 256, 0, st>>>(w.d_a5, e.a5, (long long)B * 3072);
   VG_LAUNCH_CHECK();
-  VgConvDesc d1 = make_desc(kConv[0], B, B), d2 = make_desc(kConv[1], B, B), d3 = make_desc(kConv[2], B, B),
-             d4 = make_desc(kConv[3], B, B), d5 = make_desc(kConv[4], B, B);
+  VgConvDesc d1 = make_desc(kConv[0], B, B, ar), d2 = make_desc(kConv[1], B, B, ar), d3 = make_desc(kConv[2], B, B, ar),
+             d4 = make_desc(kConv[3], B, B, ar), d5 = make_desc(kConv[4], B, B, ar);
   { cudaStream_t ws = fk.branch();
   VG_PROF("conv5.wgrad", ws);
   VG_TRY(vg_conv_wgrad(&d5, e.a4, w.d_a5, e.bn5.scale, e.bn5.shift, GF(CONV5), GF(CONV5 + 1), ws));
@@ -628,8 +679,21 @@ extern "C" int vg_step_bwd(const VgStepConfig* cfg, const VgStepIO* io, void* wo
   VG_TRY(vg_bn_bwd_apply(nullptr, io->x, e.bn1.sums, nullptr, nullptr, nullptr, B, B, V, 1, (double)B * V, 0, nullptr,
                          GF(BN1), GF(BN1 + 1), st));
   }
-  fk.join();
-  return VG_OK;
+  }
+  if (ready) VG_TRY(fk.make_ready(ready));
+  if (phases & 4u) VG_TRY(fk.join());
+  return fk.err;
+}
+
+extern "C" int vg_step_bwd(const VgStepConfig* cfg, const VgStepIO* io, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+  return step_bwd_impl(cfg, io, workspace, workspace_bytes, 7u, nullptr, as_stream(stream));
+}
+
+extern "C" int vg_step_bwd_phase(const VgStepConfig* cfg, const VgStepIO* io, void* workspace, size_t workspace_bytes,
+                                 int phase, void* ready_stream, void* stream) {
+  VG_CHECK_ARG(phase >= 0 && phase < VG_BWD_PHASES, "phase must be 0, 1 or 2");
+  return step_bwd_impl(cfg, io, workspace, workspace_bytes, 1u << phase, as_stream(ready_stream), as_stream(stream));
 }
 
 extern "C" int vg_encode_fwd(const VgStepConfig* cfg, const VgStepIO* io, float* heads, void* workspace,
@@ -641,7 +705,7 @@ extern "C" int vg_encode_fwd(const VgStepConfig* cfg, const VgStepIO* io, float*
   StepWs w;
   carve_step((char*)workspace, cfg->b, cfg->m, true, w);
   VG_CUDA(cudaMemsetAsync(w.zero_begin, 0, w.zero_bytes, st));
-  VG_TRY(run_encoder(io, w.e, cfg->b, st));
+  VG_TRY(run_encoder(io, w.e, cfg->b, step_arith(cfg).enc_fwd, st));
   VG_CUDA(cudaMemcpyAsync(heads, w.e.heads, (size_t)3 * cfg->b * L * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return VG_OK;
 }
@@ -657,9 +721,10 @@ extern "C" size_t vg_decode_workspace_bytes(int n) {
   return b.off + 512;
 }
 
-extern "C" int vg_decode_fwd(const VgStepIO* io, const float* zcat, int n, float* out, void* workspace,
+extern "C" int vg_decode_fwd(const VgStepIO* io, const float* zcat, int n, int arith, float* out, void* workspace,
                              size_t workspace_bytes, void* stream) {
   VG_CHECK_ARG(io && zcat && out && n > 0, "bad arguments");
+  VG_CHECK_ARG(arith >= VG_ARITH_DEFAULT && arith <= VG_ARITH_MIXED, "arith must be a VG_ARITH_* value");
   VG_CHECK_ARG(workspace && workspace_bytes >= vg_decode_workspace_bytes(n), "workspace too small");
   cudaStream_t st = as_stream(stream);
   Bump b{(char*)workspace, 0};
@@ -671,5 +736,6 @@ extern "C" int vg_decode_fwd(const VgStepIO* io, const float* zcat, int n, float
   take_bn_coef(b, d.bnt1, 1, 16); take_bn_coef(b, d.bnt3, 1, 16); take_bn_coef(b, d.bnt5, 1, 8);
   carve_dec(b, d, n);
   VG_CUDA(cudaMemsetAsync(z0, 0, zbytes, st));
-  return run_decoder(io, d, zcat, n, n, out, V, st);   // dense (n, V) output like VAE.decode
+  // dense (n, V) output like VAE.decode
+  return run_decoder(io, d, zcat, n, n, out, V, resolve_arith(arith) == 0 ? VG_ARITH_FP32 : VG_ARITH_BF16, st);
 }

@@ -123,6 +123,9 @@ class VAE(nn.Module):
         # TensorBoard hooks inside forward(): every `log_every` training steps (0 = never)
         self.log_every = int(os.environ.get("VAEGAM_TB_EVERY", "0"))
         self._step_counter = 0
+        # arithmetic of the convolutions, carried by every native call: "default" (the library's process default,
+        # VAEGAM_CONV_MODE / vg_set_conv_mode: mixed unless set), "fp32", "bf16" or "mixed" (include/vaegam.h)
+        self.arith = os.environ.get("VAEGAM_ARITH", "default")
         # whole-step CUDA graphs in train_batch / train_epoch (VAEGAM_CUDA_GRAPH=0 switches them off)
         self.use_cuda_graph = os.environ.get("VAEGAM_CUDA_GRAPH", "1") != "0"
         self._graph_steps = {}
@@ -177,13 +180,16 @@ class VAE(nn.Module):
         old_opt = getattr(self, "optimizer", None)
         self._flat = FlatParams(named, self.device)
         new_opt = FlatAdam(self._flat, lr=self.lr)
-        if old_opt is not None and getattr(old_opt, "_host_steps", 0) > 0:
+        same_layout = old_opt is not None and getattr(old_opt, "flat", None) is not None and \
+            old_opt.flat.slices == self._flat.slices
+        if same_layout and getattr(old_opt, "_host_steps", 0) > 0:      # moments only survive an identical layout
             new_opt.m32.copy_(old_opt.m32); new_opt.v32.copy_(old_opt.v32)
             new_opt.m64.copy_(old_opt.m64); new_opt.v64.copy_(old_opt.v64)
             new_opt.step_count.copy_(old_opt.step_count)
             new_opt._host_steps = old_opt._host_steps
         self.optimizer = new_opt
         self._engine = None
+        self._graph_steps = {}
 
     def _get_engine(self) -> StepEngine:
         native.require_cuda()
@@ -195,6 +201,7 @@ class VAE(nn.Module):
             xu = [self.gp_params[k]['xu'] for k in _GP_COVS]
             self._engine = StepEngine(self._flat, xu, self.glm_maps, self.inducing_pts, self._as_float("gp_kl_scale"),
                                       self._as_float("glm_reg_scale"), self.neural_covariates, self.device)
+        self._engine.arith = native.ARITH_BY_NAME[self.arith] if isinstance(self.arith, str) else int(self.arith)
         self._engine.gp_kl_scale = self._as_float("gp_kl_scale")
         self._engine.glm_reg_scale = self._as_float("glm_reg_scale")
         self._engine.neural_covariates = bool(self.neural_covariates)
@@ -240,8 +247,8 @@ class VAE(nn.Module):
         sb = eng.buffers(1)
         eng._bind_params(sb, with_grads=False)
         out = torch.empty(n, IMG_DIM, dtype=torch.float32, device=self.device)
-        native.check(lib.vg_decode_fwd(C.byref(sb.io), native.ptr(z), n, native.ptr(out), native.ptr(ws), nbytes,
-                                       native.stream_ptr()), "vg_decode_fwd")
+        native.check(lib.vg_decode_fwd(C.byref(sb.io), native.ptr(z), n, int(eng.arith), native.ptr(out), native.ptr(ws),
+                                       nbytes, native.stream_ptr()), "vg_decode_fwd")
         return out
 
     def calc_linW_KL(self, sa, std):
@@ -386,6 +393,7 @@ class VAE(nn.Module):
         self.loss, self.epoch = ckpt['loss'], ckpt['epoch']
         self.glm_reg_scale, self.gp_kl_scale = ckpt['glm_reg_scale'], ckpt['gp_kl_scale']
         self.inducing_pts = ckpt['inducing_pts']
+        replaced = False
         with torch.no_grad():
             self.epsilon.copy_(ckpt['epsilon'].to(self.device))
             for key, entry in ckpt['gp_params'].items():
@@ -402,14 +410,18 @@ class VAE(nn.Module):
                         cur = nn.Parameter(new.clone())
                         setattr(self, attr, cur)
                         self.gp_params[key][pname] = cur
+                        replaced = True
                     else:
                         cur.copy_(new)
         # values were copied INTO the registered parameters (they keep aliasing the flat buffer when
         # shapes match), so the optimizer keeps owning them — unlike the reference
-        if not self._flat.is_packed():
+        # A replaced Parameter (other num_inducing_pts) changes the flat layout: FlatParams still lists the OLD
+        # objects, so is_packed() cannot see it — re-pack from named_parameters() unconditionally in that case.
+        if replaced or not self._flat.is_packed():
             self._pack()
         self.optimizer.load_state_dict(ckpt['optimizer_state'])
         self._engine = None
+        self._graph_steps = {}
 
     # ------------------------------------------------------------------ callers of the hot path
     def project_latent(self, loaders_dict, save_dir, title=None, split=98):
@@ -450,7 +462,7 @@ class VAE(nn.Module):
         accumulated there (fp64 index_add) so that `build_model_recons.mk_avg_maps` does not have to
         read the 10 x N files back; one asynchronous D2H per batch into alternating pinned buffers,
         and the files of batch i are written by a small thread pool while batch i+1 computes."""
-        import nibabel as nib
+        from vaegam.nib_compat import nib
         from concurrent.futures import ThreadPoolExecutor
         eng = self._get_engine()
         n_subj = len(save_dirs)
@@ -461,7 +473,8 @@ class VAE(nn.Module):
         pending = [[], []]
         copied = [torch.cuda.Event(), torch.cuda.Event()]
 
-        def write_volume(arr10, s, vol):
+        def write_volume(arr10, s, vol, ready):
+            ready.synchronize()                   # this batch's D2H has landed (waited for here, off the main thread)
             vol_dir = os.path.join(save_dirs[s], 'vol_{}'.format(vol))
             os.makedirs(vol_dir, exist_ok=True)
             aff, hdr = ref_cache[s]
@@ -491,10 +504,10 @@ class VAE(nn.Module):
                     pinned[slot] = torch.empty(max(B, loader.batch_size or B), len(IMG_KEYS), IMG_DIM).pin_memory()
                 host = pinned[slot][:B]
                 host.copy_(per_vol, non_blocking=True)
+                copied[slot] = torch.cuda.Event()
                 copied[slot].record()
-                copied[slot].synchronize()
                 arr = host.numpy()
-                pending[slot] = [pool.submit(write_volume, arr[b], subjidx[b], vol_num[b]) for b in range(B)]
+                pending[slot] = [pool.submit(write_volume, arr[b], subjidx[b], vol_num[b], copied[slot]) for b in range(B)]
             for fs in pending:
                 for f in fs:
                     f.result()

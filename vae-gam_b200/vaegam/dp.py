@@ -3,7 +3,8 @@ NVLink/NVSwitch.  The independent unit is a MINIBATCH (BatchNorm statistics, the
 over the batch index and the B x B gain covariance couple the volumes of a batch), so each
 rank runs the full step on its own batch, BatchNorm is not synchronised, and the only
 exchange is the gradient all-reduce: 6.5 MB per step (1 494 109 fp32 + 70 315 fp64) taken
-straight from the flat gradient buffers — no bucketing copies.
+straight from the flat gradient buffers — three contiguous buckets, no bucketing copies — and
+overlapped with the backward (GradientAllReduce).
 
 N-GPU DP with local batch B equals the AVERAGE of N independent reference steps of batch B
 (the objective is not a per-sample mean: glm_reg ~ B * sum_b, GP KL is per batch).
@@ -44,8 +45,22 @@ def shard_indices(n_items: int, rank: int, world: int, epoch: int = 0, shuffle: 
 
 class GradientAllReduce:
     """Sum-all-reduce of the flat gradient buffers; the 1/world factor is folded into the fused
-    Adam kernel (`grad_scale`).  With `overlap=True` the reduce runs on a side stream so the
-    caller can keep enqueueing work (the optimizer step waits on it)."""
+    Adam kernel (`grad_scale`).
+
+    Overlap with the backward: the flat fp32 gradient is cut into three contiguous buckets
+    in the order the backward completes them — the flat layout is the reference's parameter order, so the
+    decoder's parameters (fc5.. bnt5) are its tail, the encoder's fully connected layers (fc1..fc43) its
+    middle, and the gain parameters + encoder convolutions its head:
+
+        phase 0 (objective + decoder backward)   -> epsilon (fp64 buffer) + flat32[fc5.weight:]     3.3 + 0.56 MB
+        phase 1 (latent + encoder FC backward)   -> flat32[fc1.weight : fc5.weight]                2.6 MB
+        phase 2 (encoder convolutions, gains)    -> flat32[: fc1.weight]                           0.1 MB
+
+    `vg_step_bwd_phase` makes `self.stream` wait for the producers of a phase (events only, helper stream
+    included) and `reduce_phase` enqueues that bucket's `ncclAllReduce` there, so it runs while the next phase
+    computes; only the small last bucket is exposed.  The same sequence is what a whole-step CUDA graph
+    captures (`vaegam.step.GraphStep`).  `overlap=False` (or a CPU/gloo group) gives the plain
+    reduce-after-backward."""
 
     def __init__(self, flat, optimizer=None, group=None, overlap: bool = True):
         self.flat = flat
@@ -56,13 +71,37 @@ class GradientAllReduce:
             optimizer.grad_scale = 1.0 / self.world
         self.cuda = flat.grad32.is_cuda
         self.stream = torch.cuda.Stream() if (self.cuda and overlap) else None
+        self.overlapped = self.stream is not None
         self._pending = None
+        self._buckets_for = None
+
+    def buckets(self):
+        """[[tensors of phase 0], [phase 1], [phase 2]] — views of the flat gradient buffers (rebuilt when the
+        flat buffers were re-packed)."""
+        f = self.flat
+        key = (f.version, f.grad32.data_ptr(), f.grad64.data_ptr())
+        if self._buckets_for != key:
+            o_fc1, o_fc5 = f.slices["fc1.weight"][1], f.slices["fc5.weight"][1]
+            assert 0 < o_fc1 < o_fc5 < f.n32
+            self._buckets = [[f.grad64, f.grad32[o_fc5:]], [f.grad32[o_fc1:o_fc5]], [f.grad32[:o_fc1]]]
+            self._buckets_for = key
+        return self._buckets
 
     def broadcast_parameters(self, src: int = 0):
         if self.world == 1:
             return
         dist.broadcast(self.flat.flat32, src, group=self.group)
         dist.broadcast(self.flat.flat64, src, group=self.group)
+
+    def reduce_phase(self, phase: int):
+        """All-reduce the bucket that backward phase `phase` completed, on `self.stream` (which
+        vg_step_bwd_phase has already made wait for the bucket's producers)."""
+        if self.world == 1:
+            return
+        with torch.cuda.stream(self.stream):
+            for t in self.buckets()[phase]:
+                dist.all_reduce(t, group=self.group)
+        self._pending = True
 
     def start(self):
         if self.world == 1:
@@ -72,27 +111,23 @@ class GradientAllReduce:
             for b in bufs:
                 dist.all_reduce(b, group=self.group)
             return
-        ev = torch.cuda.Event()
-        ev.record()
-        self.stream.wait_event(ev)
+        self.stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self.stream):
             for b in bufs:
                 dist.all_reduce(b, group=self.group)
-            done = torch.cuda.Event()
-            done.record()
-        self._pending = done
+        self._pending = True
 
     def inline(self):
-        """All-reduce on the CURRENT stream (no side stream, no events): the form a CUDA-graph capture of the
-        whole step records (vaegam.step.GraphStep)."""
+        """All-reduce on the CURRENT stream (no side stream, no events)."""
         if self.world == 1:
             return
         for b in (self.flat.grad32, self.flat.grad64):
             dist.all_reduce(b, group=self.group)
 
     def finish(self):
-        if self._pending is not None:
-            torch.cuda.current_stream().wait_event(self._pending)
+        """The current stream waits for every all-reduce enqueued on the reducer's stream."""
+        if self._pending:
+            torch.cuda.current_stream().wait_stream(self.stream)
             self._pending = None
 
     def __call__(self):

@@ -17,6 +17,10 @@ LIB_PATH = os.path.join(_HERE, "libvaegam_sm100.so")
 
 VG_NUM_PARAMS = 97
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
+# VG_ARITH_* (include/vaegam.h): per-call arithmetic of the convolution kernels
+ARITH_DEFAULT, ARITH_FP32, ARITH_BF16, ARITH_MIXED = 0, 1, 2, 3
+ARITH_BY_NAME = {"default": ARITH_DEFAULT, "fp32": ARITH_FP32, "bf16": ARITH_BF16, "mixed": ARITH_MIXED}
+VG_BWD_PHASES = 3
 VG_OK, VG_EINVAL = 0, -1
 V = 41 * 49 * 35
 VP = (V + 3) // 4 * 4
@@ -29,7 +33,7 @@ class NativeError(RuntimeError):
 class VgConvDesc(C.Structure):
     _fields_ = [("transposed", C.c_int32), ("cin", C.c_int32), ("cout", C.c_int32), ("k", C.c_int32 * 3),
                 ("stride", C.c_int32), ("pad", C.c_int32 * 3), ("opad", C.c_int32 * 3), ("in_", C.c_int32 * 3),
-                ("out", C.c_int32 * 3), ("n", C.c_int32), ("group_size", C.c_int32),
+                ("out", C.c_int32 * 3), ("n", C.c_int32), ("group_size", C.c_int32), ("arith", C.c_int32),
                 ("x_img_stride", C.c_int64), ("y_img_stride", C.c_int64)]
 
 
@@ -46,7 +50,8 @@ class VgGainGrads(C.Structure):
 
 class VgStepConfig(C.Structure):
     _fields_ = [("b", C.c_int32), ("m", C.c_int32), ("neural_covariates", C.c_int32), ("want_maps", C.c_int32),
-                ("gp_kl_scale", C.c_float), ("glm_reg_scale", C.c_float)]
+                ("gp_kl_scale", C.c_float), ("glm_reg_scale", C.c_float), ("arith", C.c_int32),
+                ("reserved", C.c_int32 * 3)]
 
 
 class VgMlpLayer(C.Structure):
@@ -119,13 +124,14 @@ SIGNATURES = {
     "vg_recon_plan": (_I, [_I, _LL, _I, C.POINTER(C.c_int)]),
     "vg_recon_loss_fwd": (_I, [_P, _P, _P, _P, _P, _I, _LL, _P, _P, _P, _P, _P, _SZ, _P]),
     "vg_recon_loss_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _LL, _F, _P, _P, _P, _P, _SZ, _P]),
-    "vg_adam_step": (_I, [_P, _P, _P, _P, _LL, _P, _P, _P, _P, _LL, _D, _D, _D, _D, _D, _P, _P]),
+    "vg_adam_step": (_I, [_P, _P, _P, _P, _LL, _P, _P, _P, _P, _LL, _D, _D, _D, _D, _D, _P, _P, _I, _P]),
     "vg_step_workspace_bytes": (_SZ, [C.POINTER(VgStepConfig)]),
     "vg_step_fwd": (_I, [C.POINTER(VgStepConfig), C.POINTER(VgStepIO), _P, _SZ, _P]),
     "vg_step_bwd": (_I, [C.POINTER(VgStepConfig), C.POINTER(VgStepIO), _P, _SZ, _P]),
+    "vg_step_bwd_phase": (_I, [C.POINTER(VgStepConfig), C.POINTER(VgStepIO), _P, _SZ, _I, _P, _P]),
     "vg_encode_fwd": (_I, [C.POINTER(VgStepConfig), C.POINTER(VgStepIO), _P, _P, _SZ, _P]),
     "vg_decode_workspace_bytes": (_SZ, [_I]),
-    "vg_decode_fwd": (_I, [C.POINTER(VgStepIO), _P, _I, _P, _P, _SZ, _P]),
+    "vg_decode_fwd": (_I, [C.POINTER(VgStepIO), _P, _I, _I, _P, _P, _SZ, _P]),
 }
 
 _lib = None
@@ -192,8 +198,9 @@ def profile_collect():
 
 
 def conv_desc(transposed, cin, cout, k, stride, in_, n, group_size, pad=(0, 0, 0), opad=(0, 0, 0),
-              x_img_stride=0, y_img_stride=0) -> VgConvDesc:
+              x_img_stride=0, y_img_stride=0, arith=ARITH_DEFAULT) -> VgConvDesc:
     d = VgConvDesc()
+    d.arith = arith
     d.transposed, d.cin, d.cout, d.stride = int(transposed), cin, cout, stride
     for i in range(3):
         d.k[i], d.pad[i], d.opad[i], d.in_[i] = k[i], pad[i], opad[i], in_[i]

@@ -3,8 +3,9 @@
 nibabel is not installed in this image and the reference uses only a sliver of it:
 `nib.load(p).dataobj / .affine / .header`, `nib.Nifti1Image(arr, affine, header)` and
 `nib.save(img, p)` (reference DataClass_GP.py:48, vae_reg_GP.py:618-620,
-build_model_recons.py:88,113-116).  `vae-gam_b200/nibabel/` re-exports this module under that
-name so those call sites keep working unchanged.
+build_model_recons.py:88,113-116).  `vaegam.compat.install_nibabel()` registers this module as
+`nibabel` ONLY when no real nibabel is installed, so those call sites keep working unchanged
+ and an installed nibabel is never shadowed.
 """
 from __future__ import annotations
 
@@ -14,9 +15,28 @@ import struct
 import numpy as np
 
 _DTYPES = {2: np.uint8, 4: np.int16, 8: np.int32, 16: np.float32, 64: np.float64, 256: np.int8,
-           512: np.uint16, 768: np.uint32}
+           512: np.uint16, 768: np.uint32, 1024: np.int64, 1280: np.uint64}
 _CODES = {np.dtype(v).str[1:]: k for k, v in _DTYPES.items()}
 SYNTHETIC_PREFIX = "synthetic://"
+__version__ = "0.vaegam"
+
+
+def _qform_affine(raw, endian, pixdim):
+    """NIfTI-1 'method 2': rotation from the quaternion (b, c, d), qfac = pixdim[0], offsets qoffset_*."""
+    b, c, d, qx, qy, qz = struct.unpack(endian + "6f", raw[256:280])
+    a2 = 1.0 - (b * b + c * c + d * d)
+    a = np.sqrt(a2) if a2 > 0 else 0.0
+    if a2 <= 0:                                   # normalise (b, c, d) for a 180-degree rotation
+        n = np.sqrt(b * b + c * c + d * d)
+        b, c, d = b / n, c / n, d / n
+    R = np.array([[a * a + b * b - c * c - d * d, 2 * (b * c - a * d), 2 * (b * d + a * c)],
+                  [2 * (b * c + a * d), a * a + c * c - b * b - d * d, 2 * (c * d - a * b)],
+                  [2 * (b * d - a * c), 2 * (c * d + a * b), a * a + d * d - b * b - c * c]])
+    qfac = -1.0 if pixdim[0] < 0 else 1.0
+    aff = np.eye(4)
+    aff[:3, :3] = R * np.array([pixdim[1], pixdim[2], pixdim[3] * qfac])
+    aff[:3, 3] = (qx, qy, qz)
+    return aff
 
 
 class Nifti1Header:
@@ -77,8 +97,10 @@ def load(path) -> Nifti1Image:
         if slope != 0.0:
             data = data.astype(np.float64) * slope + inter
     affine = np.eye(4)
-    if sform_code > 0:
+    if sform_code > 0:                     # nibabel's precedence: sform, then qform, then pixdim
         affine[:3, :] = srow
+    elif qform_code > 0:
+        affine = _qform_affine(raw, endian, pixdim)
     else:
         affine[0, 0], affine[1, 1], affine[2, 2] = pixdim[1], pixdim[2], pixdim[3]
     return Nifti1Image(data, affine, Nifti1Header(pixdim[1:5], affine if sform_code > 0 else None))

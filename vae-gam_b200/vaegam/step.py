@@ -122,6 +122,7 @@ class StepBuffers:
         self.cfg.want_maps = 0
         self.cfg.gp_kl_scale = float(engine.gp_kl_scale)
         self.cfg.glm_reg_scale = float(engine.glm_reg_scale)
+        self.cfg.arith = int(engine.arith)
         self.ws_bytes = int(lib.vg_step_workspace_bytes(C.byref(self.cfg)))
         self.workspace = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
         f32 = dict(dtype=torch.float32, device=dev)
@@ -155,10 +156,11 @@ class StepEngine:
     """Runs the native step for a VAE module (vae_reg_GP.VAE in this package)."""
 
     def __init__(self, flat: FlatParams, xu: List[torch.Tensor], glm_maps: torch.Tensor, m: int,
-                 gp_kl_scale: float, glm_reg_scale: float, neural_covariates: bool, device):
+                 gp_kl_scale: float, glm_reg_scale: float, neural_covariates: bool, device, arith: int = 0):
         native.require_cuda()
         native.load()
         self.flat = flat
+        self.arith = int(arith)     # VG_ARITH_* carried by every call (0 = the library's process default)
         self.device = device
         self.m = int(m)
         self.gp_kl_scale = float(gp_kl_scale)
@@ -225,6 +227,8 @@ class StepEngine:
         sb.cfg.want_maps = int(want_maps)
         sb.cfg.gp_kl_scale = float(self.gp_kl_scale)
         sb.cfg.glm_reg_scale = float(self.glm_reg_scale)
+        sb.cfg.arith = int(self.arith)
+        self.flat.last_status = sb.status       # the fused Adam skips its update when these flags are set
         if want_maps:
             sb.ensure_map_outputs(dev)
         self._bind_params(sb, with_grads=False)
@@ -232,15 +236,24 @@ class StepEngine:
                                      native.stream_ptr()), "vg_step_fwd")
         return sb
 
-    def backward(self, sb: StepBuffers):
+    def backward(self, sb: StepBuffers, reducer=None):
         """Writes d(tot)/d(param) for every parameter into the flat gradient buffers
-        (overwriting them)."""
+        (overwriting them).  With a multi-rank `reducer` (vaegam.dp.GradientAllReduce) the backward runs in
+        its three phases and each phase's gradient bucket is all-reduced on the reducer's stream while the
+        next phase computes; the caller joins with `reducer.finish()` before the optimizer step."""
         lib = native.load()
         self.flat.grad32.zero_()
         self.flat.grad64.zero_()
         self._bind_params(sb, with_grads=True)
-        native.check(lib.vg_step_bwd(C.byref(sb.cfg), C.byref(sb.io), native.ptr(sb.workspace), sb.ws_bytes,
-                                     native.stream_ptr()), "vg_step_bwd")
+        if reducer is None or reducer.world == 1 or not reducer.overlapped:
+            native.check(lib.vg_step_bwd(C.byref(sb.cfg), C.byref(sb.io), native.ptr(sb.workspace), sb.ws_bytes,
+                                         native.stream_ptr()), "vg_step_bwd")
+            return
+        for phase in range(native.VG_BWD_PHASES):
+            native.check(lib.vg_step_bwd_phase(C.byref(sb.cfg), C.byref(sb.io), native.ptr(sb.workspace), sb.ws_bytes,
+                                               phase, reducer.stream.cuda_stream, native.stream_ptr()),
+                         "vg_step_bwd_phase")
+            reducer.reduce_phase(phase)
 
 
 class _StepFn(torch.autograd.Function):
@@ -348,16 +361,21 @@ class GraphStep:
         loss weights, gradient scale) needs a new capture."""
         g = self.opt.param_groups[0]
         e = self.engine
-        return (e.gp_kl_scale, e.glm_reg_scale, e.neural_covariates, e.m, float(g["lr"]), tuple(g["betas"]),
+        return (e.gp_kl_scale, e.glm_reg_scale, e.neural_covariates, e.m, e.arith, float(g["lr"]), tuple(g["betas"]),
                 float(g["eps"]), float(self.opt.grad_scale))
 
     def _body(self):
         eng = self.engine
         sb = eng.forward(self.x, self.cov, self.noise, False)
-        eng.backward(sb)
-        if self.reducer is not None:
-            self.reducer.inline()       # sum over ranks on this stream; 1/world is folded into Adam's grad_scale
-        self.opt.launch()
+        red = self.reducer
+        if red is not None and red.world > 1 and red.overlapped:
+            eng.backward(sb, red)       # bucketed all-reduce on the reducer's stream, overlapped with the backward
+            red.finish()                # join before Adam; 1/world is folded into Adam's grad_scale
+        else:
+            eng.backward(sb)
+            if red is not None:
+                red.inline()            # sum over ranks on this stream
+        self.opt.launch(sb.status)
         self.loss.copy_(sb.scalars[:1])
         self.sb = sb
 
@@ -473,13 +491,15 @@ class FlatAdam(torch.optim.Adam):
                 gv.zero_()
             elif p.grad.data_ptr() != gv.data_ptr():
                 gv.copy_(p.grad)
-        self.launch()
+        self.launch(getattr(f, "last_status", None))
         self._host_steps += 1
 
     @torch.no_grad()
-    def launch(self):
+    def launch(self, status=None):
         """The fused Adam kernel over the flat buffers as they are (graph-capturable: the step count lives on
-        the device)."""
+        the device).  `status`: the step's 16-int device flags; when any of the 8 gain flags is set (a
+        covariance was not positive definite) the kernel leaves parameters, moments and step count untouched —
+        the reference raises inside forward before backward()/step() (vae_reg_GP.py:368, gp.py:51)."""
         f = self.flat
         lib = native.load()
         g = self.param_groups[0]
@@ -488,4 +508,5 @@ class FlatAdam(torch.optim.Adam):
                                       native.ptr(self.v32), f.n32, native.ptr(f.flat64), native.ptr(f.grad64),
                                       native.ptr(self.m64), native.ptr(self.v64), f.n64, float(g["lr"]), float(b1),
                                       float(b2), float(g["eps"]), float(self.grad_scale),
-                                      native.ptr(self.step_count), native.stream_ptr()), "vg_adam_step")
+                                      native.ptr(self.step_count), native.ptr(status), 8 if status is not None else 0,
+                                      native.stream_ptr()), "vg_adam_step")
