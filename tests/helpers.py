@@ -50,3 +50,27 @@ def sample_flat(t, n=64):
 def rel_err(a, b):
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
+
+
+def nifti_experiment(tmp_path, n_subjects=2, n_vols=5, with_test_csv=False):
+    """A tiny cohort backed by real 4-D NIfTI files (BASELINE config 5 needs reference images for affine / header)."""
+    import pandas as pd
+    from vaegam import synthetic as syn
+    from vaegam.nib_compat import nib
+    coh = syn.make_cohort(n_subjects, "checker", seed=3, n_vols=n_vols)
+    vols = coh.volumes().numpy() * 3284.5                                     # the loader divides by 3284.5
+    tab = coh.table.copy()
+    sidx = coh.subject_index()
+    paths = []
+    for s, name in enumerate(tab["subjid"].unique().tolist()):
+        v4 = np.moveaxis(vols[sidx == s], 0, -1).astype(np.float32)           # (41,49,35,T)
+        path = str(tmp_path / f"{name}.nii.gz")
+        nib.save(nib.Nifti1Image(v4, np.diag([3.0, 3.0, 3.5, 1.0])), path)
+        paths.append(path)
+    tab["nii_path"] = [paths[s] for s in sidx]
+    tab["volume #"] = np.concatenate([np.arange(n_vols)] * n_subjects)
+    csv = str(tmp_path / "train.csv")
+    tab.to_csv(csv)
+    glm = str(tmp_path / "glm.csv")
+    pd.DataFrame(syn.glm_maps_uniform(), columns=syn.GLM_COLS).to_csv(glm)
+    return csv, glm, coh
