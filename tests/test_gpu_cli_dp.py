@@ -77,9 +77,11 @@ def test_reference_cli_runs_unchanged(tmp_path):
     assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-3000:])
     assert "Loading model state from" in r.stdout
     from vaegam.nib_compat import nib
-    avg = np.asarray(nib.load(str(out2 / "reconstructions" / "001_avg_model_recons" / "base_avg.nii")).dataobj)
+    # the checkpoint written during epoch index 1 carries model.epoch == 2 (train_epoch has already advanced it,
+    # reference vae_reg_GP.py:433,712-714), so the reconstruction tree is numbered 002 again
+    avg = np.asarray(nib.load(str(out2 / "reconstructions" / "002_avg_model_recons" / "base_avg.nii")).dataobj)
     assert avg.shape == (41, 49, 35) and np.isfinite(avg).all() and 0 < avg.mean() < 1
-    one = np.asarray(nib.load(str(out2 / "reconstructions" / "001_model_recons" / subj[0] / vols[0] / "recon_full_rec.nii")).dataobj)
+    one = np.asarray(nib.load(str(out2 / "reconstructions" / "002_model_recons" / subj[0] / vols[0] / "recon_full_rec.nii")).dataobj)
     assert one.shape == (41, 49, 35) and np.isfinite(one).all()
 
 

@@ -648,11 +648,22 @@ def test_fused_adam_matches_torch(lib):
         opt.step()
         native.check(lib.vg_adam_step(native.ptr(p32), native.ptr(g32), native.ptr(m32), native.ptr(v32), p32.numel(),
                                       native.ptr(p64), native.ptr(g64), native.ptr(m64), native.ptr(v64), p64.numel(),
-                                      1e-3, 0.9, 0.999, 1e-8, 1.0, native.ptr(step), native.stream_ptr()))
+                                      1e-3, 0.9, 0.999, 1e-8, 1.0, native.ptr(step), None, 0, native.stream_ptr()))
     torch.cuda.synchronize()
     assert int(step) == 5
     assert rel_err(p32.cpu(), r32.detach().cpu()) < 1e-6
     assert rel_err(p64.cpu(), r64.detach().cpu()) < 1e-13
+    # skip flags: any non-zero flag freezes parameters, moments and the step count (non-PD minibatch)
+    flags = torch.zeros(8, dtype=torch.int32, device=dev)
+    keep = (p32.clone(), m32.clone(), v32.clone(), p64.clone())
+    for bad in (True, False):
+        flags[5] = 3 if bad else 0
+        native.check(lib.vg_adam_step(native.ptr(p32), native.ptr(g32), native.ptr(m32), native.ptr(v32), p32.numel(),
+                                      native.ptr(p64), native.ptr(g64), native.ptr(m64), native.ptr(v64), p64.numel(),
+                                      1e-3, 0.9, 0.999, 1e-8, 1.0, native.ptr(step), native.ptr(flags), 8, native.stream_ptr()))
+        torch.cuda.synchronize()
+        frozen = all(torch.equal(a, b) for a, b in zip(keep, (p32, m32, v32, p64)))
+        assert frozen == bad and int(step) == (5 if bad else 6)
 
 
 def test_gp_posterior_matches_oracle(lib):
