@@ -70,6 +70,11 @@ typedef struct VgConvDesc {
   int32_t n;               /* images */
   int32_t group_size;      /* images per BatchNorm statistics group (n % group_size == 0) */
   int32_t arith;           /* VG_ARITH_*: arithmetic of THIS call (0 = the process default below) */
+  int32_t bf16_mask;       /* storage of the big activations (tensor-core arithmetic only; 0 = all fp32):
+                              VG_BF16_X  x / bn_x / mask_act hold bf16 (2 bytes per element, same layout),
+                              VG_BF16_Y  y / dy hold bf16, VG_BF16_DX  dx is written as bf16.
+                              Supported for 8- and 16-channel tensors (a voxel = one or two 16-byte words) */
+  int32_t reserved_;
   int64_t x_img_stride;    /* floats between consecutive images of x / dx; 0 = dense (D*H*W*cin) */
   int64_t y_img_stride;    /* floats between consecutive images of y / dy; 0 = dense (D*H*W*cout) */
 } VgConvDesc;
@@ -91,6 +96,9 @@ typedef struct VgConvDesc {
  *      "2"/"mixed"; unset = mixed) and can be changed with vg_set_conv_mode(0 | 1 | 2).
  * vg_set_conv_mode / vg_set_conv_tuning / vg_recon_tune only move such process DEFAULTS and
  * benchmarking knobs; no entry point keeps per-call state in the library. */
+#define VG_BF16_X 1
+#define VG_BF16_Y 2
+#define VG_BF16_DX 4
 #define VG_ARITH_DEFAULT 0
 #define VG_ARITH_FP32 1
 #define VG_ARITH_BF16 2
@@ -111,8 +119,8 @@ int vg_conv_describe(const VgConvDesc* d, int kind, char* buf, size_t cap);
  * AFTER the affine (it pads the normalised tensor).  in_scale/in_shift: (n/group_size, cin)
  * or NULL.  out_stats: (n/group_size, cout, 2) doubles, ACCUMULATED with sum(y), sum(y^2)
  * (caller zeroes) or NULL. */
-int vg_conv_fwd(const VgConvDesc* d, const float* x, const float* w, const float* bias,
-                const float* in_scale, const float* in_shift, float* y, int act,
+int vg_conv_fwd(const VgConvDesc* d, const void* x, const float* w, const float* bias,
+                const float* in_scale, const float* in_shift, void* y, int act,
                 double* out_stats, void* stream);
 
 /* dx = conv^T(dy) w.r.t. the (affine-folded) input.  dy must already be the gradient
@@ -122,13 +130,13 @@ int vg_conv_fwd(const VgConvDesc* d, const float* x, const float* w, const float
  *                                     sum(dx), sum(dx * xhat), xhat = bn_x*bn_istd - bn_mistd
  *                                     (bn_istd, bn_mistd: (groups, cin) = 1/std, mean/std)
  *   dx == NULL                      : nothing is stored (statistics only; bn1 of conv1). */
-int vg_conv_dgrad(const VgConvDesc* d, const float* dy, const float* w, float* dx,
-                  const float* mask_act, const float* bn_x, const float* bn_istd,
+int vg_conv_dgrad(const VgConvDesc* d, const void* dy, const float* w, void* dx,
+                  const void* mask_act, const void* bn_x, const float* bn_istd,
                   const float* bn_mistd, double* bn_sums, void* stream);
 
 /* dw (PyTorch layout, ACCUMULATED — caller zeroes) and dbias (cout, accumulated) from
  * x (with the same affine fold as the forward) and dy (gradient w.r.t. pre-activation). */
-int vg_conv_wgrad(const VgConvDesc* d, const float* x, const float* dy, const float* in_scale,
+int vg_conv_wgrad(const VgConvDesc* d, const void* x, const void* dy, const float* in_scale,
                   const float* in_shift, float* dw, float* dbias, void* stream);
 
 /* ------------------------------------------------------------------------------------
@@ -147,10 +155,12 @@ int vg_bn_finalize(const double* stats, const float* gamma, const float* beta, i
                    void* stream);
 /* dx = scale[g,c] * (dy - m1 - xhat*m2) [* (x > 0) if relu_mask], m1 = sums[g,c,0]/count,
  * m2 = sums[g,c,1]/count; dgamma[c] += sum_g sums[g,c,1]; dbeta[c] += sum_g sums[g,c,0]
- * (dgamma/dbeta may be NULL; they are accumulated by one thread block). In-place (dx == dy) ok. */
-int vg_bn_bwd_apply(const float* dy, const float* x, const double* sums, const float* scale,
+ * (dgamma/dbeta may be NULL; they are accumulated by one thread block). In-place (dx == dy) ok.
+ * bf16_mask: VG_BF16_X = x holds bf16, VG_BF16_DX = dx is written as bf16 (dy is always fp32, so
+ * dx must then be a different buffer than dy); c must be 8 or 16 for bf16 storage. */
+int vg_bn_bwd_apply(const float* dy, const void* x, const double* sums, const float* scale,
                     const float* istd, const float* mistd, int n, int group_size,
-                    long long spatial, int c, double count, int relu_mask, float* dx,
+                    long long spatial, int c, double count, int relu_mask, int bf16_mask, void* dx,
                     float* dgamma, float* dbeta, void* stream);
 /* (n, c, spatial) <-> (n, spatial, c) */
 int vg_nchw_to_nhwc(const float* src, float* dst, int n, int c, long long spatial, void* stream);

@@ -198,6 +198,88 @@ def test_conv_tensor_core_path(lib, name, big):
     assert rel_err(db.cpu(), gb_exact.cpu()) < 2e-5
 
 
+@pytest.mark.parametrize("name", ["convt5", "convt4", "conv2", "convt3"])
+def test_conv_bf16_activation_storage(lib, name):
+    """VgConvDesc.bf16_mask: the big activations may live in HBM as bf16 (tensor-core arithmetic).  A kernel fed
+    bf16 x / dy must give exactly what it gives for the same values held in fp32 (they round to themselves), and a
+    bf16 output is the fp32 output rounded once."""
+    native = nat()
+    spec = LAYERS[name]
+    tr, cin, cout, k, s, in_, pad, opad = spec
+    N, group = 4, 2
+    dev = "cuda"
+    gen = torch.Generator(device=dev).manual_seed(11 + sum(map(ord, name)))
+    x = bf16r(torch.randn(N, cin, *in_, device=dev, generator=gen))
+    wshape = (cin, cout, *k) if tr else (cout, cin, *k)
+    w = torch.randn(*wshape, device=dev, generator=gen) * 0.2
+    b = torch.randn(cout, device=dev, generator=gen)
+    scale = torch.rand(N // group, cin, device=dev, generator=gen) + 0.5
+    shift = torch.randn(N // group, cin, device=dev, generator=gen)
+    native.check(lib.vg_set_conv_tuning(b"t2_min_voxels", 0))
+    st = native.stream_ptr()
+    mk = lambda mask: native.conv_desc(tr, cin, cout, k, s, in_, N, group, pad, opad, arith=native.ARITH_BF16, bf16_mask=mask)
+    d0 = mk(0)
+    x_cl = to_cl(x)
+    x16 = x_cl.to(torch.bfloat16)
+    y0 = torch.empty(N, *tuple(d0.out), cout, device=dev)
+    native.check(lib.vg_conv_fwd(C.byref(d0), native.ptr(x_cl), native.ptr(w), native.ptr(b), native.ptr(scale),
+                                 native.ptr(shift), native.ptr(y0), native.ACT_RELU, None, st))
+    # forward: bf16 x (8 input channels), bf16 y (8 / 16 output channels)
+    for mask in ([native.BF16_X] if cin == 8 else []) + ([native.BF16_Y] if cout % 8 == 0 else []) + \
+            ([native.BF16_X | native.BF16_Y] if cin == 8 and cout % 8 == 0 else []):
+        y = torch.empty(N, *tuple(d0.out), cout, device=dev, dtype=torch.bfloat16 if mask & native.BF16_Y else torch.float32)
+        dm = mk(mask)
+        native.check(lib.vg_conv_fwd(C.byref(dm), native.ptr(x16 if mask & native.BF16_X else x_cl), native.ptr(w), native.ptr(b),
+                                     native.ptr(scale), native.ptr(shift), native.ptr(y), native.ACT_RELU, None, st))
+        torch.cuda.synchronize()
+        want = y0.to(torch.bfloat16).float() if mask & native.BF16_Y else y0
+        assert rel_err(y.float().cpu(), want.cpu()) < 1e-6, ("fwd", mask)
+    # data gradient: bf16 dy (8 output channels), bf16 dx and bf16 saved activation (8 / 16 input channels)
+    dy = bf16r(torch.randn(N, cout, *tuple(d0.out), device=dev, generator=gen))
+    dy_cl = to_cl(dy)
+    dy16 = dy_cl.to(torch.bfloat16)
+    act = bf16r(torch.randn(N, cin, *in_, device=dev, generator=gen))
+    act_cl = to_cl(act)
+    act16 = act_cl.to(torch.bfloat16)
+    istd = torch.rand(N // group, cin, device=dev, generator=gen) + 0.5
+    mistd = torch.randn(N // group, cin, device=dev, generator=gen)
+    dx0 = torch.empty_like(x_cl)
+    sums0 = torch.zeros(N // group, cin, 2, dtype=torch.float64, device=dev)
+    native.check(lib.vg_conv_dgrad(C.byref(d0), native.ptr(dy_cl), native.ptr(w), native.ptr(dx0), None, native.ptr(act_cl),
+                                   native.ptr(istd), native.ptr(mistd), native.ptr(sums0), st))
+    masks = []
+    if cout == 8:
+        masks.append(native.BF16_Y)
+    if cin % 8 == 0:
+        masks += [native.BF16_X, native.BF16_DX, native.BF16_X | native.BF16_DX]
+        if cout == 8:
+            masks.append(native.BF16_X | native.BF16_Y | native.BF16_DX)
+    for mask in masks:
+        dx = torch.empty_like(x_cl, dtype=torch.bfloat16 if mask & native.BF16_DX else torch.float32)
+        sums = torch.zeros_like(sums0)
+        dm = mk(mask)
+        native.check(lib.vg_conv_dgrad(C.byref(dm), native.ptr(dy16 if mask & native.BF16_Y else dy_cl), native.ptr(w),
+                                       native.ptr(dx), None, native.ptr(act16 if mask & native.BF16_X else act_cl),
+                                       native.ptr(istd), native.ptr(mistd), native.ptr(sums), st))
+        torch.cuda.synchronize()
+        want = dx0.to(torch.bfloat16).float() if mask & native.BF16_DX else dx0
+        assert rel_err(dx.float().cpu(), want.cpu()) < 1e-6, ("dgrad", mask)
+        assert rel_err(sums.cpu(), sums0.cpu()) < 1e-6, ("dgrad sums", mask)
+    # weight gradient: bf16 x / dy with 8 or 16 channels
+    dw0, db0 = torch.zeros_like(w), torch.zeros_like(b)
+    native.check(lib.vg_conv_wgrad(C.byref(d0), native.ptr(x_cl), native.ptr(dy_cl), native.ptr(scale), native.ptr(shift),
+                                   native.ptr(dw0), native.ptr(db0), st))
+    for mask in ([native.BF16_X] if cin % 8 == 0 else []) + ([native.BF16_Y] if cout % 8 == 0 else []):
+        dw, db = torch.zeros_like(w), torch.zeros_like(b)
+        dm = mk(mask)
+        native.check(lib.vg_conv_wgrad(C.byref(dm), native.ptr(x16 if mask & native.BF16_X else x_cl),
+                                       native.ptr(dy16 if mask & native.BF16_Y else dy_cl), native.ptr(scale), native.ptr(shift),
+                                       native.ptr(dw), native.ptr(db), st))
+        torch.cuda.synchronize()
+        assert rel_err(dw.cpu(), dw0.cpu()) < 2e-5, ("wgrad", mask)       # fp32 atomics: accumulation order only
+        assert rel_err(db.cpu(), db0.cpu()) < 2e-5, ("wgrad bias", mask)
+
+
 @pytest.mark.parametrize("name", list(LAYERS))
 def test_conv_forward_dgrad_wgrad(lib, name):
     native = nat()
@@ -323,7 +405,7 @@ def test_batchnorm_helpers(lib, c, spatial):
     dx = torch.empty_like(x)
     dgamma, dbeta = torch.zeros(c, device=dev), torch.zeros(c, device=dev)
     native.check(lib.vg_bn_bwd_apply(native.ptr(dy), native.ptr(x), native.ptr(sums), native.ptr(scale),
-                                     native.ptr(istd), native.ptr(mistd), N, group, spatial, c, count, 0,
+                                     native.ptr(istd), native.ptr(mistd), N, group, spatial, c, count, 0, 0,
                                      native.ptr(dx), native.ptr(dgamma), native.ptr(dbeta), st))
     torch.cuda.synchronize()
     assert rel_err(dx.cpu(), xr.grad.cpu()) < 2e-5
@@ -332,10 +414,26 @@ def test_batchnorm_helpers(lib, c, spatial):
     # relu-masked variant
     dxm = torch.empty_like(x)
     native.check(lib.vg_bn_bwd_apply(native.ptr(dy), native.ptr(x), native.ptr(sums), native.ptr(scale),
-                                     native.ptr(istd), native.ptr(mistd), N, group, spatial, c, count, 1,
+                                     native.ptr(istd), native.ptr(mistd), N, group, spatial, c, count, 1, 0,
                                      native.ptr(dxm), None, None, st))
     torch.cuda.synchronize()
     assert rel_err(dxm.cpu(), (xr.grad * (x > 0)).cpu()) < 2e-5
+    if c % 8 == 0:
+        # bf16 storage of x and / or dx: same arithmetic on the bf16-rounded x, result rounded once on store
+        xb = x.to(torch.bfloat16)
+        ref16 = torch.empty_like(x)
+        native.check(lib.vg_bn_bwd_apply(native.ptr(dy), native.ptr(xb.float().contiguous()), native.ptr(sums), native.ptr(scale),
+                                         native.ptr(istd), native.ptr(mistd), N, group, spatial, c, count, 1, 0,
+                                         native.ptr(ref16), None, None, st))
+        for mask in (native.BF16_X, native.BF16_X | native.BF16_DX, native.BF16_DX):
+            out = torch.empty_like(x, dtype=torch.bfloat16 if mask & native.BF16_DX else torch.float32)
+            xin = xb if mask & native.BF16_X else xb.float().contiguous()
+            native.check(lib.vg_bn_bwd_apply(native.ptr(dy), native.ptr(xin), native.ptr(sums), native.ptr(scale),
+                                             native.ptr(istd), native.ptr(mistd), N, group, spatial, c, count, 1, mask,
+                                             native.ptr(out), None, None, st))
+            torch.cuda.synchronize()
+            want = ref16.to(torch.bfloat16).float() if mask & native.BF16_DX else ref16
+            assert rel_err(out.float().cpu(), want.cpu()) < 1e-6, mask
 
 
 def test_layout_transposes(lib):

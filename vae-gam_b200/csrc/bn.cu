@@ -4,6 +4,7 @@
 // produced by a convolution epilogue, the coefficient finalisation, the backward apply
 // and the layout changes at the conv <-> fully-connected seams.
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace vg {
 
@@ -140,6 +141,82 @@ bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x,
   }
 }
 
+// The same apply for tensors stored as bf16 (x and / or dx; dy is fp32): a thread item is 8 consecutive channels
+// (one 16-byte bf16 word, two fp32 words), its stride a multiple of C / 8 items, so the 8 channels' coefficients
+// stay in registers; two items in flight.
+template <int C, bool X16, bool DX16>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply8_kernel(const float* __restrict__ dy, const void* __restrict__ x_, const double* __restrict__ sums,
+                     const float* __restrict__ scale, const float* __restrict__ istd, const float* __restrict__ mistd,
+                     int group_size, long long spatial, double count, int relu_mask, void* dx_) {
+  static_assert(C % 8 == 0, "8-channel items");
+  const int n = blockIdx.y;
+  const int grp = n / group_size;
+  const long long total = spatial * C;
+  const size_t base = (size_t)n * total;
+  constexpr int U = 2;
+  const long long nv = total / 8;
+  const long long stride = (long long)gridDim.x * blockDim.x;     // multiple of 256, hence of C / 8
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float m1[8], m2[8], is[8], mis[8], sc[8];
+  {
+    const int c0 = (int)((i0 * 8) % C);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int gc = grp * C + c0 + j;
+      m1[j] = (float)(sums[2 * gc] / count);
+      m2[j] = (float)(sums[2 * gc + 1] / count);
+      is[j] = istd[gc]; mis[j] = mistd[gc]; sc[j] = scale[gc];
+    }
+  }
+  const float* xf = static_cast<const float*>(x_);
+  const __nv_bfloat16* xh = static_cast<const __nv_bfloat16*>(x_);
+  for (long long i = i0; i < nv; i += U * stride) {
+    float4 a[U][2], b[U][2];
+    uint4 bq[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long iu = i + u * stride;
+      if (iu >= nv) break;
+      a[u][0] = ldg_stream(reinterpret_cast<const float4*>(dy + base) + 2 * iu);
+      a[u][1] = ldg_stream(reinterpret_cast<const float4*>(dy + base) + 2 * iu + 1);
+      if constexpr (X16) {
+        bq[u] = ldg_u4(xh + base + 8 * iu);
+      } else {
+        b[u][0] = ldg_stream(reinterpret_cast<const float4*>(xf + base) + 2 * iu);
+        b[u][1] = ldg_stream(reinterpret_cast<const float4*>(xf + base) + 2 * iu + 1);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long iu = i + u * stride;
+      if (iu >= nv) break;
+      float d[8] = {a[u][0].x, a[u][0].y, a[u][0].z, a[u][0].w, a[u][1].x, a[u][1].y, a[u][1].z, a[u][1].w};
+      float xv[8], o[8];
+      if constexpr (X16) {
+        unpack_bf16x8(bq[u], xv);
+      } else {
+        xv[0] = b[u][0].x; xv[1] = b[u][0].y; xv[2] = b[u][0].z; xv[3] = b[u][0].w;
+        xv[4] = b[u][1].x; xv[5] = b[u][1].y; xv[6] = b[u][1].z; xv[7] = b[u][1].w;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xhat = fmaf(xv[j], is[j], -mis[j]);
+        float r = sc[j] * (d[j] - m1[j] - xhat * m2[j]);
+        if (relu_mask && !(xv[j] > 0.f)) r = 0.f;
+        o[j] = r;
+      }
+      if constexpr (DX16) {
+        reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(dx_) + base)[iu] = pack_bf16x8(o);
+      } else {
+        float* dxf = static_cast<float*>(dx_) + base;
+        stg_stream(reinterpret_cast<float4*>(dxf) + 2 * iu, make_float4(o[0], o[1], o[2], o[3]));
+        stg_stream(reinterpret_cast<float4*>(dxf) + 2 * iu + 1, make_float4(o[4], o[5], o[6], o[7]));
+      }
+    }
+  }
+}
+
 __global__ void bn_param_grad_kernel(const double* __restrict__ sums, int groups, int c, float* dgamma,
                                      float* dbeta) {
   const int ch = threadIdx.x;
@@ -210,13 +287,32 @@ extern "C" int vg_bn_finalize(const double* stats, const float* gamma, const flo
   return VG_OK;
 }
 
-extern "C" int vg_bn_bwd_apply(const float* dy, const float* x, const double* sums, const float* scale,
+extern "C" int vg_bn_bwd_apply(const float* dy, const void* x_, const double* sums, const float* scale,
                                const float* istd, const float* mistd, int n, int group_size,
-                               long long spatial, int c, double count, int relu_mask, float* dx,
+                               long long spatial, int c, double count, int relu_mask, int bf16_mask, void* dx_,
                                float* dgamma, float* dbeta, void* stream) {
+  const float* x = static_cast<const float*>(x_);
+  float* dx = static_cast<float*>(dx_);
   VG_CHECK_ARG(x && sums && n > 0 && group_size > 0 && n % group_size == 0, "bad arguments");
   cudaStream_t st = as_stream(stream);
-  if (dx) {
+  if (dx && (bf16_mask & (VG_BF16_X | VG_BF16_DX))) {
+    VG_CHECK_ARG(dy && scale && istd && mistd, "null coefficient");
+    VG_CHECK_ARG(c == 8 || c == 16, "bf16 storage needs 8 or 16 channels");
+    VG_CHECK_ARG(!(bf16_mask & VG_BF16_DX) || (const void*)dy != dx_, "bf16 dx cannot alias the fp32 dy");
+    const long long per_img = spatial * c;
+    int bx = (int)((per_img / 8 + 255) / 256);
+    int cap = 8 * vg_sm_count() / n;
+    if (cap < 1) cap = 1;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    dim3 grid(bx, n);
+    const bool x16 = (bf16_mask & VG_BF16_X) != 0, d16 = (bf16_mask & VG_BF16_DX) != 0;
+#define VG_BN8(C, X, D) bn_bwd_apply8_kernel<C, X, D><<<grid, 256, 0, st>>>(dy, x_, sums, scale, istd, mistd, group_size, spatial, count, relu_mask, dx_)
+    if (c == 8) { if (x16 && d16) VG_BN8(8, true, true); else if (x16) VG_BN8(8, true, false); else VG_BN8(8, false, true); }
+    else { if (x16 && d16) VG_BN8(16, true, true); else if (x16) VG_BN8(16, true, false); else VG_BN8(16, false, true); }
+#undef VG_BN8
+    VG_LAUNCH_CHECK();
+  } else if (dx) {
     VG_CHECK_ARG(dy && scale && istd && mistd, "null coefficient");
     long long per_img = spatial * c;
     int bx = (int)((per_img / 4 + 255) / 256);

@@ -368,8 +368,22 @@ static bool tc2_worthwhile(const Geom* gs, int ng) {
   return vox >= g_t2_min_voxels;
 }
 
+// bf16 storage is implemented by the plane-folded tensor-core kernel only
+static bool wants_bf16(const GatherArgs& a) { return a.in_bf16 || a.out_bf16 || a.aux_bf16; }
+static int check_bf16(int cin, int cout, const GatherArgs& a) {
+  VG_CHECK_ARG(!a.in_bf16 || cin == 8, "bf16 input storage needs 8 input channels");
+  VG_CHECK_ARG(!(a.out_bf16 || a.aux_bf16) || cout % 8 == 0, "bf16 output storage needs 8 or 16 output channels");
+  return VG_OK;
+}
+static int no_bf16_path() {
+  set_error("bf16 activation storage (VgConvDesc.bf16_mask) is only served by the plane-folded tensor-core kernel; "
+            "this geometry / arithmetic falls outside it");
+  return VG_EINVAL;
+}
+
 static int launch_gather(bool tc, int cin, int cout, const Geom& g, const GatherArgs& a, cudaStream_t st) {
-  if (tc && tc2_worthwhile(&g, 1) && tc2_supported(cin, cout, &g, 1)) return launch_tc2_gather(cin, cout, &g, 1, a, st);
+  if (tc && (tc2_worthwhile(&g, 1) || wants_bf16(a)) && tc2_supported(cin, cout, &g, 1)) return launch_tc2_gather(cin, cout, &g, 1, a, st);
+  if (wants_bf16(a)) return no_bf16_path();
   if (tc && tc_supported(cin, cout, g)) return launch_tc_gather(cin, cout, g, a, st);
   if (cin == 1 && cout == 8) return launch_gather_t<1, 8, 4>(g, a, st);
   if (cin == 8 && cout == 1) return launch_gather_t<8, 1, 4>(g, a, st);
@@ -420,8 +434,10 @@ static PhaseStreams& phase_streams() {
 
 // every gather of one layer pass: one fused multi-phase launch when the plane-folded kernel covers it
 static int launch_all(bool tc, int cin, int cout, const Geom* gs, int ng, const GatherArgs& a, cudaStream_t st) {
-  if (ng > 1 && tc && tc2_worthwhile(gs, ng) && tc2_supported(cin, cout, gs, ng))
+  if (wants_bf16(a)) VG_TRY(check_bf16(cin, cout, a));
+  if (ng > 1 && tc && (tc2_worthwhile(gs, ng) || wants_bf16(a)) && tc2_supported(cin, cout, gs, ng))
     return launch_tc2_gather(cin, cout, gs, ng, a, st);
+  if (ng > 1 && wants_bf16(a)) return no_bf16_path();
   PhaseStreams& ps = phase_streams();
   if (ng < 2 || ng > kPhaseStreams + 1 || !ps.ok) {
     for (int i = 0; i < ng; ++i) VG_TRY(launch_gather(tc, cin, cout, gs[i], a, st));
@@ -486,22 +502,27 @@ extern "C" int vg_conv_describe(const VgConvDesc* d, int kind, char* buf, size_t
   return ng;
 }
 
-extern "C" int vg_conv_fwd(const VgConvDesc* d, const float* x, const float* w, const float* bias,
-                           const float* in_scale, const float* in_shift, float* y, int act,
+extern "C" int vg_conv_fwd(const VgConvDesc* d, const void* x, const float* w, const float* bias,
+                           const float* in_scale, const float* in_shift, void* y, int act,
                            double* out_stats, void* stream) {
   VG_TRY(check_desc(d));
   VG_CHECK_ARG(x && w && y, "null tensor");
   Geom gs[8];
   const int ng = build_geoms(d, 0, gs);
   GatherArgs a{};
-  a.in = x; a.w = w; a.bias = bias; a.in_scale = in_scale; a.in_shift = in_shift;
-  a.out = y; a.act = act; a.stats = out_stats;
+  a.in = static_cast<const float*>(x); a.w = w; a.bias = bias; a.in_scale = in_scale; a.in_shift = in_shift;
+  a.out = static_cast<float*>(y); a.act = act; a.stats = out_stats;
+  a.in_bf16 = (d->bf16_mask & VG_BF16_X) != 0; a.out_bf16 = (d->bf16_mask & VG_BF16_Y) != 0;
   return launch_all(desc_tc(d), d->cin, d->cout, gs, ng, a, as_stream(stream));
 }
 
-extern "C" int vg_conv_dgrad(const VgConvDesc* d, const float* dy, const float* w, float* dx,
-                             const float* mask_act, const float* bn_x, const float* bn_istd,
+extern "C" int vg_conv_dgrad(const VgConvDesc* d, const void* dy_, const float* w, void* dx_,
+                             const void* mask_act_, const void* bn_x_, const float* bn_istd,
                              const float* bn_mistd, double* bn_sums, void* stream) {
+  const float* dy = static_cast<const float*>(dy_);
+  float* dx = static_cast<float*>(dx_);
+  const float* mask_act = static_cast<const float*>(mask_act_);
+  const float* bn_x = static_cast<const float*>(bn_x_);
   VG_TRY(check_desc(d));
   VG_CHECK_ARG(dy && w, "null tensor");
   VG_CHECK_ARG(!(mask_act && bn_x), "mask_act and bn_x are exclusive");
@@ -510,6 +531,8 @@ extern "C" int vg_conv_dgrad(const VgConvDesc* d, const float* dy, const float* 
   const int ng = build_geoms(d, 1, gs);
   GatherArgs a{};
   a.in = dy; a.w = w; a.out = dx; a.act = VG_ACT_NONE;
+  a.in_bf16 = (d->bf16_mask & VG_BF16_Y) != 0; a.out_bf16 = (d->bf16_mask & VG_BF16_DX) != 0;
+  a.aux_bf16 = (d->bf16_mask & VG_BF16_X) != 0 && (mask_act || bn_x);
   if (mask_act) { a.aux = mask_act; a.aux_mode = 1; }
   if (bn_x) { a.aux = bn_x; a.aux_mode = 2; a.aux_istd = bn_istd; a.aux_mistd = bn_mistd; a.aux_sums = bn_sums; }
   // the gather reads dy (cout channels) and produces cin channels
@@ -518,13 +541,13 @@ extern "C" int vg_conv_dgrad(const VgConvDesc* d, const float* dy, const float* 
 
 namespace vg {
 // wgrad_mma.cu: bf16 mma.sync weight gradient; VG_OK, a negative error, or 1 = channel pair not covered
-int wgrad_mma(const VgConvDesc* d, const float* x, const float* dy, const float* in_scale, const float* in_shift,
+int wgrad_mma(const VgConvDesc* d, const void* x, const void* dy, const float* in_scale, const float* in_shift,
               float* dw, float* dbias, cudaStream_t st);
 }
 int vg_conv_wgrad_tiled(const VgConvDesc* d, const float* x, const float* dy, const float* in_scale,
                         const float* in_shift, float* dw, float* dbias, cudaStream_t st);   // wgrad.cu
 
-extern "C" int vg_conv_wgrad(const VgConvDesc* d, const float* x, const float* dy, const float* in_scale,
+extern "C" int vg_conv_wgrad(const VgConvDesc* d, const void* x, const void* dy, const float* in_scale,
                              const float* in_shift, float* dw, float* dbias, void* stream) {
   VG_TRY(check_desc(d));
   VG_CHECK_ARG(x && dy && dw, "null tensor");
@@ -532,5 +555,7 @@ extern "C" int vg_conv_wgrad(const VgConvDesc* d, const float* x, const float* d
     const int rc = wgrad_mma(d, x, dy, in_scale, in_shift, dw, dbias, as_stream(stream));   // bias gradient fused
     if (rc <= 0) return rc;
   }
-  return vg_conv_wgrad_tiled(d, x, dy, in_scale, in_shift, dw, dbias, as_stream(stream));
+  if (d->bf16_mask & (VG_BF16_X | VG_BF16_Y)) return no_bf16_path();
+  return vg_conv_wgrad_tiled(d, static_cast<const float*>(x), static_cast<const float*>(dy), in_scale, in_shift, dw, dbias,
+                             as_stream(stream));
 }

@@ -26,6 +26,9 @@ struct Geom {
 };
 
 struct GatherArgs {
+  // storage of the three big tensors of a gather: fp32 by default, bf16 (same layout, 2 bytes per element) when
+  // the flag is set — tensor-core kernels only (VgConvDesc.bf16_mask)
+  int in_bf16, out_bf16, aux_bf16;
   const float* in;
   const float* w;
   const float* bias;      // (COUT) or null

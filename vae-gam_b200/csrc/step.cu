@@ -81,6 +81,7 @@ struct StepWs {
   float *d_used, *klz, *zcat, *eps32, *logp, *norms;
   double* kl_terms; void* gain_ws; size_t gain_ws_bytes; void* recon_ws; size_t recon_ws_bytes;
   // backward
+  uint16_t* d_t4h;
   float *dpre5, *d_t4, *d_t3, *d_t2, *d_t1, *d_t0, *d_f8, *d_f7, *d_f6, *d_f5, *d_zcat, *dheads, *d_h3, *d_h2,
       *d_h1, *d_a5f, *d_a5, *d_a4, *d_a3, *d_a2, *d_a1, *dg, *deps32, *dklz;
   double* zero_begin; size_t zero_bytes;   // contiguous region holding all BN stats / sums
@@ -149,6 +150,7 @@ static size_t carve_step(char* base, int B, int m, bool backward, StepWs& w) {
   if (backward) {
     w.dpre5 = b.take<float>((size_t)nd * VP);
     w.d_t4 = b.take<float>((size_t)nd * 60489 * 8);
+    w.d_t4h = b.take<uint16_t>((size_t)nd * 60489 * 8);      // bf16 copy of the final gradient (tensor-core arithmetic)
     w.d_t3 = b.take<float>((size_t)nd * 6624 * 8);
     w.d_t2 = b.take<float>((size_t)nd * 4704 * 16);
     w.d_t1 = b.take<float>((size_t)nd * 560 * 16);
@@ -400,6 +402,7 @@ static int run_decoder(const VgStepIO* io, const DecWs& d, const float* zcat, in
   VgConvDesc c1 = make_desc(kConvT[0], nd, group, arith), c2 = make_desc(kConvT[1], nd, group, arith),
              c3 = make_desc(kConvT[2], nd, group, arith), c4 = make_desc(kConvT[3], nd, group, arith),
              c5 = make_desc(kConvT[4], nd, group, arith, 0, out_stride);
+  if (arith == VG_ARITH_BF16) { c4.bf16_mask = VG_BF16_Y; c5.bf16_mask = VG_BF16_X; }   // t4 is stored as bf16
   { VG_PROF("convt1.fwd", st);
   VG_TRY(vg_conv_fwd(&c1, d.t0, PF(CONVT1), PF(CONVT1 + 1), d.bnt1.scale, d.bnt1.shift, d.t1, VG_ACT_RELU, nullptr, st));
   }
@@ -549,23 +552,29 @@ static int step_bwd_impl(const VgStepConfig* cfg, const VgStepIO* io, void* work
   // ---- decoder (9B images, groups of B)
   VgConvDesc c1 = make_desc(kConvT[0], nd, B, ar), c2 = make_desc(kConvT[1], nd, B, ar), c3 = make_desc(kConvT[2], nd, B, ar),
              c4 = make_desc(kConvT[3], nd, B, ar), c5 = make_desc(kConvT[4], nd, B, ar, 0, VP);
+  const bool big16 = ar == VG_ARITH_BF16;
+  if (big16) { c4.bf16_mask = VG_BF16_Y; c5.bf16_mask = VG_BF16_X; }     // convt4: y = t4, dy = its gradient; convt5: x = t4
   { cudaStream_t ws = fk.branch();
   VG_PROF("convt5.wgrad", ws);
   VG_TRY(vg_conv_wgrad(&c5, d.t4, w.dpre5, d.bnt5.scale, d.bnt5.shift, GF(CONVT5), GF(CONVT5 + 1), ws));
   }
+  // tensor-core arithmetic: t4 (the largest activation) is stored as bf16 and so is its final gradient; the raw
+  // data gradient that enters the BatchNorm backward stays fp32 (its rounding would be amplified by the projection)
+  void* d_t4_final = big16 ? (void*)w.d_t4h : (void*)w.d_t4;
   { VG_PROF("convt5.dgrad", st);
   VG_TRY(vg_conv_dgrad(&c5, w.dpre5, PF(CONVT5), w.d_t4, nullptr, d.t4, d.bnt5.istd, d.bnt5.mistd, d.bnt5.sums, st));
   }
   { VG_PROF("bnt5.bn_bwd", st);
   VG_TRY(vg_bn_bwd_apply(w.d_t4, d.t4, d.bnt5.sums, d.bnt5.scale, d.bnt5.istd, d.bnt5.mistd, nd, B,
-                         vol(kConvT[3].out), 8, (double)B * vol(kConvT[3].out), 1, w.d_t4, GF(BNT5), GF(BNT5 + 1), st));
+                         vol(kConvT[3].out), 8, (double)B * vol(kConvT[3].out), 1, big16 ? (VG_BF16_X | VG_BF16_DX) : 0,
+                         d_t4_final, GF(BNT5), GF(BNT5 + 1), st));
   }
   { cudaStream_t ws = fk.branch();
   VG_PROF("convt4.wgrad", ws);
-  VG_TRY(vg_conv_wgrad(&c4, d.t3, w.d_t4, nullptr, nullptr, GF(CONVT4), GF(CONVT4 + 1), ws));
+  VG_TRY(vg_conv_wgrad(&c4, d.t3, d_t4_final, nullptr, nullptr, GF(CONVT4), GF(CONVT4 + 1), ws));
   }
   { VG_PROF("convt4.dgrad", st);
-  VG_TRY(vg_conv_dgrad(&c4, w.d_t4, PF(CONVT4), w.d_t3, d.t3, nullptr, nullptr, nullptr, nullptr, st));
+  VG_TRY(vg_conv_dgrad(&c4, d_t4_final, PF(CONVT4), w.d_t3, d.t3, nullptr, nullptr, nullptr, nullptr, st));
   }
   { cudaStream_t ws = fk.branch();
   VG_PROF("convt3.wgrad", ws);
@@ -576,7 +585,7 @@ static int step_bwd_impl(const VgStepConfig* cfg, const VgStepIO* io, void* work
   }
   { VG_PROF("bnt3.bn_bwd", st);
   VG_TRY(vg_bn_bwd_apply(w.d_t2, d.t2, d.bnt3.sums, d.bnt3.scale, d.bnt3.istd, d.bnt3.mistd, nd, B,
-                         vol(kConvT[1].out), 16, (double)B * vol(kConvT[1].out), 1, w.d_t2, GF(BNT3), GF(BNT3 + 1), st));
+                         vol(kConvT[1].out), 16, (double)B * vol(kConvT[1].out), 1, 0, w.d_t2, GF(BNT3), GF(BNT3 + 1), st));
   }
   { cudaStream_t ws = fk.branch();
   VG_PROF("convt2.wgrad", ws);
@@ -594,7 +603,7 @@ static int step_bwd_impl(const VgStepConfig* cfg, const VgStepIO* io, void* work
   }
   { VG_PROF("bnt1.bn_bwd", st);
   VG_TRY(vg_bn_bwd_apply(w.d_t0, d.t0, d.bnt1.sums, d.bnt1.scale, d.bnt1.istd, d.bnt1.mistd, nd, B, 240, 16,
-                         (double)B * 240, 1, w.d_t0, GF(BNT1), GF(BNT1 + 1), st));
+                         (double)B * 240, 1, 0, w.d_t0, GF(BNT1), GF(BNT1 + 1), st));
   }
   { VG_PROF("layout", st);
   VG_TRY(vg_nhwc_to_nchw(w.d_t0, w.d_f8, nd, 16, 240, st));     // gradient w.r.t. fc8 pre-activation
@@ -640,7 +649,7 @@ static int step_bwd_impl(const VgStepConfig* cfg, const VgStepIO* io, void* work
   }
   { VG_PROF("bn5.bn_bwd", st);
   VG_TRY(vg_bn_bwd_apply(w.d_a4, e.a4, e.bn5.sums, e.bn5.scale, e.bn5.istd, e.bn5.mistd, B, B, vol(kConv[3].out), 16,
-                         (double)B * vol(kConv[3].out), 1, w.d_a4, GF(BN5), GF(BN5 + 1), st));
+                         (double)B * vol(kConv[3].out), 1, 0, w.d_a4, GF(BN5), GF(BN5 + 1), st));
   }
   { cudaStream_t ws = fk.branch();
   VG_PROF("conv4.wgrad", ws);
@@ -658,7 +667,7 @@ static int step_bwd_impl(const VgStepConfig* cfg, const VgStepIO* io, void* work
   }
   { VG_PROF("bn3.bn_bwd", st);
   VG_TRY(vg_bn_bwd_apply(w.d_a2, e.a2, e.bn3.sums, e.bn3.scale, e.bn3.istd, e.bn3.mistd, B, B, vol(kConv[1].out), 8,
-                         (double)B * vol(kConv[1].out), 1, w.d_a2, GF(BN3), GF(BN3 + 1), st));
+                         (double)B * vol(kConv[1].out), 1, 0, w.d_a2, GF(BN3), GF(BN3 + 1), st));
   }
   { cudaStream_t ws = fk.branch();
   VG_PROF("conv2.wgrad", ws);
@@ -676,7 +685,7 @@ static int step_bwd_impl(const VgStepConfig* cfg, const VgStepIO* io, void* work
   VG_TRY(vg_conv_dgrad(&d1, w.d_a1, PF(CONV1), nullptr, nullptr, io->x, e.bn1.istd, e.bn1.mistd, e.bn1.sums, st));
   }
   { VG_PROF("bn1.bn_bwd", st);
-  VG_TRY(vg_bn_bwd_apply(nullptr, io->x, e.bn1.sums, nullptr, nullptr, nullptr, B, B, V, 1, (double)B * V, 0, nullptr,
+  VG_TRY(vg_bn_bwd_apply(nullptr, io->x, e.bn1.sums, nullptr, nullptr, nullptr, B, B, V, 1, (double)B * V, 0, 0, nullptr,
                          GF(BN1), GF(BN1 + 1), st));
   }
   }

@@ -217,6 +217,19 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
               if (I.qd + j >= qd_end) continue;
+              if constexpr (COUT % 8 == 0) {
+                if (a.aux_bf16) {                 // saved activation stored as bf16: one 16-byte word per 8 channels
+                  const __nv_bfloat16* pb = reinterpret_cast<const __nv_bfloat16*>(a.aux) + I.o0 + (size_t)j * g.sout * plane_out;
+#pragma unroll
+                  for (int i = 0; i < COUT / 8; ++i) {
+                    float f[8];
+                    unpack_bf16x8(ldg_u4(pb + 8 * i), f);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) ax[j][8 * i + e] = f[e];
+                  }
+                  continue;
+                }
+              }
               const float* p = a.aux + I.o0 + (size_t)j * g.sout * plane_out;
               if constexpr (COUT % 4 == 0) {
 #pragma unroll
@@ -268,6 +281,19 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
                 }
               }
               if (a.out) {
+                if constexpr (COUT % 8 == 0) {
+                  if (a.out_bf16) {
+                    __nv_bfloat16* pb = reinterpret_cast<__nv_bfloat16*>(a.out) + I.o0 + (size_t)j * g.sout * plane_out;
+#pragma unroll
+                    for (int i = 0; i < COUT / 8; ++i) {
+                      float f[8];
+#pragma unroll
+                      for (int e = 0; e < 8; ++e) f[e] = y[8 * i + e];
+                      reinterpret_cast<uint4*>(pb)[i] = pack_bf16x8(f);
+                    }
+                    continue;
+                  }
+                }
                 float* p = a.out + I.o0 + (size_t)j * g.sout * plane_out;
                 if constexpr (COUT % 4 == 0) {
 #pragma unroll
@@ -327,6 +353,9 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
       const int npairs = nblocks * H2 + (pl.NPAIR - H2);
       const int grp = n / g.group_size;
       const float* in_n = a.in + (size_t)n * g.in_img;
+      // the same tensor when it is stored as bf16 (CIN == 8: a voxel is ONE 16-byte word, already the staged format)
+      const __nv_bfloat16* in_nb = reinterpret_cast<const __nv_bfloat16*>(a.in) + (size_t)n * g.in_img;
+      const bool in16 = CIN == 8 && a.in_bf16 != 0;
       float sc[CIN], sh[CIN];
 #pragma unroll
       for (int c = 0; c < CIN; ++c) {
@@ -366,9 +395,14 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
             for (int k = 0; k < MAXC; ++k) {
               if constexpr (CIN == 8) {
                 if (p_ok && goff[0][k] >= 0) {
-                  const float4* p = reinterpret_cast<const float4*>(base + goff[0][k]);
-                  v[hf][k][0] = __ldg(p);
-                  v[hf][k][1] = __ldg(p + 1);
+                  if (in16) {
+                    const uint4 q = ldg_u4(in_nb + (size_t)ip * plane_in + goff[0][k]);
+                    v[hf][k][0] = make_float4(__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w));
+                  } else {
+                    const float4* p = reinterpret_cast<const float4*>(base + goff[0][k]);
+                    v[hf][k][0] = __ldg(p);
+                    v[hf][k][1] = __ldg(p + 1);
+                  }
                 }
               } else {
 #pragma unroll
@@ -394,11 +428,23 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
               uint4 pk = make_uint4(0u, 0u, 0u, 0u);
               if (p_ok && goff[0][k] >= 0) {
                 if constexpr (CIN == 8) {
+                  if (in16) {
+                    const float4 raw = v[hf][k][0];
+                    pk = make_uint4(__float_as_uint(raw.x), __float_as_uint(raw.y), __float_as_uint(raw.z), __float_as_uint(raw.w));
+                    if (affine) {
+                      float f[8];
+                      unpack_bf16x8(pk, f);
+#pragma unroll
+                      for (int e = 0; e < 8; ++e) f[e] = fmaf(f[e], sc[e], sh[e]);
+                      pk = pack_bf16x8(f);
+                    }
+                  } else {
                   const float4 lo = v[hf][k][0], hi = v[hf][k][1];
                   pk = make_uint4(pack_bf16(fmaf(lo.x, sc[0], sh[0]), fmaf(lo.y, sc[1], sh[1])),
                                   pack_bf16(fmaf(lo.z, sc[2], sh[2]), fmaf(lo.w, sc[3], sh[3])),
                                   pack_bf16(fmaf(hi.x, sc[4], sh[4]), fmaf(hi.y, sc[5], sh[5])),
                                   pack_bf16(fmaf(hi.z, sc[6], sh[6]), fmaf(hi.w, sc[7], sh[7])));
+                  }
                 } else {
                   // one input channel: the K-chunk of a row is its own voxel and the next span_w voxels along w
                   float f[3];
@@ -475,9 +521,14 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
                 for (int k = 0; k < MAXC; ++k)
                   if (pok[hf] && goff[sg][k] >= 0) {
                     if constexpr (CIN == 8) {
+                      if (in16) {
+                        const uint4 q = ldg_u4(in_nb + (size_t)ip * plane_in + goff[sg][k]);
+                        v[hf][sg][k][0] = make_float4(__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w));
+                      } else {
                       const float4* p = reinterpret_cast<const float4*>(base + goff[sg][k]);
                       v[hf][sg][k][0] = __ldg(p);
                       v[hf][sg][k][1] = __ldg(p + 1);
+                      }
                     } else {
                       v[hf][sg][k][0] = make_float4(0.f, 0.f, 0.f, 0.f);
                       if (0 < wlim[k]) v[hf][sg][k][0].x = __ldg(base + goff[sg][k]);
@@ -496,11 +547,23 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
                   uint4 pk = make_uint4(0u, 0u, 0u, 0u);
                   if (pok[hf] && goff[sg][k] >= 0) {
                     if constexpr (CIN == 8) {
+                      if (in16) {
+                        const float4 raw = v[hf][sg][k][0];
+                        pk = make_uint4(__float_as_uint(raw.x), __float_as_uint(raw.y), __float_as_uint(raw.z), __float_as_uint(raw.w));
+                        if (affine) {
+                          float f[8];
+                          unpack_bf16x8(pk, f);
+#pragma unroll
+                          for (int e = 0; e < 8; ++e) f[e] = fmaf(f[e], sc[e], sh[e]);
+                          pk = pack_bf16x8(f);
+                        }
+                      } else {
                       const float4 lo = v[hf][sg][k][0], hi = v[hf][sg][k][1];
                       pk = make_uint4(pack_bf16(fmaf(lo.x, sc[0], sh[0]), fmaf(lo.y, sc[1], sh[1])),
                                       pack_bf16(fmaf(lo.z, sc[2], sh[2]), fmaf(lo.w, sc[3], sh[3])),
                                       pack_bf16(fmaf(hi.x, sc[4], sh[4]), fmaf(hi.y, sc[5], sh[5])),
                                       pack_bf16(fmaf(hi.z, sc[6], sh[6]), fmaf(hi.w, sc[7], sh[7])));
+                      }
                     } else {
                       const float4 t = v[hf][sg][k][0];
                       const float f0 = 0 < wlim[k] ? fmaf(t.x, sc[0], sh[0]) : 0.f;

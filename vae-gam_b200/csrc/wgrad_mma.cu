@@ -15,6 +15,7 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace vg {
 
@@ -32,6 +33,7 @@ struct WmGeom {
   int wst_t, wst_ci, wst_co;
   int ntaps, tg, taps_per_group;
   uint32_t mul_tH, mul_tW, mul_sH, mul_sW;   // ceil(2^32 / d) for the staging index decomposition (0: d == 1)
+  int x_bf16, y_bf16;    // x / dy stored as bf16 (8 or 16 channels): staged by a straight 16-byte copy when nothing is folded
 };
 
 __device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
@@ -60,7 +62,7 @@ template <int C, bool BIAS, int UV>
 __device__ __forceinline__ void stage_box_bf16(__nv_bfloat16* dst, const float* __restrict__ src, int oD, int oH, int oW,
                                                int bh, int bw, int nvox, uint32_t mul_h, uint32_t mul_w, int gD, int gH,
                                                int gW, const float* sc, const float* sh, const int (&own)[6],
-                                               float (&bs)[8]) {
+                                               float (&bs)[8], bool src16 = false) {
   constexpr int PER = C >= 8 ? C / 8 : 1;        // 16-byte bf16 chunks per voxel
   constexpr int U = C >= 8 ? UV : 4;             // elements in flight per thread (registers are shared with the accumulators)
   const int nel = nvox * PER;
@@ -83,9 +85,14 @@ __device__ __forceinline__ void stage_box_bf16(__nv_bfloat16* dst, const float* 
         if (BIAS && gd >= own[0] && gd < own[1] && gh >= own[2] && gh < own[3] && gw >= own[4] && gw < own[5]) state[u] = 3;
         const size_t off = (((size_t)gd * gH + gh) * gW + gw) * C;
         if constexpr (C >= 8) {
-          const float4* p = reinterpret_cast<const float4*>(src + off) + part * 2;
-          va[u] = __ldg(p);
-          vb[u] = __ldg(p + 1);
+          if (src16) {
+            const uint4 q = ldg_u4(reinterpret_cast<const __nv_bfloat16*>(src) + off + part * 8);
+            va[u] = make_float4(__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w));
+          } else {
+            const float4* p = reinterpret_cast<const float4*>(src + off) + part * 2;
+            va[u] = __ldg(p);
+            vb[u] = __ldg(p + 1);
+          }
         } else {
           v1[u] = __ldg(src + off);
         }
@@ -97,8 +104,16 @@ __device__ __forceinline__ void stage_box_bf16(__nv_bfloat16* dst, const float* 
       const int e = e0 + u * blockDim.x;
       if constexpr (C >= 8) {
         uint4 pk = make_uint4(0u, 0u, 0u, 0u);
-        if (state[u] >= 2) {
+        if (state[u] >= 2 && src16 && !(BIAS && state[u] == 3) && !sc) {
+          pk = make_uint4(__float_as_uint(va[u].x), __float_as_uint(va[u].y), __float_as_uint(va[u].z), __float_as_uint(va[u].w));
+        } else if (state[u] >= 2) {
           float4 a = va[u], b = vb[u];
+          if (src16) {
+            float f[8];
+            unpack_bf16x8(make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), __float_as_uint(a.w)), f);
+            a = make_float4(f[0], f[1], f[2], f[3]);
+            b = make_float4(f[4], f[5], f[6], f[7]);
+          }
           if (BIAS && state[u] == 3) {
             bs[0] += a.x; bs[1] += a.y; bs[2] += a.z; bs[3] += a.w;
             bs[4] += b.x; bs[5] += b.y; bs[6] += b.z; bs[7] += b.w;
@@ -188,8 +203,12 @@ wgrad_mma_kernel(const __grid_constant__ WmGeom g, const float* __restrict__ x, 
     const int th = tr % g.nTh;
     const int td = tr / g.nTh;
     const int q0d = td * g.tD, q0h = th * g.tH, q0w = tw * g.tW;
-    const float* xn = x + (size_t)n * g.x_img;
-    const float* yn = dy + (size_t)n * g.y_img;
+    // bf16 tensors have the same element offsets at half the element size
+    const bool x16 = g.x_bf16 != 0, y16 = g.y_bf16 != 0;
+    const float* xn = x16 ? reinterpret_cast<const float*>(reinterpret_cast<const __nv_bfloat16*>(x) + (size_t)n * g.x_img)
+                          : x + (size_t)n * g.x_img;
+    const float* yn = y16 ? reinterpret_cast<const float*>(reinterpret_cast<const __nv_bfloat16*>(dy) + (size_t)n * g.y_img)
+                          : dy + (size_t)n * g.y_img;
     const float* sc = in_scale ? in_scale + (n / g.group_size) * (MODE == 0 ? CS : CU) : nullptr;
     const float* sh = in_scale ? in_shift + (n / g.group_size) * (MODE == 0 ? CS : CU) : nullptr;
     __syncthreads();   // previous tile fully consumed
@@ -199,11 +218,11 @@ wgrad_mma_kernel(const __grid_constant__ WmGeom g, const float* __restrict__ x, 
       // dY is the un-shifted tile: tiles partition the output grid
       const int own[6] = {q0d, q0d + g.tD, q0h, q0h + g.tH, q0w, q0w + g.tW};
       stage_box_bf16<CS, false, UV>(Ssh, xn, q0d * g.s, q0h * g.s, q0w * g.s, g.sH, g.sW, box_vox, g.mul_sH, g.mul_sW, g.xD, g.xH,
-                                g.xW, sc, sh, none, bsum);
+                                g.xW, sc, sh, none, bsum, x16);
       if (dbias) stage_box_bf16<CU, true, UV>(Sun, yn, q0d, q0h, q0w, g.tH, g.tW, tile_vox, g.mul_tH, g.mul_tW, g.yD, g.yH, g.yW,
-                                          nullptr, nullptr, own, bsum);
+                                          nullptr, nullptr, own, bsum, y16);
       else stage_box_bf16<CU, false, UV>(Sun, yn, q0d, q0h, q0w, g.tH, g.tW, tile_vox, g.mul_tH, g.mul_tW, g.yD, g.yH, g.yW,
-                                     nullptr, nullptr, none, bsum);
+                                     nullptr, nullptr, none, bsum, y16);
     } else {
       // dY is the shifted box (boxes of neighbouring tiles overlap): a tile owns the outputs
       // [q0*s - p, (q0+t)*s - p), the first / last tile of a dimension also the grid's margins
@@ -211,11 +230,11 @@ wgrad_mma_kernel(const __grid_constant__ WmGeom g, const float* __restrict__ x, 
                           th == 0 ? 0 : q0h * g.s - g.pH, th == g.nTh - 1 ? g.yH : (q0h + g.tH) * g.s - g.pH,
                           tw == 0 ? 0 : q0w * g.s - g.pW, tw == g.nTw - 1 ? g.yW : (q0w + g.tW) * g.s - g.pW};
       stage_box_bf16<CU, false, UV>(Sun, xn, q0d, q0h, q0w, g.tH, g.tW, tile_vox, g.mul_tH, g.mul_tW, g.xD, g.xH, g.xW, sc, sh,
-                                none, bsum);
+                                none, bsum, x16);
       if (dbias) stage_box_bf16<CS, true, UV>(Ssh, yn, q0d * g.s - g.pD, q0h * g.s - g.pH, q0w * g.s - g.pW, g.sH, g.sW, box_vox,
-                                          g.mul_sH, g.mul_sW, g.yD, g.yH, g.yW, nullptr, nullptr, own, bsum);
+                                          g.mul_sH, g.mul_sW, g.yD, g.yH, g.yW, nullptr, nullptr, own, bsum, y16);
       else stage_box_bf16<CS, false, UV>(Ssh, yn, q0d * g.s - g.pD, q0h * g.s - g.pH, q0w * g.s - g.pW, g.sH, g.sW, box_vox,
-                                     g.mul_sH, g.mul_sW, g.yD, g.yH, g.yW, nullptr, nullptr, none, bsum);
+                                     g.mul_sH, g.mul_sW, g.yD, g.yH, g.yW, nullptr, nullptr, none, bsum, y16);
     }
     // zero the un-shifted rows of the last chunk's padding (tile_vox .. 16*nchunks)
     for (int e = threadIdx.x; e < (nchunks * 16 - tile_vox) * CU / 8; e += blockDim.x)
@@ -379,9 +398,14 @@ static int launch_wm(const WmGeom& g, const float* x, const float* dy, const flo
 }
 
 // returns VG_OK, or 1 when the channel pair is not covered (caller falls back to the fp32 kernel)
-int wgrad_mma(const VgConvDesc* d, const float* x, const float* dy, const float* in_scale, const float* in_shift,
+int wgrad_mma(const VgConvDesc* d, const void* x_, const void* dy_, const float* in_scale, const float* in_shift,
               float* dw, float* dbias, cudaStream_t st) {
+  const float* x = static_cast<const float*>(x_);
+  const float* dy = static_cast<const float*>(dy_);
   WmGeom g{};
+  g.x_bf16 = (d->bf16_mask & VG_BF16_X) != 0;
+  g.y_bf16 = (d->bf16_mask & VG_BF16_Y) != 0;
+  if ((g.x_bf16 && d->cin % 8) || (g.y_bf16 && d->cout % 8)) { set_error("bf16 storage needs 8 or 16 channels"); return VG_EINVAL; }
   g.N = d->n; g.group_size = d->group_size;
   g.mode = d->transposed ? 1 : 0;
   g.s = d->stride;

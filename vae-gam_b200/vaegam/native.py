@@ -19,6 +19,7 @@ VG_NUM_PARAMS = 97
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
 # VG_ARITH_* (include/vaegam.h): per-call arithmetic of the convolution kernels
 ARITH_DEFAULT, ARITH_FP32, ARITH_BF16, ARITH_MIXED = 0, 1, 2, 3
+BF16_X, BF16_Y, BF16_DX = 1, 2, 4            # VgConvDesc.bf16_mask
 ARITH_BY_NAME = {"default": ARITH_DEFAULT, "fp32": ARITH_FP32, "bf16": ARITH_BF16, "mixed": ARITH_MIXED}
 VG_BWD_PHASES = 3
 VG_OK, VG_EINVAL = 0, -1
@@ -34,7 +35,7 @@ class VgConvDesc(C.Structure):
     _fields_ = [("transposed", C.c_int32), ("cin", C.c_int32), ("cout", C.c_int32), ("k", C.c_int32 * 3),
                 ("stride", C.c_int32), ("pad", C.c_int32 * 3), ("opad", C.c_int32 * 3), ("in_", C.c_int32 * 3),
                 ("out", C.c_int32 * 3), ("n", C.c_int32), ("group_size", C.c_int32), ("arith", C.c_int32),
-                ("x_img_stride", C.c_int64), ("y_img_stride", C.c_int64)]
+                ("bf16_mask", C.c_int32), ("reserved_", C.c_int32), ("x_img_stride", C.c_int64), ("y_img_stride", C.c_int64)]
 
 
 class VgGainParams(C.Structure):
@@ -106,7 +107,7 @@ SIGNATURES = {
     "vg_conv_wgrad": (_I, [C.POINTER(VgConvDesc), _P, _P, _P, _P, _P, _P, _P]),
     "vg_bn_stats": (_I, [_P, _I, _I, _LL, _I, _P, _P]),
     "vg_bn_finalize": (_I, [_P, _P, _P, _I, _I, _D, _P, _P, _P, _P, _P]),
-    "vg_bn_bwd_apply": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _LL, _I, _D, _I, _P, _P, _P, _P]),
+    "vg_bn_bwd_apply": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _LL, _I, _D, _I, _I, _P, _P, _P, _P]),
     "vg_nchw_to_nhwc": (_I, [_P, _P, _I, _I, _LL, _P]),
     "vg_nhwc_to_nchw": (_I, [_P, _P, _I, _I, _LL, _P]),
     "vg_linear_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
@@ -198,9 +199,10 @@ def profile_collect():
 
 
 def conv_desc(transposed, cin, cout, k, stride, in_, n, group_size, pad=(0, 0, 0), opad=(0, 0, 0),
-              x_img_stride=0, y_img_stride=0, arith=ARITH_DEFAULT) -> VgConvDesc:
+              x_img_stride=0, y_img_stride=0, arith=ARITH_DEFAULT, bf16_mask=0) -> VgConvDesc:
     d = VgConvDesc()
     d.arith = arith
+    d.bf16_mask = bf16_mask
     d.transposed, d.cin, d.cout, d.stride = int(transposed), cin, cout, stride
     for i in range(3):
         d.k[i], d.pad[i], d.opad[i], d.in_[i] = k[i], pad[i], opad[i], in_[i]
