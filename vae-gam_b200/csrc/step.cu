@@ -402,7 +402,8 @@ static int run_decoder(const VgStepIO* io, const DecWs& d, const float* zcat, in
   VgConvDesc c1 = make_desc(kConvT[0], nd, group, arith), c2 = make_desc(kConvT[1], nd, group, arith),
              c3 = make_desc(kConvT[2], nd, group, arith), c4 = make_desc(kConvT[3], nd, group, arith),
              c5 = make_desc(kConvT[4], nd, group, arith, 0, out_stride);
-  if (arith == VG_ARITH_BF16) { c4.bf16_mask = VG_BF16_Y; c5.bf16_mask = VG_BF16_X; }   // t4 is stored as bf16
+  // tensor-core arithmetic: t3 and t4 live in HBM as bf16 (they feed the TMA-staged convt4 / convt5 directly)
+  if (arith == VG_ARITH_BF16) { c3.bf16_mask = VG_BF16_Y; c4.bf16_mask = VG_BF16_X | VG_BF16_Y; c5.bf16_mask = VG_BF16_X; }
   { VG_PROF("convt1.fwd", st);
   VG_TRY(vg_conv_fwd(&c1, d.t0, PF(CONVT1), PF(CONVT1 + 1), d.bnt1.scale, d.bnt1.shift, d.t1, VG_ACT_RELU, nullptr, st));
   }
@@ -553,7 +554,8 @@ static int step_bwd_impl(const VgStepConfig* cfg, const VgStepIO* io, void* work
   VgConvDesc c1 = make_desc(kConvT[0], nd, B, ar), c2 = make_desc(kConvT[1], nd, B, ar), c3 = make_desc(kConvT[2], nd, B, ar),
              c4 = make_desc(kConvT[3], nd, B, ar), c5 = make_desc(kConvT[4], nd, B, ar, 0, VP);
   const bool big16 = ar == VG_ARITH_BF16;
-  if (big16) { c4.bf16_mask = VG_BF16_Y; c5.bf16_mask = VG_BF16_X; }     // convt4: y = t4, dy = its gradient; convt5: x = t4
+  // convt5: x = t4 (bf16); convt4: x = t3, y = t4 and both their gradients (bf16); convt3: y = t3 and its gradient
+  if (big16) { c3.bf16_mask = VG_BF16_Y; c4.bf16_mask = VG_BF16_X | VG_BF16_Y | VG_BF16_DX; c5.bf16_mask = VG_BF16_X; }
   { cudaStream_t ws = fk.branch();
   VG_PROF("convt5.wgrad", ws);
   VG_TRY(vg_conv_wgrad(&c5, d.t4, w.dpre5, d.bnt5.scale, d.bnt5.shift, GF(CONVT5), GF(CONVT5 + 1), ws));

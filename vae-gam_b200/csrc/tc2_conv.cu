@@ -27,7 +27,9 @@
 //                        tcgen05.mma list of a (block, phase)
 // Pipelines: full/empty mbarriers per ring slot (producers <-> MMA via tcgen05.commit), and
 // full/empty per accumulator buffer (MMA <-> epilogue), accumulators double-buffered in TMEM.
+#include <cuda.h>          // CUtensorMap (the encoder itself is fetched through cudaGetDriverEntryPoint: no libcuda link)
 #include <stdlib.h>
+#include <string.h>
 
 #include <type_traits>
 
@@ -67,6 +69,11 @@ struct T2Plan {
   int pps;                     // input planes per ring slot: 2 (1 or 8 channels) or 1 (16 channels: K = the plane's two halves)
   int nsg;                     // (h,w)-parity sub-grids per staged plane: 1, or 4 when sd == 2
   int ppb;                     // ring slots consumed per block of OB output planes
+  // TMA-direct staging (bf16 channels-last input with 8 channels, unit input stride): a tile is HB whole h-lines of
+  // the row frame (rows = HB * PW), a ring slot is two TMA boxes [8 ch][PW][HB + halo lines] — exactly the staged
+  // operand layout, out-of-range voxels zero-filled by the TMA unit.  hb == 0: staging by the producer warps.
+  int hb, box_h;
+  int groups;                  // BatchNorm groups of the launch when the fold moves into the weights (TMA mode): a CTA serves ONE group
   T2Phase ph[T2_MAX_PH];
   T2Mma mma[T2_MAX_MMA];
   T2Blk blk[T2_MAX_BLK];
@@ -75,14 +82,30 @@ struct T2Plan {
 
 // roles per (cin, cout): the side that moves more bytes gets more warps
 __host__ __device__ constexpr int t2_epi_sets(int cin, int cout, int sd) { return (sd == 2 || (cin == 8 && cout == 1)) ? 1 : 2; }
+
+// ---- TMA (cp.async.bulk.tensor) primitives
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// one 5-D box (c, w, h, d, n) of the tensor map -> shared memory; completion is signalled on the mbarrier (bytes)
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3,
+                                            int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+constexpr int T2_MAX_CLS = 5;      // tap-validity classes per output dimension (k <= 5 would give more; TMA mode has k = 3)
 __host__ __device__ constexpr int t2_max_chunk(int cin, int es, int sd) {
   return sd == 2 ? 1 : (cin == 8 ? (es == 1 ? 2 : 4) : (cin == 16 ? (es == 1 ? 2 : 3) : (es == 1 ? 3 : 5)));
 }
 
-template <int CIN, int COUT, int SD>
+template <int CIN, int COUT, int SD, bool TMA>
 __global__ void __launch_bounds__(T2_THREADS, 1)
-tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_constant__ T2Plan pl) {
-  constexpr int ES = t2_epi_sets(CIN, COUT, SD);
+tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_constant__ T2Plan pl,
+           const __grid_constant__ CUtensorMap tmap) {
+  static_assert(!TMA || (CIN == 8 && SD == 1), "TMA-direct staging: 8 bf16 channels = one 16-byte word per voxel, unit stride");
+  constexpr int ES = TMA ? 2 : t2_epi_sets(CIN, COUT, SD);
   constexpr int NSG = SD == 2 ? 4 : 1;
   constexpr int EPI_WARPS = 4 * ES, PROD_WARPS = 12 - EPI_WARPS, PT = PROD_WARPS * 32;
   constexpr int MAXC = t2_max_chunk(CIN, ES, SD);
@@ -94,6 +117,12 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
   __shared__ uint32_t tmem_base_s;
   __shared__ int lut[T2_MAX_PH][45];
   __shared__ float s_bias[16];
+  // TMA mode: the BatchNorm shift cannot be added to the staged operand any more, so it becomes a bias that
+  // depends on which taps fall inside the input — a (class_d, class_h, class_w) table built once per CTA
+  __shared__ float s_btab[TMA ? T2_MAX_CLS * T2_MAX_CLS * T2_MAX_CLS * COUT : 1];
+  __shared__ float s_tapsum[TMA ? 27 * COUT : 1];
+  __shared__ uint8_t s_cls[3][64], s_cmask[3][8];
+  __shared__ int s_ncls[3];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int SRB = pl.SR * 16;                   // bytes per staged plane
@@ -105,7 +134,7 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
   // ---------------------------------------------------------------- one-time setup
   if (tid == 0) {
     for (int s = 0; s < pl.R; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), PT);
+      mbar_init(smem_u32(&full_bar[s]), TMA ? 1u : (uint32_t)PT);
       mbar_init(smem_u32(&empty_bar[s]), (uint32_t)pl.nrb);
     }
     for (int b = 0; b < 2; ++b) {
@@ -137,6 +166,19 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
+  // Column schedule.  Default: columns (image, tile, d-chunk) dealt round-robin to the persistent CTAs.  TMA mode
+  // with a BatchNorm fold: the scale lives in the weight tiles, so a CTA is pinned to ONE statistics group
+  // (group = blockIdx % groups) and walks that group's columns only.
+  const int cols_per_img = pl.ntiles * pl.ndchunks;
+  const bool grouped = TMA && pl.groups > 1;
+  const int my_grp = grouped ? (int)(blockIdx.x % pl.groups) : 0;
+  const int col_first = grouped ? (int)(blockIdx.x / pl.groups) : (int)blockIdx.x;
+  const int col_step = grouped ? (int)((gridDim.x - my_grp + pl.groups - 1) / pl.groups) : (int)gridDim.x;
+  const int col_count = grouped ? g.group_size * cols_per_img : g.N * cols_per_img;
+  const int col_img0 = grouped ? my_grp * g.group_size : 0;
+  const float* fold_scale = (TMA && a.in_scale) ? a.in_scale + (size_t)my_grp * CIN : nullptr;
+  const float* fold_shift = (TMA && a.in_scale) ? a.in_shift + (size_t)my_grp * CIN : nullptr;
+
   // Toeplitz weight blocks: element (n, k) of a block = W[tap(i - j, dh, dw)][ci][co], canonical K-major layout.
   // The raw weights (a few KB, contiguous) are first copied into the still unused ring area, coalesced.
   {
@@ -162,10 +204,54 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
         if (ddr >= 0 && ddr <= pl.span_d && dwr <= pl.span_w) {
           const int widx = lut[bk.ph][ddr * 9 + bk.dh * 3 + dwr];
           if (widx >= 0) w = wraw[widx * g.wst_t + ci * g.wst_ci + co * g.wst_co];
+          if constexpr (TMA) { if (fold_scale) w *= __ldg(fold_scale + ci); }     // BatchNorm scale folded into the weights
         }
         dst[(((n >> 3) * 256 + chunk * 128 + (n & 7) * 16) >> 1) + el] = __float2bfloat16(w);
       }
     }
+  }
+  if constexpr (TMA) {
+    // ---- per-dimension tap-validity classes and the bias table (single phase, unit strides: the only layers folded)
+    const float* wraw = reinterpret_cast<const float*>(ring);
+    if (tid < 3) {
+      const int In = tid == 0 ? g.inD : (tid == 1 ? g.inH : g.inW), Out = tid == 0 ? g.outD : (tid == 1 ? g.outH : g.outW);
+      const int lo = tid == 0 ? pl.lo_d : (tid == 1 ? pl.lo_h : pl.lo_w), span = tid == 0 ? pl.span_d : (tid == 1 ? pl.span_h : pl.span_w);
+      int ncls = 0;
+      for (int o = 0; o < Out && o < 64; ++o) {
+        int m = 0;
+        if (fold_shift)
+          for (int k = 0; k <= span; ++k) { const int i = o + lo + k; if (i >= 0 && i < In) m |= 1 << k; }
+        int c = -1;
+        for (int q = 0; q < ncls; ++q) if (s_cmask[tid][q] == m) c = q;
+        if (c < 0 && ncls < T2_MAX_CLS) { c = ncls; s_cmask[tid][ncls++] = (uint8_t)m; }
+        s_cls[tid][o] = (uint8_t)(c < 0 ? 0 : c);
+      }
+      s_ncls[tid] = ncls < 1 ? 1 : ncls;
+    }
+    for (int e = tid; e < 27 * COUT; e += T2_THREADS) {       // per-tap sum over input channels of shift * W
+      const int t = e / COUT, co = e - t * COUT;
+      float sacc = 0.f;
+      const int widx = (t < 45 && pl.nph == 1) ? lut[0][t] : -1;   // t = kd * 9 + kh * 3 + kw (relative to lo_*)
+      if (fold_shift && widx >= 0)
+        for (int ci = 0; ci < CIN; ++ci) sacc = fmaf(__ldg(fold_shift + ci), wraw[widx * g.wst_t + ci * g.wst_ci + co * g.wst_co], sacc);
+      s_tapsum[e] = sacc;
+    }
+    __syncthreads();
+    const int nd_ = s_ncls[0], nh_ = s_ncls[1], nw_ = s_ncls[2];
+    for (int e = tid; e < nd_ * nh_ * nw_ * COUT; e += T2_THREADS) {
+      const int co = e % COUT, cw = (e / COUT) % nw_, ch = (e / (COUT * nw_)) % nh_, cd = e / (COUT * nw_ * nh_);
+      float bsum = s_bias[co];
+      const int md = s_cmask[0][cd], mh = s_cmask[1][ch], mw = s_cmask[2][cw];
+      for (int kd = 0; kd < 3; ++kd)
+        for (int kh = 0; kh < 3; ++kh)
+          for (int kw = 0; kw < 3; ++kw)
+            if (((md >> kd) & 1) && ((mh >> kh) & 1) && ((mw >> kw) & 1)) bsum += s_tapsum[(kd * 9 + kh * 3 + kw) * COUT + co];
+      s_btab[e] = bsum;
+    }
+    __syncthreads();
+    // the raw weights are no longer needed: clear the ring (rows beyond a TMA box are read by the last row block's
+    // MMAs and must at least be finite)
+    for (int i = tid; i < (pl.R * PAIRB) / 16; i += T2_THREADS) reinterpret_cast<uint4*>(ring)[i] = make_uint4(0u, 0u, 0u, 0u);
   }
   if (warp < 4) {                               // all MMAs accumulate: start from zero
     for (int c = 0; c < pl.tmem_cols; c += 16) tmem_zero16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c);
@@ -176,7 +262,6 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
   __syncthreads();
   tc_fence_after();
 
-  const int ncols = g.N * pl.ntiles * pl.ndchunks;
   int pair_base = 0, acc_base = 0;              // running counters, identical in every role
 
   if (warp < EPI_WARPS) {
@@ -185,9 +270,10 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
     const int eset = warp >> 2, etid = tid & 127;            // TMEM lane = etid
     const int ipr = pl.ACCW >> 4, nitems = pl.nrb * ipr;     // 16-column items per row block / per accumulator
     const size_t plane_out = (size_t)g.outH * g.outW * COUT;
-    struct Item { int rb, k, qd; bool row_ok; size_t o0; };
-    for (int col = blockIdx.x; col < ncols; col += gridDim.x) {
-      const int dc = col % pl.ndchunks, t = (col / pl.ndchunks) % pl.ntiles, n = col / (pl.ndchunks * pl.ntiles);
+    struct Item { int rb, k, qd, bofs; bool row_ok; size_t o0; };
+    const int cls_hw = TMA ? s_ncls[1] * s_ncls[2] * COUT : 0;
+    for (int col = col_first; col < col_count; col += col_step) {
+      const int dc = col % pl.ndchunks, t = (col / pl.ndchunks) % pl.ntiles, n = col_img0 + col / cols_per_img;
       const int qd0 = dc * pl.dchunk, qd1 = min(pl.qDmax, qd0 + pl.dchunk);
       const int nblocks = (qd1 - qd0 + pl.OB - 1) / pl.OB;
       const int grp = n / g.group_size;
@@ -205,9 +291,18 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
           const int qd_end = min((int)P.qD, qd1);
           auto setup = [&](int it, Item& I) {
             I.rb = it / ipr; I.k = it - I.rb * ipr;
-            const int r = t * pl.TR + I.rb * 128 + etid;
-            const int qh = r / pl.PW, qw = r - qh * pl.PW;
-            I.row_ok = qh < P.qH && qw < P.qW;
+            int qh, qw;
+            if constexpr (TMA) {                  // tile = hb whole lines of the row frame
+              const int rl = I.rb * 128 + etid, lh = rl / pl.PW;
+              qh = t * pl.hb + lh; qw = rl - lh * pl.PW;
+              I.row_ok = lh < pl.hb && qh < P.qH && qw < P.qW;
+              I.bofs = I.row_ok ? (s_cls[1][min(qh, 63)] * s_ncls[2] + s_cls[2][min(qw, 63)]) * COUT : 0;
+            } else {
+              const int r = t * pl.TR + I.rb * 128 + etid;
+              qh = r / pl.PW; qw = r - qh * pl.PW;
+              I.row_ok = qh < P.qH && qw < P.qW;
+              I.bofs = 0;
+            }
             I.qd = qd0 + b * pl.OB + I.k * NJ;
             I.o0 = (size_t)n * g.out_img + (size_t)(I.qd * g.sout + P.rD) * plane_out +
                    ((size_t)(qh * g.sout + P.rH) * g.outW + (size_t)(qw * g.sout + P.rW)) * COUT;
@@ -221,11 +316,10 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
                 if (a.aux_bf16) {                 // saved activation stored as bf16: one 16-byte word per 8 channels
                   const __nv_bfloat16* pb = reinterpret_cast<const __nv_bfloat16*>(a.aux) + I.o0 + (size_t)j * g.sout * plane_out;
 #pragma unroll
-                  for (int i = 0; i < COUT / 8; ++i) {
-                    float f[8];
-                    unpack_bf16x8(ldg_u4(pb + 8 * i), f);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) ax[j][8 * i + e] = f[e];
+                  for (int i = 0; i < COUT / 8; ++i) {      // raw words only: unpacked at use, so the load stays in flight
+                    const uint4 q = ldg_u4(pb + 8 * i);
+                    ax[j][4 * i] = __uint_as_float(q.x); ax[j][4 * i + 1] = __uint_as_float(q.y);
+                    ax[j][4 * i + 2] = __uint_as_float(q.z); ax[j][4 * i + 3] = __uint_as_float(q.w);
                   }
                   continue;
                 }
@@ -255,20 +349,34 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
             for (int j = 0; j < NJ; ++j) {
               if (I.qd + j >= qd_end) continue;
               float y[COUT];
+              const float* bsrc = s_bias;
+              if constexpr (TMA) bsrc = s_btab + s_cls[0][min(I.qd + j, 63)] * cls_hw + I.bofs;
 #pragma unroll
               for (int c = 0; c < COUT; ++c) {
-                float v = __uint_as_float(rr[j * COUT + c]) + s_bias[c];
+                float v = __uint_as_float(rr[j * COUT + c]) + bsrc[c];
                 if (a.act == VG_ACT_RELU) v = fmaxf(v, 0.f);
                 else if (a.act == VG_ACT_SIGMOID) v = 1.f / (1.f + __expf(-v));
                 y[c] = v;
               }
+              float av[COUT];
+#pragma unroll
+              for (int c = 0; c < COUT; ++c) av[c] = ax[j][c];
+              if constexpr (COUT % 8 == 0) {
+                if (a.aux_bf16) {
+#pragma unroll
+                  for (int c = 0; c < COUT / 2; ++c) {
+                    const uint32_t wv = __float_as_uint(ax[j][c]);
+                    av[2 * c] = bf16_lo(wv); av[2 * c + 1] = bf16_hi(wv);
+                  }
+                }
+              }
               if (a.aux_mode == 1) {
 #pragma unroll
-                for (int c = 0; c < COUT; ++c) y[c] = ax[j][c] > 0.f ? y[c] : 0.f;
+                for (int c = 0; c < COUT; ++c) y[c] = av[c] > 0.f ? y[c] : 0.f;
               } else if (a.aux_mode == 2) {
 #pragma unroll
                 for (int c = 0; c < COUT; ++c) {
-                  const float xh = fmaf(ax[j][c], istd[c], -mistd[c]);
+                  const float xh = fmaf(av[c], istd[c], -mistd[c]);
                   s1[c] += y[c];
                   s2[c] = fmaf(y[c], xh, s2[c]);
                 }
@@ -341,13 +449,42 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
       pair_base += nblocks * H2 + (pl.NPAIR - H2);
       acc_base += nblocks * pl.nph;
     }
+  } else if (TMA && warp < T2_MMA_WARP) {
+    // ================================================================ TMA producer: one elected lane of one warp
+    if constexpr (TMA) {
+      if (warp == EPI_WARPS) {
+        const uint32_t ring_a = smem_u32(ring);
+        const uint32_t slot_tx = (uint32_t)(2 * pl.box_h * pl.PW * 16);     // two boxes of [8 ch][PW][box_h] bf16
+        for (int col = col_first; col < col_count; col += col_step) {
+          const int dc = col % pl.ndchunks, t = (col / pl.ndchunks) % pl.ntiles, n = col_img0 + col / cols_per_img;
+          const int qd0 = dc * pl.dchunk, qd1 = min(pl.qDmax, qd0 + pl.dchunk);
+          const int nblocks = (qd1 - qd0 + pl.OB - 1) / pl.OB;
+          const int npairs = nblocks * H2 + (pl.NPAIR - H2);
+          for (int P = 0; P < npairs; ++P) {
+            const int G = pair_base + P, slot = G % pl.R, use = G / pl.R;
+            if (use > 0) mbar_wait(smem_u32(&empty_bar[slot]), (uint32_t)((use - 1) & 1));
+            if (elect_one()) {
+              const uint32_t bar = smem_u32(&full_bar[slot]);
+              mbar_arrive_expect_tx(bar, slot_tx);
+#pragma unroll
+              for (int hf = 0; hf < 2; ++hf)      // plane ip may lie outside the input: the whole box is then zero-filled
+                tma_load_5d(ring_a + (uint32_t)slot * (uint32_t)PAIRB + (uint32_t)hf * (uint32_t)SRB, &tmap, bar, 0, pl.lo_w,
+                            t * pl.hb + pl.lo_h, qd0 + pl.lo_d + 2 * P + hf, n);
+            }
+            __syncwarp();
+          }
+          pair_base += npairs;
+          acc_base += nblocks * pl.nph;
+        }
+      }
+    }
   } else if (warp < T2_MMA_WARP) {
     // ================================================================ producer warps
     const int ptid = tid - EPI_WARPS * 32;
     const bool affine = a.in_scale != nullptr;
     const size_t plane_in = (size_t)g.inH * g.inW * CIN;
-    for (int col = blockIdx.x; col < ncols; col += gridDim.x) {
-      const int dc = col % pl.ndchunks, t = (col / pl.ndchunks) % pl.ntiles, n = col / (pl.ndchunks * pl.ntiles);
+    for (int col = col_first; col < col_count; col += col_step) {
+      const int dc = col % pl.ndchunks, t = (col / pl.ndchunks) % pl.ntiles, n = col_img0 + col / cols_per_img;
       const int qd0 = dc * pl.dchunk, qd1 = min(pl.qDmax, qd0 + pl.dchunk);
       const int nblocks = (qd1 - qd0 + pl.OB - 1) / pl.OB;
       const int npairs = nblocks * H2 + (pl.NPAIR - H2);
@@ -590,7 +727,7 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
     const uint32_t ring16 = (smem_u32(ring) >> 4) + (uint32_t)rb * 128u, w16 = smem_u32(wts) >> 4;
     const uint32_t lbo_field = ((uint32_t)(NSG * SRB) >> 4) << 16;
     const uint32_t a_hi = (128u >> 4) | (1u << 14), b_hi = (256u >> 4) | (1u << 14);
-    for (int col = blockIdx.x; col < ncols; col += gridDim.x) {
+    for (int col = col_first; col < col_count; col += col_step) {
       const int dc = col % pl.ndchunks;
       const int qd0 = dc * pl.dchunk, qd1 = min(pl.qDmax, qd0 + pl.dchunk);
       const int nblocks = (qd1 - qd0 + pl.OB - 1) / pl.OB;
@@ -649,7 +786,11 @@ static constexpr int kT2SmemBudget = 212 * 1024;
 // merged: gs[0] with every phase's taps (Tap::pad_ = phase).
 static inline int t2_ceil_div(int a, int b) { return a >= 0 ? (a + b - 1) / b : -((-a) / b); }
 
-static bool t2_build_plan(int cin, int cout, const Geom* gs, int ng, Geom& merged, T2Plan& pl) {
+// tma: TMA-direct staging requested (bf16 input; see T2Plan::hb) — falls back to producer-warp staging (returns
+// true with pl.hb == 0) when the geometry is outside what the TMA path covers.
+static bool t2_build_plan(int cin, int cout, const Geom* gs, int ng, Geom& merged, T2Plan& pl, bool tma = false,
+                          bool affine = false) {
+  pl.hb = 0; pl.box_h = 0; pl.groups = 1;
   if (ng < 1 || ng > T2_MAX_PH) return false;
   if (cin != 1 && cin != 8 && cin != 16) return false;
   if (cout != 1 && cout != 8 && cout != 16) return false;
@@ -769,6 +910,47 @@ static bool t2_build_plan(int cin, int cout, const Geom* gs, int ng, Geom& merge
   pl.wbytes = (woff + 1023) & ~1023;
   if (pl.wbytes > 96 * 1024) return false;
 
+  if (tma && cin == 8 && sd == 1 && (ng == 1 || !affine) && pl.span_d <= 2 && merged.outD <= 64 && merged.outH <= 64 &&
+      merged.outW <= 64 && pl.PW <= 256) {
+    // ---- TMA-direct staging: tile = hb whole lines of the row frame, a slot = two boxes [8][PW][hb + halo]
+    int nrb_max = 512 / (2 * pl.ACCW);
+    if (nrb_max > 4) nrb_max = 4;
+    int hb = (128 * nrb_max) / pl.PW;
+    if (hb > qmax[1]) hb = qmax[1];
+    if (hb >= 1) {
+      const int nt = (qmax[1] + hb - 1) / hb;
+      hb = (qmax[1] + nt - 1) / nt;                        // balanced tiles
+      const int nrb = (hb * pl.PW + 127) / 128;
+      const int box_h = hb + sm_h;
+      int sr = box_h * pl.PW;
+      const int reach = 128 * nrb + sm_h * pl.PW + sm_w;   // rows the last row block's shifted windows touch
+      if (sr < reach) sr = reach;
+      sr = (sr + 7) & ~7;
+      const size_t slot = (size_t)2 * sr * 16;
+      int r = pl.NPAIR + 3;
+      if (r > T2_MAX_RING) r = T2_MAX_RING;
+      while (r > pl.NPAIR + 1 && (size_t)r * slot + pl.wbytes > (size_t)kT2SmemBudget) --r;
+      if ((size_t)r * slot + pl.wbytes <= (size_t)kT2SmemBudget && box_h <= 256) {
+        pl.hb = hb; pl.box_h = box_h; pl.nrb = nrb; pl.TR = 128 * nrb; pl.SR = sr; pl.R = r;
+        pl.ntiles = nt;
+        pl.groups = affine ? merged.N / merged.group_size : 1;
+        for (int m = 0; m < nmma; ++m) pl.mma[m].a_shift = (uint32_t)(m_sg[m] * pl.SR + m_mh[m] * pl.PW + m_mw[m]);
+        int tc = 32;
+        while (tc < 2 * pl.nrb * pl.ACCW) tc <<= 1;
+        if (tc > 512) return false;
+        pl.tmem_cols = tc;
+        const int nblocks_all = (pl.qDmax + pl.OB - 1) / pl.OB;
+        const long long cols = (long long)merged.N * pl.ntiles;
+        const long long want = 2LL * vg_sm_count();
+        int nch = (int)((want + cols - 1) / cols);
+        if (nch > nblocks_all) nch = nblocks_all;
+        if (nch < 1) nch = 1;
+        pl.dchunk = ((nblocks_all + nch - 1) / nch) * pl.OB;
+        pl.ndchunks = (pl.qDmax + pl.dchunk - 1) / pl.dchunk;
+        return true;
+      }
+    }
+  }
   // rows per tile: as many 128-row blocks as TMEM (2 buffers), the producers' reach and shared memory allow
   const int es = t2_epi_sets(cin, cout, sd);
   const int max_sr = t2_max_chunk(cin, es, sd) * (12 - 4 * es) * 32;
@@ -836,14 +1018,64 @@ int tc2_describe(int cin, int cout, const Geom* gs, int ng, char* buf, size_t ca
                   (size_t)pl.R * 2 * pl.nsg * pl.SR * 16 + pl.wbytes, pl.dchunk, pl.ndchunks, cols);
 }
 
-template <int CIN, int COUT, int SD>
+// ---- TMA tensor map of a channels-last bf16 tensor (N, D, H, W, 8): dims fastest-first (c, w, h, d, n); a box is
+// [8][PW][box_h][1][1], out-of-range coordinates (the halo of a transposed convolution, planes beyond the
+// volume) are zero-filled by the hardware.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tma_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    else
+      (void)cudaGetLastError();
+  }
+  return fn;
+}
+static bool tma_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("VAEGAM_TMA"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on == 1 && tma_encoder() != nullptr;
+}
+static int make_tmap(const Geom& g, const T2Plan& pl, const void* base, CUtensorMap& tm) {
+  const cuuint64_t dims[5] = {8, (cuuint64_t)g.inW, (cuuint64_t)g.inH, (cuuint64_t)g.inD, (cuuint64_t)g.N};
+  const cuuint64_t strides[4] = {16, (cuuint64_t)g.inW * 16, (cuuint64_t)g.inW * g.inH * 16, (cuuint64_t)g.in_img * 2};
+  const cuuint32_t box[5] = {8, (cuuint32_t)pl.PW, (cuuint32_t)pl.box_h, 1, 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  if (((uintptr_t)base & 15) || (strides[3] & 15)) { set_error("TMA staging: tensor not 16-byte aligned"); return VG_EINVAL; }
+  const CUresult rc = tma_encoder()(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)rc); return VG_ECUDA; }
+  return VG_OK;
+}
+
+template <int CIN, int COUT, int SD, bool TMA = false>
 static int launch_tc2_t(const Geom& g, const GatherArgs& a, const T2Plan& pl, cudaStream_t st) {
   const size_t smem = (size_t)pl.R * 2 * pl.nsg * pl.SR * 16 + pl.wbytes;
-  VG_CUDA(cudaFuncSetAttribute(tc2_kernel<CIN, COUT, SD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VG_CUDA(cudaFuncSetAttribute(tc2_kernel<CIN, COUT, SD, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long cols = (long long)g.N * pl.ntiles * pl.ndchunks;
   const int sms = vg_sm_count();
-  const unsigned grid = (unsigned)(cols < sms ? cols : sms);
-  tc2_kernel<CIN, COUT, SD><<<grid, T2_THREADS, smem, st>>>(g, a, pl);
+  unsigned grid = (unsigned)(cols < sms ? cols : sms);
+  alignas(64) CUtensorMap tm;
+  memset(&tm, 0, sizeof(tm));
+  if constexpr (TMA) {
+    VG_TRY(make_tmap(g, pl, a.in, tm));
+    if (pl.groups > 1) {                          // a CTA serves one statistics group: equal CTA counts per group
+      const long long per_group = (long long)g.group_size * pl.ntiles * pl.ndchunks;
+      long long per = sms / pl.groups;
+      if (per < 1) per = 1;
+      if (per > per_group) per = per_group;
+      grid = (unsigned)(per * pl.groups);
+    }
+  }
+  tc2_kernel<CIN, COUT, SD, TMA><<<grid, T2_THREADS, smem, st>>>(g, a, pl, tm);
   VG_LAUNCH_CHECK();
   return VG_OK;
 }
@@ -851,7 +1083,15 @@ static int launch_tc2_t(const Geom& g, const GatherArgs& a, const T2Plan& pl, cu
 int launch_tc2_gather(int cin, int cout, const Geom* gs, int ng, const GatherArgs& a, cudaStream_t st) {
   T2Plan pl;
   Geom merged;
-  if (!t2_build_plan(cin, cout, gs, ng, merged, pl)) { set_error("plane-folded tensor-core path: unsupported geometry"); return VG_EINVAL; }
+  const bool want_tma = a.in_bf16 && tma_enabled();
+  if (!t2_build_plan(cin, cout, gs, ng, merged, pl, want_tma, a.in_scale != nullptr)) { set_error("plane-folded tensor-core path: unsupported geometry"); return VG_EINVAL; }
+  if (pl.hb > 0) {                                // TMA-direct staging of a bf16 input
+    if (cin == 8 && cout == 1) return launch_tc2_t<8, 1, 1, true>(merged, a, pl, st);
+    if (cin == 8 && cout == 8) return launch_tc2_t<8, 8, 1, true>(merged, a, pl, st);
+    if (cin == 8 && cout == 16) return launch_tc2_t<8, 16, 1, true>(merged, a, pl, st);
+    set_error("TMA staging: unsupported channel pair (%d,%d)", cin, cout);
+    return VG_EINVAL;
+  }
   if (pl.sd == 2) {
     if (cin == 8 && cout == 8) return launch_tc2_t<8, 8, 2>(merged, a, pl, st);
     if (cin == 8 && cout == 16) return launch_tc2_t<8, 16, 2>(merged, a, pl, st);
