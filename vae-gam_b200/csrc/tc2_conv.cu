@@ -87,12 +87,11 @@ __host__ __device__ constexpr int t2_epi_sets(int cin, int cout, int sd) { retur
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// one 5-D box (c, w, h, d, n) of the tensor map -> shared memory; completion is signalled on the mbarrier (bytes)
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3,
-                                            int c4) {
+// one 4-D box (line words, h, d, n) of the tensor map -> shared memory; completion is signalled on the mbarrier (bytes)
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
   asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 constexpr int T2_MAX_CLS = 5;      // tap-validity classes per output dimension (k <= 5 would give more; TMA mode has k = 3)
@@ -122,7 +121,7 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
   __shared__ float s_btab[TMA ? T2_MAX_CLS * T2_MAX_CLS * T2_MAX_CLS * COUT : 1];
   __shared__ float s_tapsum[TMA ? 27 * COUT : 1];
   __shared__ uint8_t s_cls[3][64], s_cmask[3][8];
-  __shared__ int s_ncls[3];
+  __shared__ int s_ncls[3], s_midrange[2];     // [lo, hi): the output planes around the middle whose d-taps are all inside
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int SRB = pl.SR * 16;                   // bytes per staged plane
@@ -227,6 +226,13 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
         s_cls[tid][o] = (uint8_t)(c < 0 ? 0 : c);
       }
       s_ncls[tid] = ncls < 1 ? 1 : ncls;
+      if (tid == 0) {
+        const int lim = Out < 64 ? Out : 64, mid = lim / 2;
+        int a0 = mid, a1 = mid + 1;
+        while (a0 > 0 && s_cls[0][a0 - 1] == s_cls[0][mid]) --a0;
+        while (a1 < lim && s_cls[0][a1] == s_cls[0][mid]) ++a1;
+        s_midrange[0] = a0; s_midrange[1] = a1;
+      }
     }
     for (int e = tid; e < 27 * COUT; e += T2_THREADS) {       // per-tap sum over input channels of shift * W
       const int t = e / COUT, co = e - t * COUT;
@@ -272,6 +278,19 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
     const size_t plane_out = (size_t)g.outH * g.outW * COUT;
     struct Item { int rb, k, qd, bofs; bool row_ok; size_t o0; };
     const int cls_hw = TMA ? s_ncls[1] * s_ncls[2] * COUT : 0;
+    // bias of a voxel whose taps are all inside the input (the bulk): kept in registers; only border voxels (or border
+    // planes) read the class table.  Interior class = the class of the middle coordinate.
+    int cls_mid[3] = {0, 0, 0};
+    float b_mid[COUT];
+    bool one_cls = true;
+    if constexpr (TMA) {
+      cls_mid[0] = s_cls[0][min(g.outD / 2, 63)]; cls_mid[1] = s_cls[1][min(g.outH / 2, 63)]; cls_mid[2] = s_cls[2][min(g.outW / 2, 63)];
+      one_cls = s_ncls[0] * s_ncls[1] * s_ncls[2] == 1;
+#pragma unroll
+      for (int c = 0; c < COUT; ++c) b_mid[c] = s_btab[cls_mid[0] * cls_hw + (cls_mid[1] * s_ncls[2] + cls_mid[2]) * COUT + c];
+    }
+    const int mid_bofs = (cls_mid[1] * (TMA ? s_ncls[2] : 0) + cls_mid[2]) * COUT;
+    const int mid_d0 = TMA ? s_midrange[0] : 0, mid_d1 = TMA ? s_midrange[1] : 0;
     for (int col = col_first; col < col_count; col += col_step) {
       const int dc = col % pl.ndchunks, t = (col / pl.ndchunks) % pl.ntiles, n = col_img0 + col / cols_per_img;
       const int qd0 = dc * pl.dchunk, qd1 = min(pl.qDmax, qd0 + pl.dchunk);
@@ -296,7 +315,7 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
               const int rl = I.rb * 128 + etid, lh = rl / pl.PW;
               qh = t * pl.hb + lh; qw = rl - lh * pl.PW;
               I.row_ok = lh < pl.hb && qh < P.qH && qw < P.qW;
-              I.bofs = I.row_ok ? (s_cls[1][min(qh, 63)] * s_ncls[2] + s_cls[2][min(qw, 63)]) * COUT : 0;
+              I.bofs = (I.row_ok && !one_cls) ? (s_cls[1][min(qh, 63)] * s_ncls[2] + s_cls[2][min(qw, 63)]) * COUT : mid_bofs;
             } else {
               const int r = t * pl.TR + I.rb * 128 + etid;
               qh = r / pl.PW; qw = r - qh * pl.PW;
@@ -349,11 +368,25 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
             for (int j = 0; j < NJ; ++j) {
               if (I.qd + j >= qd_end) continue;
               float y[COUT];
-              const float* bsrc = s_bias;
-              if constexpr (TMA) bsrc = s_btab + s_cls[0][min(I.qd + j, 63)] * cls_hw + I.bofs;
+              float bv[COUT];
+              if constexpr (TMA) {
+                const int od = I.qd + j;
+                const bool mid_plane = one_cls || (od >= mid_d0 && od < mid_d1);    // same d-class as the middle plane
+                if (mid_plane && I.bofs == mid_bofs) {
+#pragma unroll
+                  for (int c = 0; c < COUT; ++c) bv[c] = b_mid[c];
+                } else {
+                  const float* bsrc = s_btab + s_cls[0][min(od, 63)] * cls_hw + I.bofs;
+#pragma unroll
+                  for (int c = 0; c < COUT; ++c) bv[c] = bsrc[c];
+                }
+              } else {
+#pragma unroll
+                for (int c = 0; c < COUT; ++c) bv[c] = s_bias[c];
+              }
 #pragma unroll
               for (int c = 0; c < COUT; ++c) {
-                float v = __uint_as_float(rr[j * COUT + c]) + bsrc[c];
+                float v = __uint_as_float(rr[j * COUT + c]) + bv[c];
                 if (a.act == VG_ACT_RELU) v = fmaxf(v, 0.f);
                 else if (a.act == VG_ACT_SIGMOID) v = 1.f / (1.f + __expf(-v));
                 y[c] = v;
@@ -468,7 +501,7 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
               mbar_arrive_expect_tx(bar, slot_tx);
 #pragma unroll
               for (int hf = 0; hf < 2; ++hf)      // plane ip may lie outside the input: the whole box is then zero-filled
-                tma_load_5d(ring_a + (uint32_t)slot * (uint32_t)PAIRB + (uint32_t)hf * (uint32_t)SRB, &tmap, bar, 0, pl.lo_w,
+                tma_load_4d(ring_a + (uint32_t)slot * (uint32_t)PAIRB + (uint32_t)hf * (uint32_t)SRB, &tmap, bar, 4 * pl.lo_w,
                             t * pl.hb + pl.lo_h, qd0 + pl.lo_d + 2 * P + hf, n);
             }
             __syncwarp();
@@ -911,7 +944,7 @@ static bool t2_build_plan(int cin, int cout, const Geom* gs, int ng, Geom& merge
   if (pl.wbytes > 96 * 1024) return false;
 
   if (tma && cin == 8 && sd == 1 && (ng == 1 || !affine) && pl.span_d <= 2 && merged.outD <= 64 && merged.outH <= 64 &&
-      merged.outW <= 64 && pl.PW <= 256) {
+      merged.outW <= 64 && pl.PW <= 64) {
     // ---- TMA-direct staging: tile = hb whole lines of the row frame, a slot = two boxes [8][PW][hb + halo]
     int nrb_max = 512 / (2 * pl.ACCW);
     if (nrb_max > 4) nrb_max = 4;
@@ -1018,9 +1051,11 @@ int tc2_describe(int cin, int cout, const Geom* gs, int ng, char* buf, size_t ca
                   (size_t)pl.R * 2 * pl.nsg * pl.SR * 16 + pl.wbytes, pl.dchunk, pl.ndchunks, cols);
 }
 
-// ---- TMA tensor map of a channels-last bf16 tensor (N, D, H, W, 8): dims fastest-first (c, w, h, d, n); a box is
-// [8][PW][box_h][1][1], out-of-range coordinates (the halo of a transposed convolution, planes beyond the
-// volume) are zero-filled by the hardware.
+// ---- TMA tensor map of a channels-last bf16 tensor (N, D, H, W, 8).  A voxel is one 16-byte word and the voxels of
+// an h-line are contiguous, so (channel, w) is ONE dimension of 4 * W 32-bit words: dims fastest-first (line words,
+// h, d, n), a box is [4 * PW][box_h][1][1] — every box row is a whole padded line (a few hundred contiguous bytes,
+// not 16).  Out-of-range coordinates (the halo of a transposed convolution, planes beyond the volume) are
+// zero-filled by the hardware.
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1044,12 +1079,12 @@ static bool tma_enabled() {
   return on == 1 && tma_encoder() != nullptr;
 }
 static int make_tmap(const Geom& g, const T2Plan& pl, const void* base, CUtensorMap& tm) {
-  const cuuint64_t dims[5] = {8, (cuuint64_t)g.inW, (cuuint64_t)g.inH, (cuuint64_t)g.inD, (cuuint64_t)g.N};
-  const cuuint64_t strides[4] = {16, (cuuint64_t)g.inW * 16, (cuuint64_t)g.inW * g.inH * 16, (cuuint64_t)g.in_img * 2};
-  const cuuint32_t box[5] = {8, (cuuint32_t)pl.PW, (cuuint32_t)pl.box_h, 1, 1};
-  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  if (((uintptr_t)base & 15) || (strides[3] & 15)) { set_error("TMA staging: tensor not 16-byte aligned"); return VG_EINVAL; }
-  const CUresult rc = tma_encoder()(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+  const cuuint64_t dims[4] = {(cuuint64_t)g.inW * 4, (cuuint64_t)g.inH, (cuuint64_t)g.inD, (cuuint64_t)g.N};
+  const cuuint64_t strides[3] = {(cuuint64_t)g.inW * 16, (cuuint64_t)g.inW * g.inH * 16, (cuuint64_t)g.in_img * 2};
+  const cuuint32_t box[4] = {(cuuint32_t)pl.PW * 4, (cuuint32_t)pl.box_h, 1, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  if (((uintptr_t)base & 15) || (strides[2] & 15)) { set_error("TMA staging: tensor not 16-byte aligned"); return VG_EINVAL; }
+  const CUresult rc = tma_encoder()(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, const_cast<void*>(base), dims, strides, box, estr,
                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (rc != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)rc); return VG_ECUDA; }
