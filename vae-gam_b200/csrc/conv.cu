@@ -481,16 +481,18 @@ extern "C" int vg_conv_describe(const VgConvDesc* d, int kind, char* buf, size_t
   const int ng = build_geoms(d, kind, gs);
   const int cin = kind == 0 ? d->cin : d->cout, cout = kind == 0 ? d->cout : d->cin;
   const bool use_tc = desc_tc(d);
+  const bool in16 = (d->bf16_mask & (kind == 0 ? VG_BF16_X : VG_BF16_Y)) != 0;      // the tensor this gather reads
+  const bool any16 = d->bf16_mask != 0;
   size_t off = 0;
   buf[0] = 0;
-  if (ng > 1 && use_tc && tc2_worthwhile(gs, ng) && tc2_supported(cin, cout, gs, ng)) {
-    const int n = tc2_describe(cin, cout, gs, ng, buf, cap);
+  if (ng > 1 && use_tc && (tc2_worthwhile(gs, ng) || any16) && tc2_supported(cin, cout, gs, ng)) {
+    const int n = tc2_describe(cin, cout, gs, ng, buf, cap, in16);
     if (n > 0 && (size_t)n + 2 < cap) { buf[n] = '\n'; buf[n + 1] = 0; }
     return 1;
   }
   for (int i = 0; i < ng && off + 8 < cap; ++i) {
     int n = 0;
-    if (use_tc && tc2_worthwhile(&gs[i], 1)) n = tc2_describe(cin, cout, &gs[i], 1, buf + off, cap - off);
+    if (use_tc && (tc2_worthwhile(&gs[i], 1) || any16)) n = tc2_describe(cin, cout, &gs[i], 1, buf + off, cap - off, in16);
     if (n <= 0) {
       const bool tc = use_tc && tc_supported(cin, cout, gs[i]);
       n = snprintf(buf + off, cap - off, "%s cin=%d cout=%d q=(%d,%d,%d) taps=%d", tc ? "tc1" : "fp32", cin, cout,

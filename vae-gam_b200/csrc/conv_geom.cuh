@@ -52,7 +52,7 @@ int launch_tc_gather(int cin, int cout, const Geom& g, const GatherArgs& a, cuda
 // gs[0..ng): gathers of one layer pass sharing their input (ng > 1: the output-parity phases of a stride-2 layer)
 bool tc2_supported(int cin, int cout, const Geom* gs, int ng);
 int launch_tc2_gather(int cin, int cout, const Geom* gs, int ng, const GatherArgs& a, cudaStream_t st);
-int tc2_describe(int cin, int cout, const Geom* gs, int ng, char* buf, size_t cap);
+int tc2_describe(int cin, int cout, const Geom* gs, int ng, char* buf, size_t cap, bool in_bf16 = false);
 int conv_mode();   // process default: 0 fp32 CUDA cores ("check mode"), 1 bf16 tcgen05 where the geometry allows, 2 mixed
 int resolve_arith(int arith);   // VG_ARITH_* -> 0 / 1 / 2 (VG_ARITH_DEFAULT -> conv_mode())
 

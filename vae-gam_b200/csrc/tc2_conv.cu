@@ -948,9 +948,10 @@ static bool t2_build_plan(int cin, int cout, const Geom* gs, int ng, Geom& merge
     // ---- TMA-direct staging: tile = hb whole lines of the row frame, a slot = two boxes [8][PW][hb + halo]
     int nrb_max = 512 / (2 * pl.ACCW);
     if (nrb_max > 4) nrb_max = 4;
-    int hb = (128 * nrb_max) / pl.PW;
-    if (hb > qmax[1]) hb = qmax[1];
-    if (hb >= 1) {
+    for (int nrb_try = nrb_max; nrb_try >= 1; --nrb_try) {   // largest tile whose ring still fits next to the weights
+      int hb = (128 * nrb_try) / pl.PW;
+      if (hb > qmax[1]) hb = qmax[1];
+      if (hb < 1) continue;
       const int nt = (qmax[1] + hb - 1) / hb;
       hb = (qmax[1] + nt - 1) / nt;                        // balanced tiles
       const int nrb = (hb * pl.PW + 127) / 128;
@@ -963,25 +964,24 @@ static bool t2_build_plan(int cin, int cout, const Geom* gs, int ng, Geom& merge
       int r = pl.NPAIR + 3;
       if (r > T2_MAX_RING) r = T2_MAX_RING;
       while (r > pl.NPAIR + 1 && (size_t)r * slot + pl.wbytes > (size_t)kT2SmemBudget) --r;
-      if ((size_t)r * slot + pl.wbytes <= (size_t)kT2SmemBudget && box_h <= 256) {
-        pl.hb = hb; pl.box_h = box_h; pl.nrb = nrb; pl.TR = 128 * nrb; pl.SR = sr; pl.R = r;
-        pl.ntiles = nt;
-        pl.groups = affine ? merged.N / merged.group_size : 1;
-        for (int m = 0; m < nmma; ++m) pl.mma[m].a_shift = (uint32_t)(m_sg[m] * pl.SR + m_mh[m] * pl.PW + m_mw[m]);
-        int tc = 32;
-        while (tc < 2 * pl.nrb * pl.ACCW) tc <<= 1;
-        if (tc > 512) return false;
-        pl.tmem_cols = tc;
-        const int nblocks_all = (pl.qDmax + pl.OB - 1) / pl.OB;
-        const long long cols = (long long)merged.N * pl.ntiles;
-        const long long want = 2LL * vg_sm_count();
-        int nch = (int)((want + cols - 1) / cols);
-        if (nch > nblocks_all) nch = nblocks_all;
-        if (nch < 1) nch = 1;
-        pl.dchunk = ((nblocks_all + nch - 1) / nch) * pl.OB;
-        pl.ndchunks = (pl.qDmax + pl.dchunk - 1) / pl.dchunk;
-        return true;
-      }
+      if ((size_t)r * slot + pl.wbytes > (size_t)kT2SmemBudget || box_h > 256) continue;
+      pl.hb = hb; pl.box_h = box_h; pl.nrb = nrb; pl.TR = 128 * nrb; pl.SR = sr; pl.R = r;
+      pl.ntiles = nt;
+      pl.groups = affine ? merged.N / merged.group_size : 1;
+      for (int m = 0; m < nmma; ++m) pl.mma[m].a_shift = (uint32_t)(m_sg[m] * pl.SR + m_mh[m] * pl.PW + m_mw[m]);
+      int tc = 32;
+      while (tc < 2 * pl.nrb * pl.ACCW) tc <<= 1;
+      if (tc > 512) return false;
+      pl.tmem_cols = tc;
+      const int nblocks_all = (pl.qDmax + pl.OB - 1) / pl.OB;
+      const long long cols = (long long)merged.N * pl.ntiles;
+      const long long want = 2LL * vg_sm_count();
+      int nch = (int)((want + cols - 1) / cols);
+      if (nch > nblocks_all) nch = nblocks_all;
+      if (nch < 1) nch = 1;
+      pl.dchunk = ((nblocks_all + nch - 1) / nch) * pl.OB;
+      pl.ndchunks = (pl.qDmax + pl.dchunk - 1) / pl.dchunk;
+      return true;
     }
   }
   // rows per tile: as many 128-row blocks as TMEM (2 buffers), the producers' reach and shared memory allow
@@ -1038,17 +1038,22 @@ bool tc2_supported(int cin, int cout, const Geom* gs, int ng) {
 }
 
 // human-readable plan (vg_conv_describe): tile shape, ring, MMA list size, shared memory
-int tc2_describe(int cin, int cout, const Geom* gs, int ng, char* buf, size_t cap) {
+static bool tma_wanted() {      // VAEGAM_TMA=0 switches the TMA-direct staging off (producer-warp staging of the same bf16 tensors)
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("VAEGAM_TMA"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on == 1;
+}
+int tc2_describe(int cin, int cout, const Geom* gs, int ng, char* buf, size_t cap, bool in_bf16) {
   T2Plan pl;
   Geom merged;
-  if (!t2_build_plan(cin, cout, gs, ng, merged, pl)) return 0;
+  if (!t2_build_plan(cin, cout, gs, ng, merged, pl, in_bf16 && tma_wanted(), false)) return 0;
   const long long cols = (long long)merged.N * pl.ntiles * pl.ndchunks;
   return snprintf(buf, cap,
                   "tc2 cin=%d cout=%d sin=%d phases=%d q=(%d,%d,%d) taps=%d PW=%d RTOT=%d TR=%d ntiles=%d SR=%d OB=%d NPAIR=%d R=%d "
-                  "ACCW=%d tmem=%d nmma=%d nblk=%d wbytes=%d smem=%zu dchunk=%d ndchunks=%d cols=%lld",
+                  "ACCW=%d tmem=%d nmma=%d nblk=%d wbytes=%d smem=%zu dchunk=%d ndchunks=%d cols=%lld tma_hb=%d",
                   cin, cout, pl.sd, ng, pl.qDmax, pl.RTOT / pl.PW, merged.qW, merged.ntaps, pl.PW, pl.RTOT, pl.TR, pl.ntiles,
                   pl.SR, pl.OB, pl.NPAIR, pl.R, pl.ACCW, pl.tmem_cols, pl.nmma, pl.nblk, pl.wbytes,
-                  (size_t)pl.R * 2 * pl.nsg * pl.SR * 16 + pl.wbytes, pl.dchunk, pl.ndchunks, cols);
+                  (size_t)pl.R * 2 * pl.nsg * pl.SR * 16 + pl.wbytes, pl.dchunk, pl.ndchunks, cols, pl.hb);
 }
 
 // ---- TMA tensor map of a channels-last bf16 tensor (N, D, H, W, 8).  A voxel is one 16-byte word and the voxels of
@@ -1073,11 +1078,7 @@ static EncodeTiledFn tma_encoder() {
   }
   return fn;
 }
-static bool tma_enabled() {
-  static int on = -1;
-  if (on < 0) { const char* e = getenv("VAEGAM_TMA"); on = (e && e[0] == '0') ? 0 : 1; }
-  return on == 1 && tma_encoder() != nullptr;
-}
+static bool tma_enabled() { return tma_wanted() && tma_encoder() != nullptr; }
 static int make_tmap(const Geom& g, const T2Plan& pl, const void* base, CUtensorMap& tm) {
   const cuuint64_t dims[4] = {(cuuint64_t)g.inW * 4, (cuuint64_t)g.inH, (cuuint64_t)g.inD, (cuuint64_t)g.N};
   const cuuint64_t strides[3] = {(cuuint64_t)g.inW * 16, (cuuint64_t)g.inW * g.inH * 16, (cuuint64_t)g.in_img * 2};
