@@ -175,6 +175,7 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
   const int col_step = grouped ? (int)((gridDim.x - my_grp + pl.groups - 1) / pl.groups) : (int)gridDim.x;
   const int col_count = grouped ? g.group_size * cols_per_img : g.N * cols_per_img;
   const int col_img0 = grouped ? my_grp * g.group_size : 0;
+  const int per_dc = (grouped ? g.group_size : g.N) * pl.ntiles;      // columns per d-chunk index
   const float* fold_scale = (TMA && a.in_scale) ? a.in_scale + (size_t)my_grp * CIN : nullptr;
   const float* fold_shift = (TMA && a.in_scale) ? a.in_shift + (size_t)my_grp * CIN : nullptr;
 
@@ -292,7 +293,9 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
     const int mid_bofs = (cls_mid[1] * (TMA ? s_ncls[2] : 0) + cls_mid[2]) * COUT;
     const int mid_d0 = TMA ? s_midrange[0] : 0, mid_d1 = TMA ? s_midrange[1] : 0;
     for (int col = col_first; col < col_count; col += col_step) {
-      const int dc = col % pl.ndchunks, t = (col / pl.ndchunks) % pl.ntiles, n = col_img0 + col / cols_per_img;
+      // d-chunk major: the chunks of an image differ in length (the last one is short), so all the long columns come
+      // first and a CTA's round-robin share mixes long and short ones whatever the parity of the grid
+      const int dc = col / per_dc, t = (col - dc * per_dc) % pl.ntiles, n = col_img0 + (col - dc * per_dc) / pl.ntiles;
       const int qd0 = dc * pl.dchunk, qd1 = min(pl.qDmax, qd0 + pl.dchunk);
       const int nblocks = (qd1 - qd0 + pl.OB - 1) / pl.OB;
       const int grp = n / g.group_size;
@@ -489,7 +492,9 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
         const uint32_t ring_a = smem_u32(ring);
         const uint32_t slot_tx = (uint32_t)(2 * pl.box_h * pl.PW * 16);     // two boxes of [8 ch][PW][box_h] bf16
         for (int col = col_first; col < col_count; col += col_step) {
-          const int dc = col % pl.ndchunks, t = (col / pl.ndchunks) % pl.ntiles, n = col_img0 + col / cols_per_img;
+          // d-chunk major: the chunks of an image differ in length (the last one is short), so all the long columns come
+      // first and a CTA's round-robin share mixes long and short ones whatever the parity of the grid
+      const int dc = col / per_dc, t = (col - dc * per_dc) % pl.ntiles, n = col_img0 + (col - dc * per_dc) / pl.ntiles;
           const int qd0 = dc * pl.dchunk, qd1 = min(pl.qDmax, qd0 + pl.dchunk);
           const int nblocks = (qd1 - qd0 + pl.OB - 1) / pl.OB;
           const int npairs = nblocks * H2 + (pl.NPAIR - H2);
@@ -517,7 +522,9 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
     const bool affine = a.in_scale != nullptr;
     const size_t plane_in = (size_t)g.inH * g.inW * CIN;
     for (int col = col_first; col < col_count; col += col_step) {
-      const int dc = col % pl.ndchunks, t = (col / pl.ndchunks) % pl.ntiles, n = col_img0 + col / cols_per_img;
+      // d-chunk major: the chunks of an image differ in length (the last one is short), so all the long columns come
+      // first and a CTA's round-robin share mixes long and short ones whatever the parity of the grid
+      const int dc = col / per_dc, t = (col - dc * per_dc) % pl.ntiles, n = col_img0 + (col - dc * per_dc) / pl.ntiles;
       const int qd0 = dc * pl.dchunk, qd1 = min(pl.qDmax, qd0 + pl.dchunk);
       const int nblocks = (qd1 - qd0 + pl.OB - 1) / pl.OB;
       const int npairs = nblocks * H2 + (pl.NPAIR - H2);
@@ -761,7 +768,7 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
     const uint32_t lbo_field = ((uint32_t)(NSG * SRB) >> 4) << 16;
     const uint32_t a_hi = (128u >> 4) | (1u << 14), b_hi = (256u >> 4) | (1u << 14);
     for (int col = col_first; col < col_count; col += col_step) {
-      const int dc = col % pl.ndchunks;
+      const int dc = col / per_dc;
       const int qd0 = dc * pl.dchunk, qd1 = min(pl.qDmax, qd0 + pl.dchunk);
       const int nblocks = (qd1 - qd0 + pl.OB - 1) / pl.OB;
       for (int b = 0; b < nblocks; ++b)
@@ -948,7 +955,29 @@ static bool t2_build_plan(int cin, int cout, const Geom* gs, int ng, Geom& merge
     // ---- TMA-direct staging: tile = hb whole lines of the row frame, a slot = two boxes [8][PW][hb + halo]
     int nrb_max = 512 / (2 * pl.ACCW);
     if (nrb_max > 4) nrb_max = 4;
-    for (int nrb_try = nrb_max; nrb_try >= 1; --nrb_try) {   // largest tile whose ring still fits next to the weights
+    // whole-line tiles quantise: pick the row-block count whose tiles waste the fewest MMA rows (ties: the larger tile)
+    int order[4], nord = 0;
+    {
+      double effs[5] = {0, 0, 0, 0, 0};
+      for (int q = 1; q <= nrb_max; ++q) {
+        int hb = (128 * q) / pl.PW;
+        if (hb > qmax[1]) hb = qmax[1];
+        if (hb < 1) continue;
+        const int nt = (qmax[1] + hb - 1) / hb;
+        hb = (qmax[1] + nt - 1) / nt;
+        effs[q] = (double)(qmax[1] * pl.PW) / ((double)nt * 128.0 * ((hb * pl.PW + 127) / 128)) + 1e-3 * q;
+      }
+      bool used[5] = {false, false, false, false, false};
+      for (int k = 0; k < nrb_max; ++k) {
+        int best_q = 0;
+        for (int q = 1; q <= nrb_max; ++q) if (!used[q] && effs[q] > 0 && (best_q == 0 || effs[q] > effs[best_q])) best_q = q;
+        if (!best_q) break;
+        used[best_q] = true;
+        order[nord++] = best_q;
+      }
+    }
+    for (int oi = 0; oi < nord; ++oi) {                      // best tile whose ring still fits next to the weights
+      const int nrb_try = order[oi];
       int hb = (128 * nrb_try) / pl.PW;
       if (hb > qmax[1]) hb = qmax[1];
       if (hb < 1) continue;
