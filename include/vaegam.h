@@ -157,11 +157,14 @@ int vg_bn_finalize(const double* stats, const float* gamma, const float* beta, i
  * m2 = sums[g,c,1]/count; dgamma[c] += sum_g sums[g,c,1]; dbeta[c] += sum_g sums[g,c,0]
  * (dgamma/dbeta may be NULL; they are accumulated by one thread block). In-place (dx == dy) ok.
  * bf16_mask: VG_BF16_X = x holds bf16, VG_BF16_DX = dx is written as bf16 (dy is always fp32, so
- * dx must then be a different buffer than dy); c must be 8 or 16 for bf16 storage. */
+ * dx must then be a different buffer than dy); c must be 8 or 16 for bf16 storage.
+ * dx_chan_sum (c floats, ACCUMULATED, may be NULL; bf16-storage variant only): sum of dx per channel =
+ * the bias gradient of the layer whose ReLU output x is, so that its weight-gradient call can take
+ * dbias == NULL and stage dx with plain asynchronous copies. */
 int vg_bn_bwd_apply(const float* dy, const void* x, const double* sums, const float* scale,
                     const float* istd, const float* mistd, int n, int group_size,
                     long long spatial, int c, double count, int relu_mask, int bf16_mask, void* dx,
-                    float* dgamma, float* dbeta, void* stream);
+                    float* dgamma, float* dbeta, float* dx_chan_sum, void* stream);
 /* (n, c, spatial) <-> (n, spatial, c) */
 int vg_nchw_to_nhwc(const float* src, float* dst, int n, int c, long long spatial, void* stream);
 int vg_nhwc_to_nchw(const float* src, float* dst, int n, int c, long long spatial, void* stream);

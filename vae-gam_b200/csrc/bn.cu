@@ -148,8 +148,11 @@ template <int C, bool X16, bool DX16>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply8_kernel(const float* __restrict__ dy, const void* __restrict__ x_, const double* __restrict__ sums,
                      const float* __restrict__ scale, const float* __restrict__ istd, const float* __restrict__ mistd,
-                     int group_size, long long spatial, double count, int relu_mask, void* dx_) {
+                     int group_size, long long spatial, double count, int relu_mask, void* dx_, float* dx_sum) {
   static_assert(C % 8 == 0, "8-channel items");
+  __shared__ float s_sum[C];
+  if (dx_sum && threadIdx.x < C) s_sum[threadIdx.x] = 0.f;
+  float osum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const int n = blockIdx.y;
   const int grp = n / group_size;
   const long long total = spatial * C;
@@ -205,6 +208,7 @@ bn_bwd_apply8_kernel(const float* __restrict__ dy, const void* __restrict__ x_, 
         float r = sc[j] * (d[j] - m1[j] - xhat * m2[j]);
         if (relu_mask && !(xv[j] > 0.f)) r = 0.f;
         o[j] = r;
+        osum[j] += r;
       }
       if constexpr (DX16) {
         reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(dx_) + base)[iu] = pack_bf16x8(o);
@@ -214,6 +218,19 @@ bn_bwd_apply8_kernel(const float* __restrict__ dy, const void* __restrict__ x_, 
         stg_stream(reinterpret_cast<float4*>(dxf) + 2 * iu + 1, make_float4(o[4], o[5], o[6], o[7]));
       }
     }
+  }
+  if (dx_sum) {      // per-channel sum of dx (the bias gradient of the layer that produced x): block reduce, one atomic per channel
+    __syncthreads();
+    const int c0 = (int)((i0 * 8) % C);
+    constexpr int PERL = C / 8;                      // lanes l and l + PERL hold the same channels
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = osum[j];
+      for (int o = 16; o >= PERL; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((threadIdx.x & 31) < PERL) atomicAdd(&s_sum[c0 + j], v);
+    }
+    __syncthreads();
+    if (threadIdx.x < C) atomicAdd(dx_sum + threadIdx.x, s_sum[threadIdx.x]);
   }
 }
 
@@ -290,7 +307,7 @@ extern "C" int vg_bn_finalize(const double* stats, const float* gamma, const flo
 extern "C" int vg_bn_bwd_apply(const float* dy, const void* x_, const double* sums, const float* scale,
                                const float* istd, const float* mistd, int n, int group_size,
                                long long spatial, int c, double count, int relu_mask, int bf16_mask, void* dx_,
-                               float* dgamma, float* dbeta, void* stream) {
+                               float* dgamma, float* dbeta, float* dx_chan_sum, void* stream) {
   const float* x = static_cast<const float*>(x_);
   float* dx = static_cast<float*>(dx_);
   VG_CHECK_ARG(x && sums && n > 0 && group_size > 0 && n % group_size == 0, "bad arguments");
@@ -307,13 +324,14 @@ extern "C" int vg_bn_bwd_apply(const float* dy, const void* x_, const double* su
     if (bx < 1) bx = 1;
     dim3 grid(bx, n);
     const bool x16 = (bf16_mask & VG_BF16_X) != 0, d16 = (bf16_mask & VG_BF16_DX) != 0;
-#define VG_BN8(C, X, D) bn_bwd_apply8_kernel<C, X, D><<<grid, 256, 0, st>>>(dy, x_, sums, scale, istd, mistd, group_size, spatial, count, relu_mask, dx_)
+#define VG_BN8(C, X, D) bn_bwd_apply8_kernel<C, X, D><<<grid, 256, 0, st>>>(dy, x_, sums, scale, istd, mistd, group_size, spatial, count, relu_mask, dx_, dx_chan_sum)
     if (c == 8) { if (x16 && d16) VG_BN8(8, true, true); else if (x16) VG_BN8(8, true, false); else VG_BN8(8, false, true); }
     else { if (x16 && d16) VG_BN8(16, true, true); else if (x16) VG_BN8(16, true, false); else VG_BN8(16, false, true); }
 #undef VG_BN8
     VG_LAUNCH_CHECK();
   } else if (dx) {
     VG_CHECK_ARG(dy && scale && istd && mistd, "null coefficient");
+    VG_CHECK_ARG(dx_chan_sum == nullptr, "dx_chan_sum is produced by the bf16-storage variant only");
     long long per_img = spatial * c;
     int bx = (int)((per_img / 4 + 255) / 256);
     int cap = 8 * vg_sm_count() / n;          // whole grid resident at once (8 CTAs of 256 threads per SM): no tail wave

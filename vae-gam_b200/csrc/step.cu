@@ -569,11 +569,13 @@ static int step_bwd_impl(const VgStepConfig* cfg, const VgStepIO* io, void* work
   { VG_PROF("bnt5.bn_bwd", st);
   VG_TRY(vg_bn_bwd_apply(w.d_t4, d.t4, d.bnt5.sums, d.bnt5.scale, d.bnt5.istd, d.bnt5.mistd, nd, B,
                          vol(kConvT[3].out), 8, (double)B * vol(kConvT[3].out), 1, big16 ? (VG_BF16_X | VG_BF16_DX) : 0,
-                         d_t4_final, GF(BNT5), GF(BNT5 + 1), st));
+                         d_t4_final, GF(BNT5), GF(BNT5 + 1), big16 ? GF(CONVT4 + 1) : nullptr, st));
   }
   { cudaStream_t ws = fk.branch();
   VG_PROF("convt4.wgrad", ws);
-  VG_TRY(vg_conv_wgrad(&c4, d.t3, d_t4_final, nullptr, nullptr, GF(CONVT4), GF(CONVT4 + 1), ws));
+  // bf16 storage: convt4's bias gradient was summed by the BatchNorm backward above, so both operands of the
+  // weight gradient are plain bf16 tensors that go to shared memory with asynchronous copies
+  VG_TRY(vg_conv_wgrad(&c4, d.t3, d_t4_final, nullptr, nullptr, GF(CONVT4), big16 ? nullptr : GF(CONVT4 + 1), ws));
   }
   { VG_PROF("convt4.dgrad", st);
   VG_TRY(vg_conv_dgrad(&c4, d_t4_final, PF(CONVT4), w.d_t3, d.t3, nullptr, nullptr, nullptr, nullptr, st));
@@ -587,7 +589,7 @@ static int step_bwd_impl(const VgStepConfig* cfg, const VgStepIO* io, void* work
   }
   { VG_PROF("bnt3.bn_bwd", st);
   VG_TRY(vg_bn_bwd_apply(w.d_t2, d.t2, d.bnt3.sums, d.bnt3.scale, d.bnt3.istd, d.bnt3.mistd, nd, B,
-                         vol(kConvT[1].out), 16, (double)B * vol(kConvT[1].out), 1, 0, w.d_t2, GF(BNT3), GF(BNT3 + 1), st));
+                         vol(kConvT[1].out), 16, (double)B * vol(kConvT[1].out), 1, 0, w.d_t2, GF(BNT3), GF(BNT3 + 1), nullptr, st));
   }
   { cudaStream_t ws = fk.branch();
   VG_PROF("convt2.wgrad", ws);
@@ -605,7 +607,7 @@ static int step_bwd_impl(const VgStepConfig* cfg, const VgStepIO* io, void* work
   }
   { VG_PROF("bnt1.bn_bwd", st);
   VG_TRY(vg_bn_bwd_apply(w.d_t0, d.t0, d.bnt1.sums, d.bnt1.scale, d.bnt1.istd, d.bnt1.mistd, nd, B, 240, 16,
-                         (double)B * 240, 1, 0, w.d_t0, GF(BNT1), GF(BNT1 + 1), st));
+                         (double)B * 240, 1, 0, w.d_t0, GF(BNT1), GF(BNT1 + 1), nullptr, st));
   }
   { VG_PROF("layout", st);
   VG_TRY(vg_nhwc_to_nchw(w.d_t0, w.d_f8, nd, 16, 240, st));     // gradient w.r.t. fc8 pre-activation
@@ -651,7 +653,7 @@ static int step_bwd_impl(const VgStepConfig* cfg, const VgStepIO* io, void* work
   }
   { VG_PROF("bn5.bn_bwd", st);
   VG_TRY(vg_bn_bwd_apply(w.d_a4, e.a4, e.bn5.sums, e.bn5.scale, e.bn5.istd, e.bn5.mistd, B, B, vol(kConv[3].out), 16,
-                         (double)B * vol(kConv[3].out), 1, 0, w.d_a4, GF(BN5), GF(BN5 + 1), st));
+                         (double)B * vol(kConv[3].out), 1, 0, w.d_a4, GF(BN5), GF(BN5 + 1), nullptr, st));
   }
   { cudaStream_t ws = fk.branch();
   VG_PROF("conv4.wgrad", ws);
@@ -669,7 +671,7 @@ static int step_bwd_impl(const VgStepConfig* cfg, const VgStepIO* io, void* work
   }
   { VG_PROF("bn3.bn_bwd", st);
   VG_TRY(vg_bn_bwd_apply(w.d_a2, e.a2, e.bn3.sums, e.bn3.scale, e.bn3.istd, e.bn3.mistd, B, B, vol(kConv[1].out), 8,
-                         (double)B * vol(kConv[1].out), 1, 0, w.d_a2, GF(BN3), GF(BN3 + 1), st));
+                         (double)B * vol(kConv[1].out), 1, 0, w.d_a2, GF(BN3), GF(BN3 + 1), nullptr, st));
   }
   { cudaStream_t ws = fk.branch();
   VG_PROF("conv2.wgrad", ws);
@@ -688,7 +690,7 @@ static int step_bwd_impl(const VgStepConfig* cfg, const VgStepIO* io, void* work
   }
   { VG_PROF("bn1.bn_bwd", st);
   VG_TRY(vg_bn_bwd_apply(nullptr, io->x, e.bn1.sums, nullptr, nullptr, nullptr, B, B, V, 1, (double)B * V, 0, 0, nullptr,
-                         GF(BN1), GF(BN1 + 1), st));
+                         GF(BN1), GF(BN1 + 1), nullptr, st));
   }
   }
   if (ready) VG_TRY(fk.make_ready(ready));

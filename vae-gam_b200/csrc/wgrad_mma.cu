@@ -144,6 +144,30 @@ __device__ __forceinline__ void stage_box_bf16(__nv_bfloat16* dst, const float* 
   }
 }
 
+// Same box, but the source is ALREADY bf16 and nothing has to be folded or summed: every 16-byte voxel part goes
+// global -> shared with one cp.async (LDGSTS, zero-filled outside the tensor), no register round trip, and all
+// copies of a tile are in flight together.  The caller waits with cp_async_wait_all() before its __syncthreads().
+template <int C>
+__device__ __forceinline__ void stage_box_async(__nv_bfloat16* dst, const __nv_bfloat16* __restrict__ src, int oD, int oH,
+                                                int oW, int bh, int bw, int nvox, uint32_t mul_h, uint32_t mul_w, int gD,
+                                                int gH, int gW) {
+  static_assert(C % 8 == 0, "16-byte voxel parts");
+  constexpr int PER = C / 8;
+  const int nel = nvox * PER;
+  const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(dst);
+  for (int e = threadIdx.x; e < nel; e += blockDim.x) {
+    const int v = e / PER, part = e & (PER - 1);
+    const int r = fast_div(v, mul_w), l = v - r * bw;
+    const int i = fast_div(r, mul_h), j = r - i * bh;
+    const int gd = oD + i, gh = oH + j, gw = oW + l;
+    const bool ok = gd >= 0 && gd < gD && gh >= 0 && gh < gH && gw >= 0 && gw < gW;
+    const __nv_bfloat16* p = ok ? src + ((((size_t)gd * gH + gh) * gW + gw) * C + part * 8) : src;
+    const uint32_t nbytes = ok ? 16u : 0u;            // 0 source bytes: the 16 destination bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + (uint32_t)e * 16u), "l"(p), "r"(nbytes) : "memory");
+  }
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // CS: channels of the tap-shifted operand (1, 8, 16); CU: channels of the un-shifted operand (8, 16);
 // MT: m16 tiles of (tap, shifted channel) rows a warp accumulates.
 template <int CS, int CU, int MT, int MODE>
@@ -214,12 +238,21 @@ wgrad_mma_kernel(const __grid_constant__ WmGeom g, const float* __restrict__ x, 
     __syncthreads();   // previous tile fully consumed
     // un-shifted tile: clipped to the base grid (voxels of the tile beyond it contribute zeros)
     const int none[6] = {0, 0, 0, 0, 0, 0};
+    // operands that are already bf16 with nothing to fold / sum go straight to shared memory (cp.async)
+    const bool x_async = x16 && !sc, y_async = y16 && !dbias;
     if (MODE == 0) {
       // dY is the un-shifted tile: tiles partition the output grid
       const int own[6] = {q0d, q0d + g.tD, q0h, q0h + g.tH, q0w, q0w + g.tW};
+      if constexpr (CS >= 8) {
+        if (x_async) stage_box_async<CS>(Ssh, reinterpret_cast<const __nv_bfloat16*>(xn), q0d * g.s, q0h * g.s, q0w * g.s, g.sH, g.sW,
+                                         box_vox, g.mul_sH, g.mul_sW, g.xD, g.xH, g.xW);
+      }
+      if (!(CS >= 8 && x_async))
       stage_box_bf16<CS, false, UV>(Ssh, xn, q0d * g.s, q0h * g.s, q0w * g.s, g.sH, g.sW, box_vox, g.mul_sH, g.mul_sW, g.xD, g.xH,
                                 g.xW, sc, sh, none, bsum, x16);
-      if (dbias) stage_box_bf16<CU, true, UV>(Sun, yn, q0d, q0h, q0w, g.tH, g.tW, tile_vox, g.mul_tH, g.mul_tW, g.yD, g.yH, g.yW,
+      if (y_async) stage_box_async<CU>(Sun, reinterpret_cast<const __nv_bfloat16*>(yn), q0d, q0h, q0w, g.tH, g.tW, tile_vox, g.mul_tH,
+                                       g.mul_tW, g.yD, g.yH, g.yW);
+      else if (dbias) stage_box_bf16<CU, true, UV>(Sun, yn, q0d, q0h, q0w, g.tH, g.tW, tile_vox, g.mul_tH, g.mul_tW, g.yD, g.yH, g.yW,
                                           nullptr, nullptr, own, bsum, y16);
       else stage_box_bf16<CU, false, UV>(Sun, yn, q0d, q0h, q0w, g.tH, g.tW, tile_vox, g.mul_tH, g.mul_tW, g.yD, g.yH, g.yW,
                                      nullptr, nullptr, none, bsum, y16);
@@ -229,9 +262,17 @@ wgrad_mma_kernel(const __grid_constant__ WmGeom g, const float* __restrict__ x, 
       const int own[6] = {td == 0 ? 0 : q0d * g.s - g.pD, td == g.nTd - 1 ? g.yD : (q0d + g.tD) * g.s - g.pD,
                           th == 0 ? 0 : q0h * g.s - g.pH, th == g.nTh - 1 ? g.yH : (q0h + g.tH) * g.s - g.pH,
                           tw == 0 ? 0 : q0w * g.s - g.pW, tw == g.nTw - 1 ? g.yW : (q0w + g.tW) * g.s - g.pW};
+      if (x_async) stage_box_async<CU>(Sun, reinterpret_cast<const __nv_bfloat16*>(xn), q0d, q0h, q0w, g.tH, g.tW, tile_vox, g.mul_tH,
+                                       g.mul_tW, g.xD, g.xH, g.xW);
+      else
       stage_box_bf16<CU, false, UV>(Sun, xn, q0d, q0h, q0w, g.tH, g.tW, tile_vox, g.mul_tH, g.mul_tW, g.xD, g.xH, g.xW, sc, sh,
                                 none, bsum, x16);
-      if (dbias) stage_box_bf16<CS, true, UV>(Ssh, yn, q0d * g.s - g.pD, q0h * g.s - g.pH, q0w * g.s - g.pW, g.sH, g.sW, box_vox,
+      if constexpr (CS >= 8) {
+        if (y_async) stage_box_async<CS>(Ssh, reinterpret_cast<const __nv_bfloat16*>(yn), q0d * g.s - g.pD, q0h * g.s - g.pH,
+                                         q0w * g.s - g.pW, g.sH, g.sW, box_vox, g.mul_sH, g.mul_sW, g.yD, g.yH, g.yW);
+      }
+      if (CS >= 8 && y_async) {
+      } else if (dbias) stage_box_bf16<CS, true, UV>(Ssh, yn, q0d * g.s - g.pD, q0h * g.s - g.pH, q0w * g.s - g.pW, g.sH, g.sW, box_vox,
                                           g.mul_sH, g.mul_sW, g.yD, g.yH, g.yW, nullptr, nullptr, own, bsum, y16);
       else stage_box_bf16<CS, false, UV>(Ssh, yn, q0d * g.s - g.pD, q0h * g.s - g.pH, q0w * g.s - g.pW, g.sH, g.sW, box_vox,
                                      g.mul_sH, g.mul_sW, g.yD, g.yH, g.yW, nullptr, nullptr, none, bsum, y16);
@@ -239,6 +280,7 @@ wgrad_mma_kernel(const __grid_constant__ WmGeom g, const float* __restrict__ x, 
     // zero the un-shifted rows of the last chunk's padding (tile_vox .. 16*nchunks)
     for (int e = threadIdx.x; e < (nchunks * 16 - tile_vox) * CU / 8; e += blockDim.x)
       reinterpret_cast<uint4*>(Sun + (size_t)tile_vox * CU)[e] = make_uint4(0u, 0u, 0u, 0u);
+    cp_async_wait_all();
     __syncthreads();
     if (tap_lo >= tap_hi) continue;
 

@@ -107,7 +107,7 @@ SIGNATURES = {
     "vg_conv_wgrad": (_I, [C.POINTER(VgConvDesc), _P, _P, _P, _P, _P, _P, _P]),
     "vg_bn_stats": (_I, [_P, _I, _I, _LL, _I, _P, _P]),
     "vg_bn_finalize": (_I, [_P, _P, _P, _I, _I, _D, _P, _P, _P, _P, _P]),
-    "vg_bn_bwd_apply": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _LL, _I, _D, _I, _I, _P, _P, _P, _P]),
+    "vg_bn_bwd_apply": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _LL, _I, _D, _I, _I, _P, _P, _P, _P, _P]),
     "vg_nchw_to_nhwc": (_I, [_P, _P, _I, _I, _LL, _P]),
     "vg_nhwc_to_nchw": (_I, [_P, _P, _I, _I, _LL, _P]),
     "vg_linear_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
