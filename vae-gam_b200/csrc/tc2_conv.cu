@@ -104,7 +104,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1)
 tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_constant__ T2Plan pl,
            const __grid_constant__ CUtensorMap tmap) {
   static_assert(!TMA || (CIN == 8 && SD == 1), "TMA-direct staging: 8 bf16 channels = one 16-byte word per voxel, unit stride");
-  constexpr int ES = TMA ? 2 : t2_epi_sets(CIN, COUT, SD);
+  // TMA mode has no producer warps: 12 epilogue warps (3 sets), warp 12 issues the TMA loads, warps 13..15 the MMAs
+  constexpr int ES = TMA ? 3 : t2_epi_sets(CIN, COUT, SD);
+  constexpr int MMA_WARP0 = TMA ? 13 : T2_MMA_WARP, NMW = 16 - MMA_WARP0;      // MMA issuer warps
   constexpr int NSG = SD == 2 ? 4 : 1;
   constexpr int EPI_WARPS = 4 * ES, PROD_WARPS = 12 - EPI_WARPS, PT = PROD_WARPS * 32;
   constexpr int MAXC = t2_max_chunk(CIN, ES, SD);
@@ -134,10 +136,10 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
   if (tid == 0) {
     for (int s = 0; s < pl.R; ++s) {
       mbar_init(smem_u32(&full_bar[s]), TMA ? 1u : (uint32_t)PT);
-      mbar_init(smem_u32(&empty_bar[s]), (uint32_t)pl.nrb);
+      mbar_init(smem_u32(&empty_bar[s]), (uint32_t)min(pl.nrb, NMW));     // one commit per MMA issuer warp
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(smem_u32(&accf_bar[b]), (uint32_t)pl.nrb);
+      mbar_init(smem_u32(&accf_bar[b]), (uint32_t)min(pl.nrb, NMW));
       mbar_init(smem_u32(&acce_bar[b]), EPI_WARPS * 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;");
@@ -276,22 +278,34 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
     const bool want_stats = a.stats != nullptr, want_bn = a.aux_mode == 2;
     const int eset = warp >> 2, etid = tid & 127;            // TMEM lane = etid
     const int ipr = pl.ACCW >> 4, nitems = pl.nrb * ipr;     // 16-column items per row block / per accumulator
-    const size_t plane_out = (size_t)g.outH * g.outW * COUT;
-    struct Item { int rb, k, qd, bofs; bool row_ok; size_t o0; };
+    const int ipr_shift = 31 - __clz(ipr);                   // ACCW is 16, 32, 64 or 128: ipr is a power of two
+    const uint32_t plane_out = (uint32_t)(g.outH * g.outW * COUT);   // offsets inside ONE image fit 32 bits
+    const uint32_t plane_step = (uint32_t)g.sout * plane_out;
+    const bool relu = a.act == VG_ACT_RELU, sigm = a.act == VG_ACT_SIGMOID;
+    // Item = 16 accumulator columns (NJ output planes x COUT) of one 128-row block.  Everything that depends on
+    // the ROW only (division by the pitch, validity, offset inside the plane, bias class) is computed once per
+    // row block and reused by the items that share it.
+    struct Item { int rb, k, qd, bofs; bool row_ok; uint32_t off; };
     const int cls_hw = TMA ? s_ncls[1] * s_ncls[2] * COUT : 0;
     // bias of a voxel whose taps are all inside the input (the bulk): kept in registers; only border voxels (or border
     // planes) read the class table.  Interior class = the class of the middle coordinate.
     int cls_mid[3] = {0, 0, 0};
-    float b_mid[COUT];
+    constexpr bool BREG = COUT < 8;            // few channels: the bulk bias lives in registers, else it is a broadcast LDS
+    float b_mid[BREG ? COUT : 1];
+    const float* b_mid_s = s_bias;
     bool one_cls = true;
     if constexpr (TMA) {
       cls_mid[0] = s_cls[0][min(g.outD / 2, 63)]; cls_mid[1] = s_cls[1][min(g.outH / 2, 63)]; cls_mid[2] = s_cls[2][min(g.outW / 2, 63)];
       one_cls = s_ncls[0] * s_ncls[1] * s_ncls[2] == 1;
+      b_mid_s = s_btab + cls_mid[0] * cls_hw + (cls_mid[1] * s_ncls[2] + cls_mid[2]) * COUT;
+    }
+    if constexpr (BREG) {
 #pragma unroll
-      for (int c = 0; c < COUT; ++c) b_mid[c] = s_btab[cls_mid[0] * cls_hw + (cls_mid[1] * s_ncls[2] + cls_mid[2]) * COUT + c];
+      for (int c = 0; c < COUT; ++c) b_mid[c] = b_mid_s[c];
     }
     const int mid_bofs = (cls_mid[1] * (TMA ? s_ncls[2] : 0) + cls_mid[2]) * COUT;
     const int mid_d0 = TMA ? s_midrange[0] : 0, mid_d1 = TMA ? s_midrange[1] : 0;
+    const uint32_t pw_mul = (uint32_t)((0x100000000ULL + (uint64_t)pl.PW - 1) / (uint64_t)pl.PW);   // exact r / PW for r * PW < 2^32
     for (int col = col_first; col < col_count; col += col_step) {
       // d-chunk major: the chunks of an image differ in length (the last one is short), so all the long columns come
       // first and a CTA's round-robin share mixes long and short ones whatever the parity of the grid
@@ -299,6 +313,11 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
       const int qd0 = dc * pl.dchunk, qd1 = min(pl.qDmax, qd0 + pl.dchunk);
       const int nblocks = (qd1 - qd0 + pl.OB - 1) / pl.OB;
       const int grp = n / g.group_size;
+      // image bases (64-bit once per column); bf16 tensors have the same element offsets at half the size
+      float* const out_n = a.out ? (a.out_bf16 ? reinterpret_cast<float*>(reinterpret_cast<__nv_bfloat16*>(a.out) + (size_t)n * g.out_img)
+                                               : a.out + (size_t)n * g.out_img) : nullptr;
+      const float* const aux_n = a.aux ? (a.aux_bf16 ? reinterpret_cast<const float*>(reinterpret_cast<const __nv_bfloat16*>(a.aux) + (size_t)n * g.out_img)
+                                                     : a.aux + (size_t)n * g.out_img) : nullptr;
       float istd[COUT], mistd[COUT], s1[COUT], s2[COUT];
 #pragma unroll
       for (int c = 0; c < COUT; ++c) {
@@ -311,32 +330,41 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
           const T2Phase& P = pl.ph[ph];
           const int au = acc_base + b * pl.nph + ph, buf = au & 1;
           const int qd_end = min((int)P.qD, qd1);
+          const uint32_t ph_off = (uint32_t)P.rD * plane_out + ((uint32_t)P.rH * (uint32_t)g.outW + (uint32_t)P.rW) * COUT;
+          // row cache: valid for the row block `c_rb` of this (column, phase)
+          int c_rb = -1, c_bofs = mid_bofs;
+          bool c_ok = false;
+          uint32_t c_rowoff = 0;
           auto setup = [&](int it, Item& I) {
-            I.rb = it / ipr; I.k = it - I.rb * ipr;
-            int qh, qw;
-            if constexpr (TMA) {                  // tile = hb whole lines of the row frame
-              const int rl = I.rb * 128 + etid, lh = rl / pl.PW;
-              qh = t * pl.hb + lh; qw = rl - lh * pl.PW;
-              I.row_ok = lh < pl.hb && qh < P.qH && qw < P.qW;
-              I.bofs = (I.row_ok && !one_cls) ? (s_cls[1][min(qh, 63)] * s_ncls[2] + s_cls[2][min(qw, 63)]) * COUT : mid_bofs;
-            } else {
-              const int r = t * pl.TR + I.rb * 128 + etid;
-              qh = r / pl.PW; qw = r - qh * pl.PW;
-              I.row_ok = qh < P.qH && qw < P.qW;
-              I.bofs = 0;
+            I.rb = it >> ipr_shift; I.k = it & (ipr - 1);
+            if (I.rb != c_rb) {
+              c_rb = I.rb;
+              int qh, qw;
+              if constexpr (TMA) {                  // tile = hb whole lines of the row frame
+                const int rl = I.rb * 128 + etid, lh = (int)__umulhi((uint32_t)rl, pw_mul);
+                qh = t * pl.hb + lh; qw = rl - lh * pl.PW;
+                c_ok = lh < pl.hb && qh < P.qH && qw < P.qW;
+                c_bofs = (c_ok && !one_cls) ? (s_cls[1][min(qh, 63)] * s_ncls[2] + s_cls[2][min(qw, 63)]) * COUT : mid_bofs;
+              } else {
+                const int r = t * pl.TR + I.rb * 128 + etid;
+                qh = (int)__umulhi((uint32_t)r, pw_mul); qw = r - qh * pl.PW;
+                c_ok = qh < P.qH && qw < P.qW;
+              }
+              c_rowoff = ph_off + ((uint32_t)(qh * g.sout) * (uint32_t)g.outW + (uint32_t)(qw * g.sout)) * COUT;
             }
+            I.row_ok = c_ok; I.bofs = c_bofs;
             I.qd = qd0 + b * pl.OB + I.k * NJ;
-            I.o0 = (size_t)n * g.out_img + (size_t)(I.qd * g.sout + P.rD) * plane_out +
-                   ((size_t)(qh * g.sout + P.rH) * g.outW + (size_t)(qw * g.sout + P.rW)) * COUT;
+            I.off = (uint32_t)I.qd * plane_step + c_rowoff;
           };
           auto load_aux = [&](const Item& I, float (&ax)[NJ][COUT]) {
             if (a.aux_mode == 0 || !I.row_ok) return;
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
               if (I.qd + j >= qd_end) continue;
+              const uint32_t off = I.off + (uint32_t)j * plane_step;
               if constexpr (COUT % 8 == 0) {
                 if (a.aux_bf16) {                 // saved activation stored as bf16: one 16-byte word per 8 channels
-                  const __nv_bfloat16* pb = reinterpret_cast<const __nv_bfloat16*>(a.aux) + I.o0 + (size_t)j * g.sout * plane_out;
+                  const __nv_bfloat16* pb = reinterpret_cast<const __nv_bfloat16*>(aux_n) + off;
 #pragma unroll
                   for (int i = 0; i < COUT / 8; ++i) {      // raw words only: unpacked at use, so the load stays in flight
                     const uint4 q = ldg_u4(pb + 8 * i);
@@ -346,7 +374,7 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
                   continue;
                 }
               }
-              const float* p = a.aux + I.o0 + (size_t)j * g.sout * plane_out;
+              const float* p = aux_n + off;
               if constexpr (COUT % 4 == 0) {
 #pragma unroll
                 for (int i = 0; i < COUT / 4; ++i) {
@@ -370,51 +398,47 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
               if (I.qd + j >= qd_end) continue;
+              const uint32_t off = I.off + (uint32_t)j * plane_step;
               float y[COUT];
-              float bv[COUT];
+              const float* bsrc = BREG ? nullptr : b_mid_s;        // border voxel / border plane: bias from the class table
               if constexpr (TMA) {
                 const int od = I.qd + j;
-                const bool mid_plane = one_cls || (od >= mid_d0 && od < mid_d1);    // same d-class as the middle plane
-                if (mid_plane && I.bofs == mid_bofs) {
-#pragma unroll
-                  for (int c = 0; c < COUT; ++c) bv[c] = b_mid[c];
-                } else {
-                  const float* bsrc = s_btab + s_cls[0][min(od, 63)] * cls_hw + I.bofs;
-#pragma unroll
-                  for (int c = 0; c < COUT; ++c) bv[c] = bsrc[c];
-                }
-              } else {
-#pragma unroll
-                for (int c = 0; c < COUT; ++c) bv[c] = s_bias[c];
+                if (!one_cls && !(od >= mid_d0 && od < mid_d1 && I.bofs == mid_bofs))
+                  bsrc = s_btab + s_cls[0][min(od, 63)] * cls_hw + I.bofs;
               }
 #pragma unroll
               for (int c = 0; c < COUT; ++c) {
-                float v = __uint_as_float(rr[j * COUT + c]) + bv[c];
-                if (a.act == VG_ACT_RELU) v = fmaxf(v, 0.f);
-                else if (a.act == VG_ACT_SIGMOID) v = 1.f / (1.f + __expf(-v));
+                float bc;
+                if constexpr (BREG) bc = bsrc ? bsrc[c] : b_mid[c];
+                else bc = bsrc[c];
+                float v = __uint_as_float(rr[j * COUT + c]) + bc;
+                if (relu) v = fmaxf(v, 0.f);
+                else if (sigm) v = 1.f / (1.f + __expf(-v));
                 y[c] = v;
               }
-              float av[COUT];
+              if (a.aux_mode != 0) {
+                float av[COUT];
 #pragma unroll
-              for (int c = 0; c < COUT; ++c) av[c] = ax[j][c];
-              if constexpr (COUT % 8 == 0) {
-                if (a.aux_bf16) {
+                for (int c = 0; c < COUT; ++c) av[c] = ax[j][c];
+                if constexpr (COUT % 8 == 0) {
+                  if (a.aux_bf16) {
 #pragma unroll
-                  for (int c = 0; c < COUT / 2; ++c) {
-                    const uint32_t wv = __float_as_uint(ax[j][c]);
-                    av[2 * c] = bf16_lo(wv); av[2 * c + 1] = bf16_hi(wv);
+                    for (int c = 0; c < COUT / 2; ++c) {
+                      const uint32_t wv = __float_as_uint(ax[j][c]);
+                      av[2 * c] = bf16_lo(wv); av[2 * c + 1] = bf16_hi(wv);
+                    }
                   }
                 }
-              }
-              if (a.aux_mode == 1) {
+                if (a.aux_mode == 1) {
 #pragma unroll
-                for (int c = 0; c < COUT; ++c) y[c] = av[c] > 0.f ? y[c] : 0.f;
-              } else if (a.aux_mode == 2) {
+                  for (int c = 0; c < COUT; ++c) y[c] = av[c] > 0.f ? y[c] : 0.f;
+                } else {
 #pragma unroll
-                for (int c = 0; c < COUT; ++c) {
-                  const float xh = fmaf(av[c], istd[c], -mistd[c]);
-                  s1[c] += y[c];
-                  s2[c] = fmaf(y[c], xh, s2[c]);
+                  for (int c = 0; c < COUT; ++c) {
+                    const float xh = fmaf(av[c], istd[c], -mistd[c]);
+                    s1[c] += y[c];
+                    s2[c] = fmaf(y[c], xh, s2[c]);
+                  }
                 }
               }
               if (want_stats) {
@@ -424,10 +448,10 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
                   s2[c] = fmaf(y[c], y[c], s2[c]);
                 }
               }
-              if (a.out) {
+              if (out_n) {
                 if constexpr (COUT % 8 == 0) {
                   if (a.out_bf16) {
-                    __nv_bfloat16* pb = reinterpret_cast<__nv_bfloat16*>(a.out) + I.o0 + (size_t)j * g.sout * plane_out;
+                    __nv_bfloat16* pb = reinterpret_cast<__nv_bfloat16*>(out_n) + off;
 #pragma unroll
                     for (int i = 0; i < COUT / 8; ++i) {
                       float f[8];
@@ -438,7 +462,7 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
                     continue;
                   }
                 }
-                float* p = a.out + I.o0 + (size_t)j * g.sout * plane_out;
+                float* p = out_n + off;
                 if constexpr (COUT % 4 == 0) {
 #pragma unroll
                   for (int i = 0; i < COUT / 4; ++i)
@@ -759,12 +783,13 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
       pair_base += npairs;
       acc_base += nblocks * pl.nph;
     }
-  } else if (warp - T2_MMA_WARP < pl.nrb) {
-    // ================================================================ MMA warps (one per 128-row block)
+  } else if (warp >= MMA_WARP0 && warp - MMA_WARP0 < pl.nrb) {
+    // ================================================================ MMA warps (one per 128-row block; with fewer
+    // issuer warps than row blocks a warp also takes the row blocks NMW further on)
     // The whole warp walks the loops (uniform control flow, waits included); one elected lane
     // issues the tcgen05.mma / tcgen05.commit instructions, so operands stay in uniform registers.
-    const int rb = warp - T2_MMA_WARP;
-    const uint32_t ring16 = (smem_u32(ring) >> 4) + (uint32_t)rb * 128u, w16 = smem_u32(wts) >> 4;
+    const int rb0 = warp - MMA_WARP0;
+    const uint32_t ring16 = (smem_u32(ring) >> 4), w16 = smem_u32(wts) >> 4;
     const uint32_t lbo_field = ((uint32_t)(NSG * SRB) >> 4) << 16;
     const uint32_t a_hi = (128u >> 4) | (1u << 14), b_hi = (256u >> 4) | (1u << 14);
     for (int col = col_first; col < col_count; col += col_step) {
@@ -776,7 +801,6 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
           const int au = acc_base + b * pl.nph + ph, buf = au & 1;
           mbar_wait(smem_u32(&acce_bar[buf]), (uint32_t)(((au >> 1) & 1) ^ 1));
           tc_fence_after();
-          const uint32_t d_buf = tmem_base + (uint32_t)((buf * pl.nrb + rb) * pl.ACCW);
           const bool last_ph = ph == pl.nph - 1;
           for (int p = 0; p < pl.NPAIR; ++p) {
             const int G = pair_base + b * H2 + p, slot = G % pl.R, use = G / pl.R;
@@ -785,13 +809,16 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
               tc_fence_after();
             }
             if (elect_one()) {
-              const uint32_t a_lo0 = ((ring16 + (uint32_t)slot * ((uint32_t)PAIRB >> 4)) & 0x3FFFu) | lbo_field;
               const int m1 = pl.ph[ph].pair_begin[p + 1];
+              for (int rb = rb0; rb < pl.nrb; rb += NMW) {
+                const uint32_t d_buf = tmem_base + (uint32_t)((buf * pl.nrb + rb) * pl.ACCW);
+                const uint32_t a_lo0 = ((ring16 + (uint32_t)rb * 128u + (uint32_t)slot * ((uint32_t)PAIRB >> 4)) & 0x3FFFu) | lbo_field;
 #pragma unroll 4
-              for (int m = pl.ph[ph].pair_begin[p]; m < m1; ++m) {
-                const T2Mma e = pl.mma[m];
-                umma_bf16(d_buf + e.dcol, ((uint64_t)a_hi << 32) | (uint64_t)(a_lo0 + e.a_shift),
-                          ((uint64_t)b_hi << 32) | (uint64_t)(e.b_lo + w16), e.idesc, 1u);
+                for (int m = pl.ph[ph].pair_begin[p]; m < m1; ++m) {
+                  const T2Mma e = pl.mma[m];
+                  umma_bf16(d_buf + e.dcol, ((uint64_t)a_hi << 32) | (uint64_t)(a_lo0 + e.a_shift),
+                            ((uint64_t)b_hi << 32) | (uint64_t)(e.b_lo + w16), e.idesc, 1u);
+                }
               }
               if (last_ph && (p < H2 || b == nblocks - 1)) umma_commit(smem_u32(&empty_bar[slot]));
               if (p == pl.NPAIR - 1) umma_commit(smem_u32(&accf_bar[buf]));

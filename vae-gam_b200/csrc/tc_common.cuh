@@ -62,7 +62,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "=r"(done)
         : "r"(bar), "r"(parity)
         : "memory");
-    if (!done && spin > (1 << 22)) asm volatile("trap;");
+    if (!done) {
+      __nanosleep(32);                               // waiting warps must not eat the issue slots of the working ones
+      if (spin > (1 << 22)) asm volatile("trap;");
+    }
   }
 }
 
