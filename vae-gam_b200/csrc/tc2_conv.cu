@@ -509,7 +509,7 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
       pair_base += nblocks * H2 + (pl.NPAIR - H2);
       acc_base += nblocks * pl.nph;
     }
-  } else if (TMA && warp < T2_MMA_WARP) {
+  } else if (TMA && warp < MMA_WARP0) {
     // ================================================================ TMA producer: one elected lane of one warp
     if constexpr (TMA) {
       if (warp == EPI_WARPS) {
@@ -540,7 +540,7 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
         }
       }
     }
-  } else if (warp < T2_MMA_WARP) {
+  } else if (!TMA && warp < T2_MMA_WARP) {
     // ================================================================ producer warps
     const int ptid = tid - EPI_WARPS * 32;
     const bool affine = a.in_scale != nullptr;
