@@ -140,6 +140,31 @@ int vg_conv_wgrad(const VgConvDesc* d, const void* x, const void* dy, const floa
                   const float* in_shift, float* dw, float* dbias, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Fused backward of a BatchNorm -> ConvTranspose3d(k = 3, stride 1, one output channel) junction
+ * (bnt5 -> convt5, vae_reg_GP.py:264; autograd of :215,218).  Instead of data gradient -> statistics ->
+ * separate BatchNorm-backward pass over the largest tensor of the step, the statistics come from the
+ * WEIGHT-gradient products, which do not depend on the data gradient:
+ *   vg_box_sums            out (groups, 28) fp64 (caller zeroes): box sums of dy per tap + total
+ *   vg_conv_wgrad_grouped  raw (groups, taps, cs, cu) fp32 (caller zeroes): per-group products of the
+ *                          UN-normalised x with dy (x may be bf16: staged with asynchronous copies)
+ *   vg_bn_fused_finalize   -> dw, dbias of the convolution, dgamma, dbeta of the BatchNorm (all
+ *                          ACCUMULATED) and coef (groups, c, 3) for the apply
+ *   vg_conv_dgrad_bn_apply dx = (bn_x > 0) * (A * conv^T(dy) + B * bn_x + C): the gradient w.r.t. the
+ *                          pre-ReLU activation of the layer BEFORE the BatchNorm, written once (bf16
+ *                          with VG_BF16_DX); dx_chan_sum (cin, accumulated, may be NULL) = that
+ *                          layer's bias gradient.
+ * ---------------------------------------------------------------------------------- */
+int vg_box_sums(const float* dy, int n, int group_size, const int32_t* y_dims, long long y_img_stride,
+                const int32_t* x_dims, const int32_t* pad, double* out, void* stream);
+int vg_conv_wgrad_grouped(const VgConvDesc* d, const void* x, const void* dy, float* raw, void* stream);
+int vg_bn_fused_finalize(const float* raw, const double* box, const float* w, const float* scale,
+                         const float* shift, const float* istd, const float* mistd, int groups, int c,
+                         double count, float* dw, float* dbias, float* dgamma, float* dbeta, float* coef,
+                         void* stream);
+int vg_conv_dgrad_bn_apply(const VgConvDesc* d, const void* dy, const float* w, void* dx, const void* bn_x,
+                           const float* coef, float* dx_chan_sum, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Batch-norm helpers (nn.BatchNorm3d(track_running_stats=False), vae_reg_GP.py:194-196,
  * 216-218; applied at :238,240,242,260,262,264).
  * ---------------------------------------------------------------------------------- */

@@ -305,6 +305,74 @@ def test_conv_bf16_activation_storage(lib, name):
         assert rel_err(dw2.cpu(), dw0.cpu()) < 2e-5, ("wgrad without bias", mask)
 
 
+@pytest.mark.parametrize("in_", [(9, 11, 7), (39, 47, 33)], ids=["small", "bnt5_convt5"])
+def test_fused_bn_backward_junction(lib, in_):
+    """relu -> BatchNorm(batch statistics per group) -> ConvTranspose3d(8 -> 1, k3): the fused backward
+    (vg_box_sums + vg_conv_wgrad_grouped + vg_bn_fused_finalize + vg_conv_dgrad_bn_apply, x stored as bf16) against
+    PyTorch autograd of the same junction in fp32.  The tensor-core passes round dy and W to bf16: 1e-2."""
+    native = nat()
+    dev = "cuda"
+    N, group, cin = 4, 2, 8
+    G = N // group
+    gen = torch.Generator(device=dev).manual_seed(5)
+    x = bf16r(torch.relu(torch.randn(N, cin, *in_, device=dev, generator=gen) + 0.3))       # the stored activation
+    w = torch.randn(cin, 1, 3, 3, 3, device=dev, generator=gen) * 0.2
+    gamma = torch.rand(cin, device=dev, generator=gen) + 0.5
+    beta = torch.randn(cin, device=dev, generator=gen) * 0.3
+    out_dims = tuple(i + 2 for i in in_)
+    dpre = torch.randn(N, 1, *out_dims, device=dev, generator=gen)
+    # ---- reference: autograd
+    xr = x.clone().requires_grad_(True)
+    wr, gr, br = w.clone().requires_grad_(True), gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    bias = torch.zeros(1, device=dev, requires_grad=True)
+    outs = []
+    for gi in range(G):
+        xn = F.batch_norm(xr[gi * group:(gi + 1) * group], None, None, gr, br, True, 0.0, 1e-5)
+        outs.append(F.conv_transpose3d(xn, wr, bias))
+    (torch.cat(outs) * dpre).sum().backward()
+    du_ref = xr.grad * (x > 0)
+    # ---- BatchNorm coefficients per (group, channel), as vg_bn_finalize gives them
+    xg = x.reshape(G, group, cin, -1)
+    mean = xg.mean((1, 3)); var = xg.var((1, 3), unbiased=False)
+    istd = 1.0 / torch.sqrt(var + 1e-5)
+    scale = (gamma[None] * istd).contiguous(); shift = (beta[None] - mean * scale).contiguous()
+    mistd = (mean * istd).contiguous(); istd = istd.contiguous()
+    spatial = in_[0] * in_[1] * in_[2]
+    count = float(group * spatial)
+    # ---- fused path
+    st = native.stream_ptr()
+    d = native.conv_desc(1, cin, 1, (3, 3, 3), 1, in_, N, group, arith=native.ARITH_BF16,
+                         bf16_mask=native.BF16_X | native.BF16_DX)
+    x16 = to_cl(x).to(torch.bfloat16)
+    dpre_cl = to_cl(dpre)
+    box = torch.zeros(G, 28, dtype=torch.float64, device=dev)
+    I3 = C.c_int32 * 3
+    native.check(lib.vg_box_sums(native.ptr(dpre_cl), N, group, I3(*out_dims), 0, I3(*in_), I3(0, 0, 0), native.ptr(box), st))
+    raw = torch.zeros(G, 27, 1, cin, device=dev)
+    native.check(lib.vg_conv_wgrad_grouped(C.byref(d), native.ptr(x16), native.ptr(dpre_cl), native.ptr(raw), st))
+    dw, dbias = torch.zeros_like(w), torch.zeros(1, device=dev)
+    dgamma, dbeta = torch.zeros(cin, device=dev), torch.zeros(cin, device=dev)
+    coef = torch.empty(G, cin, 3, device=dev)
+    native.check(lib.vg_bn_fused_finalize(native.ptr(raw), native.ptr(box), native.ptr(w), native.ptr(scale), native.ptr(shift),
+                                          native.ptr(istd), native.ptr(mistd), G, cin, count, native.ptr(dw), native.ptr(dbias),
+                                          native.ptr(dgamma), native.ptr(dbeta), native.ptr(coef), st))
+    du = torch.empty(N, *in_, cin, device=dev, dtype=torch.bfloat16)
+    csum = torch.zeros(cin, device=dev)
+    native.check(lib.vg_conv_dgrad_bn_apply(C.byref(d), native.ptr(dpre_cl), native.ptr(w), native.ptr(du), native.ptr(x16),
+                                            native.ptr(coef), native.ptr(csum), st))
+    torch.cuda.synchronize()
+    # box sums are exact fp32 sums
+    want_total = dpre.reshape(G, -1).double().sum(1)
+    assert rel_err(box[:, 27].cpu(), want_total.cpu()) < 1e-5
+    assert rel_err(box[:, 0].cpu(), dpre[:, 0, :in_[0], :in_[1], :in_[2]].reshape(G, -1).double().sum(1).cpu()) < 1e-5
+    assert rel_err(dw.cpu(), wr.grad.cpu()) < 1e-2, rel_err(dw.cpu(), wr.grad.cpu())
+    assert rel_err(dbias.cpu(), bias.grad.cpu()) < 1e-4
+    assert rel_err(dgamma.cpu(), gr.grad.cpu()) < 1e-2 and rel_err(dbeta.cpu(), br.grad.cpu()) < 1e-2
+    got = from_cl(du.float())
+    assert rel_err(got.cpu(), du_ref.cpu()) < 1.5e-2, rel_err(got.cpu(), du_ref.cpu())
+    assert rel_err(csum.cpu(), got.sum((0, 2, 3, 4)).cpu()) < 1e-3
+
+
 @pytest.mark.parametrize("name", list(LAYERS))
 def test_conv_forward_dgrad_wgrad(lib, name):
     native = nat()

@@ -234,6 +234,102 @@ bn_bwd_apply8_kernel(const float* __restrict__ dy, const void* __restrict__ x_, 
   }
 }
 
+// ---- fused BatchNorm backward of a BatchNorm -> ConvTranspose3d(k3, s1) junction (bnt5 -> convt5) ------------------
+// Box sums of a one-channel gradient: out[g][t] = sum_{n in g} sum_{v in x-grid} dy(n, v + tap_t - pad), t = (a,b,c) in
+// 3x3x3, plus out[g][27] = sum of all of dy.  One block per (image, d-plane); a voxel's contribution to the nine
+// (b, c) taps is decided by its (h, w), to the three a's by its d.
+__global__ void __launch_bounds__(256)
+box_sums_kernel(const float* __restrict__ dy, int group_size, int yD, int yH, int yW, long long y_img, int xD, int xH, int xW,
+                int pD, int pH, int pW, double* out) {
+  const int n = blockIdx.y, d = blockIdx.x;
+  const float* p = dy + (size_t)n * y_img + (size_t)d * yH * yW;
+  float acc[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) acc[i] = 0.f;
+  for (int e = threadIdx.x; e < yH * yW; e += blockDim.x) {
+    const int h = e / yW, w = e - h * yW;
+    const float v = __ldg(p + e);
+    acc[9] += v;
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      const int xh = h - b + pH;
+      if (xh < 0 || xh >= xH) continue;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int xw = w - c + pW;
+        if (xw >= 0 && xw < xW) acc[b * 3 + c] += v;
+      }
+    }
+  }
+  __shared__ float red[10];
+  if (threadIdx.x < 10) red[threadIdx.x] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const float r = warp_sum(acc[i]);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&red[i], r);
+  }
+  __syncthreads();
+  double* o = out + (size_t)(n / group_size) * 28;
+  if (threadIdx.x < 27) {
+    const int a = threadIdx.x / 9, bc = threadIdx.x % 9;
+    const int xd = d - a + pD;
+    if (xd >= 0 && xd < xD) atomicAdd(o + threadIdx.x, (double)red[bc]);
+  } else if (threadIdx.x == 27) {
+    atomicAdd(o + 27, (double)red[9]);
+  }
+}
+
+// From the per-group raw products R[g][t][c] = sum x(v,c) dy(v + t) (x = the BatchNorm INPUT, un-normalised), the box
+// sums D0[g][t] and the layer's weights W[c][t] (ConvTranspose3d with one output channel): everything the junction's
+// backward needs that is not per-voxel.
+//   weight gradient   dW[c][t] += sum_g scale[g,c] R[g,t,c] + shift[g,c] D0[g,t];   dbias += sum_g D0[g][27]
+//   BatchNorm sums    s1[g,c] = sum_t W[c,t] D0[g,t];  s2[g,c] = sum_t W[c,t] (istd[g,c] R[g,t,c] - mistd[g,c] D0[g,t])
+//   (s1 = sum of the data gradient, s2 = sum of data gradient x xhat: the identities hold because every tap of a
+//    full transposed convolution with stride 1 is inside the output for every input voxel)
+//   dgamma[c] += sum_g s2, dbeta[c] += sum_g s1
+//   apply coefficients  dx = (x > 0) * (A dy + B x + C):  A = scale, B = -scale m2 istd, C = scale (mistd m2 - m1),
+//   m1 = s1 / count, m2 = s2 / count  ->  coef[g][c][0..2]
+__global__ void bn_fused_finalize_kernel(const float* __restrict__ raw, const double* __restrict__ box, const float* __restrict__ w,
+                                         const float* __restrict__ scale, const float* __restrict__ shift,
+                                         const float* __restrict__ istd, const float* __restrict__ mistd, int groups, int c,
+                                         double count, float* dw, float* dbias, float* dgamma, float* dbeta, float* coef) {
+  // one warp per channel; lanes over taps
+  const int ch = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (ch >= c) return;
+  double dg = 0.0, db = 0.0;
+  float dwt = 0.f;
+  for (int g = 0; g < groups; ++g) {
+    const int gc = g * c + ch;
+    double s1 = 0.0, s2 = 0.0;
+    if (lane < 27) {
+      const double r = (double)raw[((size_t)g * 27 + lane) * c + ch], d0 = box[(size_t)g * 28 + lane];
+      const double wv = (double)w[(size_t)ch * 27 + lane];          // ConvTranspose3d weight (cin, 1, 3, 3, 3)
+      s1 = wv * d0;
+      s2 = wv * ((double)istd[gc] * r - (double)mistd[gc] * d0);
+      dwt += (float)((double)scale[gc] * r + (double)shift[gc] * d0);
+    }
+    s1 = warp_sum(s1); s2 = warp_sum(s2);
+    const double m1 = s1 / count, m2 = s2 / count;
+    if (lane == 0) {
+      coef[3 * gc] = scale[gc];
+      coef[3 * gc + 1] = (float)(-(double)scale[gc] * m2 * (double)istd[gc]);
+      coef[3 * gc + 2] = (float)((double)scale[gc] * ((double)mistd[gc] * m2 - m1));
+    }
+    dg += s2; db += s1;
+  }
+  if (lane < 27) dw[(size_t)ch * 27 + lane] += dwt;
+  if (lane == 0) {
+    if (dgamma) dgamma[ch] += (float)dg;
+    if (dbeta) dbeta[ch] += (float)db;
+    if (ch == 0 && dbias) {
+      double t = 0.0;
+      for (int g = 0; g < groups; ++g) t += box[(size_t)g * 28 + 27];
+      dbias[0] += (float)t;
+    }
+  }
+}
+
 __global__ void bn_param_grad_kernel(const double* __restrict__ sums, int groups, int c, float* dgamma,
                                      float* dbeta) {
   const int ch = threadIdx.x;
@@ -359,4 +455,26 @@ extern "C" int vg_nchw_to_nhwc(const float* src, float* dst, int n, int c, long 
 extern "C" int vg_nhwc_to_nchw(const float* src, float* dst, int n, int c, long long spatial, void* stream) {
   VG_CHECK_ARG(src && dst && n > 0 && c > 0 && spatial > 0, "bad arguments");
   return transpose(src, dst, n, (int)spatial, c, as_stream(stream));
+}
+
+extern "C" int vg_box_sums(const float* dy, int n, int group_size, const int32_t* y_dims, long long y_img_stride,
+                           const int32_t* x_dims, const int32_t* pad, double* out, void* stream) {
+  VG_CHECK_ARG(dy && out && y_dims && x_dims && pad && n > 0 && group_size > 0 && n % group_size == 0, "bad arguments");
+  const long long img = y_img_stride ? y_img_stride : (long long)y_dims[0] * y_dims[1] * y_dims[2];
+  dim3 grid(y_dims[0], n);
+  box_sums_kernel<<<grid, 256, 0, as_stream(stream)>>>(dy, group_size, y_dims[0], y_dims[1], y_dims[2], img, x_dims[0], x_dims[1],
+                                                        x_dims[2], pad[0], pad[1], pad[2], out);
+  VG_LAUNCH_CHECK();
+  return VG_OK;
+}
+
+extern "C" int vg_bn_fused_finalize(const float* raw, const double* box, const float* w, const float* scale, const float* shift,
+                                    const float* istd, const float* mistd, int groups, int c, double count, float* dw,
+                                    float* dbias, float* dgamma, float* dbeta, float* coef, void* stream) {
+  VG_CHECK_ARG(raw && box && w && scale && shift && istd && mistd && dw && coef, "null argument");
+  VG_CHECK_ARG(groups > 0 && c > 0 && c <= 32, "at most 32 channels");
+  bn_fused_finalize_kernel<<<1, 32 * c, 0, as_stream(stream)>>>(raw, box, w, scale, shift, istd, mistd, groups, c, count, dw, dbias,
+                                                                dgamma, dbeta, coef);
+  VG_LAUNCH_CHECK();
+  return VG_OK;
 }

@@ -544,7 +544,7 @@ extern "C" int vg_conv_dgrad(const VgConvDesc* d, const void* dy_, const float* 
 namespace vg {
 // wgrad_mma.cu: bf16 mma.sync weight gradient; VG_OK, a negative error, or 1 = channel pair not covered
 int wgrad_mma(const VgConvDesc* d, const void* x, const void* dy, const float* in_scale, const float* in_shift,
-              float* dw, float* dbias, cudaStream_t st);
+              float* dw, float* dbias, cudaStream_t st, float* dw_group = nullptr);
 }
 int vg_conv_wgrad_tiled(const VgConvDesc* d, const float* x, const float* dy, const float* in_scale,
                         const float* in_shift, float* dw, float* dbias, cudaStream_t st);   // wgrad.cu
@@ -560,4 +560,35 @@ extern "C" int vg_conv_wgrad(const VgConvDesc* d, const void* x, const void* dy,
   if (d->bf16_mask & (VG_BF16_X | VG_BF16_Y)) return no_bf16_path();
   return vg_conv_wgrad_tiled(d, static_cast<const float*>(x), static_cast<const float*>(dy), in_scale, in_shift, dw, dbias,
                              as_stream(stream));
+}
+
+// ---- fused BatchNorm-backward junction (BatchNorm -> stride-1 ConvTranspose3d), see include/vaegam.h
+extern "C" int vg_conv_wgrad_grouped(const VgConvDesc* d, const void* x, const void* dy, float* raw, void* stream) {
+  VG_TRY(check_desc(d));
+  VG_CHECK_ARG(x && dy && raw, "null tensor");
+  VG_CHECK_ARG(desc_tc(d), "grouped weight gradients exist in the tensor-core arithmetic only");
+  const int rc = wgrad_mma(d, x, dy, nullptr, nullptr, raw /* unused */, nullptr, as_stream(stream), raw);
+  if (rc > 0) { set_error("vg_conv_wgrad_grouped: channel pair (%d,%d) is not covered", d->cin, d->cout); return VG_EINVAL; }
+  return rc;
+}
+
+extern "C" int vg_conv_dgrad_bn_apply(const VgConvDesc* d, const void* dy_, const float* w, void* dx_, const void* bn_x_,
+                                      const float* coef, float* dx_chan_sum, void* stream) {
+  VG_TRY(check_desc(d));
+  VG_CHECK_ARG(dy_ && w && dx_ && bn_x_ && coef, "null tensor");
+  Geom gs[8];
+  const int ng = build_geoms(d, 1, gs);
+  GatherArgs a{};
+  a.in = static_cast<const float*>(dy_); a.w = w; a.out = static_cast<float*>(dx_); a.act = VG_ACT_NONE;
+  a.in_bf16 = (d->bf16_mask & VG_BF16_Y) != 0; a.out_bf16 = (d->bf16_mask & VG_BF16_DX) != 0;
+  a.aux_bf16 = (d->bf16_mask & VG_BF16_X) != 0;
+  a.aux = static_cast<const float*>(bn_x_); a.aux_mode = 3; a.aux_coef = coef; a.chan_sum = dx_chan_sum;
+  // only the plane-folded tensor-core kernel implements this epilogue
+  const int cin = d->cout, cout = d->cin;
+  if (a.in_bf16 || a.out_bf16 || a.aux_bf16) VG_TRY(check_bf16(cin, cout, a));
+  if (!desc_tc(d) || !tc2_supported(cin, cout, gs, ng)) {
+    set_error("vg_conv_dgrad_bn_apply: the fused BatchNorm-backward epilogue needs the plane-folded tensor-core kernel");
+    return VG_EINVAL;
+  }
+  return launch_tc2_gather(cin, cout, gs, ng, a, as_stream(stream));
 }

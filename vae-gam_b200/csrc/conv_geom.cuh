@@ -38,7 +38,9 @@ struct GatherArgs {
   int act;
   double* stats;          // (groups, COUT, 2): sum y, sum y^2   (forward)
   const float* aux;       // saved tensor at the output positions (backward)
-  int aux_mode;           // 0 none, 1 relu mask, 2 batch-norm backward sums
+  int aux_mode;           // 0 none, 1 relu mask, 2 batch-norm backward sums, 3 fused batch-norm backward apply + relu mask
+  const float* aux_coef;  // mode 3: (groups, COUT, 3) = A, B, C of  out = (aux > 0) * (A y + B aux + C)
+  float* chan_sum;        // mode 3: (COUT) accumulated sum of the output per channel (bias gradient of the producer layer) or null
   const float* aux_istd;  // (groups, COUT)
   const float* aux_mistd;
   double* aux_sums;       // (groups, COUT, 2): sum dy, sum dy*xhat

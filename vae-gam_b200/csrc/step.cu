@@ -82,6 +82,7 @@ struct StepWs {
   double* kl_terms; void* gain_ws; size_t gain_ws_bytes; void* recon_ws; size_t recon_ws_bytes;
   // backward
   uint16_t* d_t4h;
+  double* j5_box; float *j5_raw, *j5_coef;
   float *dpre5, *d_t4, *d_t3, *d_t2, *d_t1, *d_t0, *d_f8, *d_f7, *d_f6, *d_f5, *d_zcat, *dheads, *d_h3, *d_h2,
       *d_h1, *d_a5f, *d_a5, *d_a4, *d_a3, *d_a2, *d_a1, *dg, *deps32, *dklz;
   double* zero_begin; size_t zero_bytes;   // contiguous region holding all BN stats / sums
@@ -117,8 +118,11 @@ static size_t carve_step(char* base, int B, int m, bool backward, StepWs& w) {
   w.zero_begin = b.take<double>(0);
   take_bn(b, w.e.bn1, 1, 1); take_bn(b, w.e.bn3, 1, 8); take_bn(b, w.e.bn5, 1, 16);
   take_bn(b, w.d.bnt1, NDEC, 16); take_bn(b, w.d.bnt3, NDEC, 16); take_bn(b, w.d.bnt5, NDEC, 8);
+  w.j5_box = b.take<double>((size_t)NDEC * 28);           // fused bnt5 junction: accumulated, so cleared with the statistics
+  w.j5_raw = b.take<float>((size_t)NDEC * 27 * 8);
   b.off = (b.off + 255) & ~size_t(255);
   w.zero_bytes = b.off - (size_t)((char*)w.zero_begin - base);
+  w.j5_coef = b.take<float>((size_t)NDEC * 8 * 3);
   take_bn_coef(b, w.e.bn1, 1, 1); take_bn_coef(b, w.e.bn3, 1, 8); take_bn_coef(b, w.e.bn5, 1, 16);
   take_bn_coef(b, w.d.bnt1, NDEC, 16); take_bn_coef(b, w.d.bnt3, NDEC, 16); take_bn_coef(b, w.d.bnt5, NDEC, 8);
   EncWs& e = w.e;
@@ -556,20 +560,39 @@ static int step_bwd_impl(const VgStepConfig* cfg, const VgStepIO* io, void* work
   const bool big16 = ar == VG_ARITH_BF16;
   // convt5: x = t4 (bf16); convt4: x = t3, y = t4 and both their gradients (bf16); convt3: y = t3 and its gradient
   if (big16) { c3.bf16_mask = VG_BF16_Y; c4.bf16_mask = VG_BF16_X | VG_BF16_Y | VG_BF16_DX; c5.bf16_mask = VG_BF16_X; }
+  // tensor-core arithmetic: t4 (the largest activation) is stored as bf16 and so is its final gradient
+  void* d_t4_final = big16 ? (void*)w.d_t4h : (void*)w.d_t4;
+  if (big16) {
+    // Fused bnt5 junction: the BatchNorm-backward statistics come from the weight-gradient products (which do not
+    // depend on the data gradient), so the data gradient's epilogue applies BatchNorm backward + ReLU mask directly
+    // and writes the final gradient once, as bf16 — no raw fp32 gradient, no separate pass over the largest tensor.
+    const int32_t ydims[3] = {kConvT[4].out[0], kConvT[4].out[1], kConvT[4].out[2]};
+    const int32_t xdims[3] = {kConvT[4].in[0], kConvT[4].in[1], kConvT[4].in[2]};
+    const int32_t pads[3] = {0, 0, 0};
+    { VG_PROF("convt5.wgrad", st);
+    VG_TRY(vg_box_sums(w.dpre5, nd, B, ydims, VP, xdims, pads, w.j5_box, st));
+    VG_TRY(vg_conv_wgrad_grouped(&c5, d.t4, w.dpre5, w.j5_raw, st));
+    VG_TRY(vg_bn_fused_finalize(w.j5_raw, w.j5_box, PF(CONVT5), d.bnt5.scale, d.bnt5.shift, d.bnt5.istd, d.bnt5.mistd, NDEC, 8,
+                                (double)B * vol(kConvT[3].out), GF(CONVT5), GF(CONVT5 + 1), GF(BNT5), GF(BNT5 + 1), w.j5_coef, st));
+    }
+    { VG_PROF("convt5.dgrad", st);
+    VgConvDesc c5a = c5;
+    c5a.bf16_mask = VG_BF16_X | VG_BF16_DX;
+    VG_TRY(vg_conv_dgrad_bn_apply(&c5a, w.dpre5, PF(CONVT5), w.d_t4h, d.t4, w.j5_coef, GF(CONVT4 + 1), st));
+    }
+  } else {
   { cudaStream_t ws = fk.branch();
   VG_PROF("convt5.wgrad", ws);
   VG_TRY(vg_conv_wgrad(&c5, d.t4, w.dpre5, d.bnt5.scale, d.bnt5.shift, GF(CONVT5), GF(CONVT5 + 1), ws));
   }
-  // tensor-core arithmetic: t4 (the largest activation) is stored as bf16 and so is its final gradient; the raw
-  // data gradient that enters the BatchNorm backward stays fp32 (its rounding would be amplified by the projection)
-  void* d_t4_final = big16 ? (void*)w.d_t4h : (void*)w.d_t4;
   { VG_PROF("convt5.dgrad", st);
   VG_TRY(vg_conv_dgrad(&c5, w.dpre5, PF(CONVT5), w.d_t4, nullptr, d.t4, d.bnt5.istd, d.bnt5.mistd, d.bnt5.sums, st));
   }
   { VG_PROF("bnt5.bn_bwd", st);
   VG_TRY(vg_bn_bwd_apply(w.d_t4, d.t4, d.bnt5.sums, d.bnt5.scale, d.bnt5.istd, d.bnt5.mistd, nd, B,
-                         vol(kConvT[3].out), 8, (double)B * vol(kConvT[3].out), 1, big16 ? (VG_BF16_X | VG_BF16_DX) : 0,
-                         d_t4_final, GF(BNT5), GF(BNT5 + 1), big16 ? GF(CONVT4 + 1) : nullptr, st));
+                         vol(kConvT[3].out), 8, (double)B * vol(kConvT[3].out), 1, 0,
+                         w.d_t4, GF(BNT5), GF(BNT5 + 1), nullptr, st));
+  }
   }
   { cudaStream_t ws = fk.branch();
   VG_PROF("convt4.wgrad", ws);

@@ -275,7 +275,7 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
 
   if (warp < EPI_WARPS) {
     // ================================================================ epilogue warps
-    const bool want_stats = a.stats != nullptr, want_bn = a.aux_mode == 2;
+    const bool want_stats = a.stats != nullptr, want_bn = a.aux_mode == 2, bn_apply = a.aux_mode == 3;
     const int eset = warp >> 2, etid = tid & 127;            // TMEM lane = etid
     const int ipr = pl.ACCW >> 4, nitems = pl.nrb * ipr;     // 16-column items per row block / per accumulator
     const int ipr_shift = 31 - __clz(ipr);                   // ACCW is 16, 32, 64 or 128: ipr is a power of two
@@ -324,6 +324,11 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
         s1[c] = s2[c] = 0.f;
         istd[c] = want_bn ? __ldg(a.aux_istd + grp * COUT + c) : 0.f;
         mistd[c] = want_bn ? __ldg(a.aux_mistd + grp * COUT + c) : 0.f;
+        if (bn_apply) {      // fused BatchNorm backward: the three per-channel coefficients reuse these registers
+          istd[c] = __ldg(a.aux_coef + (grp * COUT + c) * 3);
+          mistd[c] = __ldg(a.aux_coef + (grp * COUT + c) * 3 + 1);
+          s2[c] = __ldg(a.aux_coef + (grp * COUT + c) * 3 + 2);
+        }
       }
       for (int b = 0; b < nblocks; ++b)
         for (int ph = 0; ph < pl.nph; ++ph) {
@@ -432,12 +437,18 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
                 if (a.aux_mode == 1) {
 #pragma unroll
                   for (int c = 0; c < COUT; ++c) y[c] = av[c] > 0.f ? y[c] : 0.f;
-                } else {
+                } else if (a.aux_mode == 2) {
 #pragma unroll
                   for (int c = 0; c < COUT; ++c) {
                     const float xh = fmaf(av[c], istd[c], -mistd[c]);
                     s1[c] += y[c];
                     s2[c] = fmaf(y[c], xh, s2[c]);
+                  }
+                } else {                          // out = (x > 0) * (A dy + B x + C); its sum = the producer's bias gradient
+#pragma unroll
+                  for (int c = 0; c < COUT; ++c) {
+                    y[c] = av[c] > 0.f ? fmaf(istd[c], y[c], fmaf(mistd[c], av[c], s2[c])) : 0.f;
+                    s1[c] += y[c];
                   }
                 }
               }
@@ -494,6 +505,13 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
           tc_fence_before();
           mbar_arrive(smem_u32(&acce_bar[buf]));
         }
+      if (bn_apply && a.chan_sum) {
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) {
+          const float r1 = warp_sum(s1[c]);
+          if (lane == 0) atomicAdd(a.chan_sum + c, r1);
+        }
+      }
       if (want_stats || want_bn) {
         double* dst = (want_stats ? a.stats : a.aux_sums) + (size_t)grp * COUT * 2;
 #pragma unroll

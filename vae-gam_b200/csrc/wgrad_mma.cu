@@ -173,7 +173,8 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 template <int CS, int CU, int MT, int MODE>
 __global__ void __launch_bounds__(256, 2)
 wgrad_mma_kernel(const __grid_constant__ WmGeom g, const float* __restrict__ x, const float* __restrict__ dy,
-                 const float* __restrict__ in_scale, const float* __restrict__ in_shift, float* dw, float* dbias) {
+                 const float* __restrict__ in_scale, const float* __restrict__ in_shift, float* dw, float* dbias,
+                 float* dw_group) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ int s_tapoff[48];
   __shared__ float s_bias[16];
@@ -220,7 +221,48 @@ wgrad_mma_kernel(const __grid_constant__ WmGeom g, const float* __restrict__ x, 
 
   const int tiles_per_img = g.nTd * g.nTh * g.nTw;
   const long long ntiles = (long long)tiles_per_img * g.N;
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  const int nred = g.ntaps * CS * CU;
+  // reduce the warps' accumulators through shared memory (which holds no tile at that point), then one global
+  // atomic per weight into `dst` laid out by (st_t, st_cs, st_cu)
+  auto flush = [&](float* dst, int st_t, int st_cs, int st_cu) {
+    float* red = reinterpret_cast<float*>(smem_raw);            // [tap][shifted ch][un-shifted ch]
+    for (int e = threadIdx.x; e < nred; e += blockDim.x) red[e] = 0.f;
+    __syncthreads();
+    {
+      const int gq = lane >> 2, q4 = lane & 3;
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int row = mt * 16 + gq + (k >> 1) * 8;                // (tap, shifted channel) within the group
+            const int colu = nt * 8 + 2 * q4 + (k & 1);                 // un-shifted channel
+            int t, cs;
+            if constexpr (CS == 1) { t = tap_lo + row; cs = 0; }
+            else { t = tap_lo + row / CS; cs = row % CS; }
+            if (t < tap_hi) atomicAdd(&red[((size_t)t * CS + cs) * CU + colu], acc[mt][nt][k]);
+            acc[mt][nt][k] = 0.f;
+          }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < nred; e += blockDim.x) {
+      const int colu = e % CU, rest = e / CU;
+      const int cs = rest % CS, t = rest / CS;
+      atomicAdd(dst + (size_t)t * st_t + (size_t)cs * st_cs + (size_t)colu * st_cu, red[e]);
+    }
+    __syncthreads();
+  };
+  // Grouped mode (dw_group != NULL): the products are accumulated PER BatchNorm statistics group, un-folded, into
+  // dw_group[group][tap][cs][cu]; a CTA then walks a contiguous span of tiles (images in order), so it meets at
+  // most a couple of groups and flushes when the group changes.
+  const bool grouped = dw_group != nullptr;
+  const long long span = (ntiles + gridDim.x - 1) / gridDim.x;
+  const long long t_begin = grouped ? (long long)blockIdx.x * span : (long long)blockIdx.x;
+  const long long t_end = grouped ? (t_begin + span < ntiles ? t_begin + span : ntiles) : ntiles;
+  const long long t_step = grouped ? 1 : (long long)gridDim.x;
+  int cur_grp = -1;
+  for (long long tile = t_begin; tile < t_end; tile += t_step) {
     const int n = (int)(tile / tiles_per_img);
     int tr = (int)(tile - (long long)n * tiles_per_img);
     const int tw = tr % g.nTw; tr /= g.nTw;
@@ -236,6 +278,11 @@ wgrad_mma_kernel(const __grid_constant__ WmGeom g, const float* __restrict__ x, 
     const float* sc = in_scale ? in_scale + (n / g.group_size) * (MODE == 0 ? CS : CU) : nullptr;
     const float* sh = in_scale ? in_shift + (n / g.group_size) * (MODE == 0 ? CS : CU) : nullptr;
     __syncthreads();   // previous tile fully consumed
+    if (grouped) {
+      const int grp = n / g.group_size;
+      if (cur_grp >= 0 && grp != cur_grp) flush(dw_group + (size_t)cur_grp * nred, CS * CU, CU, 1);
+      cur_grp = grp;
+    }
     // un-shifted tile: clipped to the base grid (voxels of the tile beyond it contribute zeros)
     const int none[6] = {0, 0, 0, 0, 0, 0};
     // operands that are already bf16 with nothing to fold / sum go straight to shared memory (cp.async)
@@ -358,32 +405,11 @@ wgrad_mma_kernel(const __grid_constant__ WmGeom g, const float* __restrict__ x, 
   // ---- flush: reduce the warps through shared memory, then one global atomic per weight
   __syncthreads();
   if (dbias && threadIdx.x < (MODE == 0 ? CU : CS)) atomicAdd(dbias + threadIdx.x, s_bias[threadIdx.x]);
-  float* red = reinterpret_cast<float*>(smem_raw);            // [tap][shifted ch][un-shifted ch]
-  const int nred = g.ntaps * CS * CU;
-  for (int e = threadIdx.x; e < nred; e += blockDim.x) red[e] = 0.f;
-  __syncthreads();
-  {
-    const int gq = lane >> 2, q4 = lane & 3;
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int row = mt * 16 + gq + (k >> 1) * 8;                // (tap, shifted channel) within the group
-          const int colu = nt * 8 + 2 * q4 + (k & 1);                 // un-shifted channel
-          int t, cs;
-          if constexpr (CS == 1) { t = tap_lo + row; cs = 0; }
-          else { t = tap_lo + row / CS; cs = row % CS; }
-          if (t < tap_hi) atomicAdd(&red[((size_t)t * CS + cs) * CU + colu], acc[mt][nt][k]);
-        }
-  }
-  __syncthreads();
-  for (int e = threadIdx.x; e < nred; e += blockDim.x) {
-    const int colu = e % CU, rest = e / CU;
-    const int cs = rest % CS, t = rest / CS;
-    const int ci = MODE == 0 ? cs : colu, co = MODE == 0 ? colu : cs;
-    atomicAdd(dw + (size_t)t * g.wst_t + (size_t)ci * g.wst_ci + (size_t)co * g.wst_co, red[e]);
+  if (grouped) {
+    if (cur_grp >= 0) flush(dw_group + (size_t)cur_grp * nred, CS * CU, CU, 1);
+  } else {
+    // (shifted, un-shifted) channel -> (ci, co) of the PyTorch weight layout
+    flush(dw, g.wst_t, MODE == 0 ? g.wst_ci : g.wst_co, MODE == 0 ? g.wst_co : g.wst_ci);
   }
 }
 
@@ -420,7 +446,7 @@ static void wm_pick_tile(int cs, int cu, WmGeom& g) {
 
 template <int CS, int CU, int MT>
 static int launch_wm(const WmGeom& g, const float* x, const float* dy, const float* sc, const float* sh, float* dw,
-                     float* dbias, cudaStream_t st) {
+                     float* dbias, cudaStream_t st, float* dw_group = nullptr) {
   const long long tile = (long long)g.tD * g.tH * g.tW, box = (long long)g.sD * g.sH * g.sW;
   size_t smem = ((size_t)box * CS * 2 + 64 + 15) / 16 * 16 + (size_t)((tile + 15) / 16 * 16) * (CU * 2 + 2) + 64;
   const size_t red = (size_t)g.ntaps * CS * CU * sizeof(float);
@@ -430,10 +456,10 @@ static int launch_wm(const WmGeom& g, const float* x, const float* dy, const flo
   if (blocks > ntiles) blocks = ntiles;
   if (g.mode == 0) {
     VG_CUDA(cudaFuncSetAttribute(wgrad_mma_kernel<CS, CU, MT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    wgrad_mma_kernel<CS, CU, MT, 0><<<(unsigned)blocks, 256, smem, st>>>(g, x, dy, sc, sh, dw, dbias);
+    wgrad_mma_kernel<CS, CU, MT, 0><<<(unsigned)blocks, 256, smem, st>>>(g, x, dy, sc, sh, dw, dbias, dw_group);
   } else {
     VG_CUDA(cudaFuncSetAttribute(wgrad_mma_kernel<CS, CU, MT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    wgrad_mma_kernel<CS, CU, MT, 1><<<(unsigned)blocks, 256, smem, st>>>(g, x, dy, sc, sh, dw, dbias);
+    wgrad_mma_kernel<CS, CU, MT, 1><<<(unsigned)blocks, 256, smem, st>>>(g, x, dy, sc, sh, dw, dbias, dw_group);
   }
   VG_LAUNCH_CHECK();
   return VG_OK;
@@ -441,7 +467,7 @@ static int launch_wm(const WmGeom& g, const float* x, const float* dy, const flo
 
 // returns VG_OK, or 1 when the channel pair is not covered (caller falls back to the fp32 kernel)
 int wgrad_mma(const VgConvDesc* d, const void* x_, const void* dy_, const float* in_scale, const float* in_shift,
-              float* dw, float* dbias, cudaStream_t st) {
+              float* dw, float* dbias, cudaStream_t st, float* dw_group) {
   const float* x = static_cast<const float*>(x_);
   const float* dy = static_cast<const float*>(dy_);
   WmGeom g{};
@@ -476,12 +502,12 @@ int wgrad_mma(const VgConvDesc* d, const void* x_, const void* dy_, const float*
     g.taps_per_group = ((tiles + tg - 1) / tg) * tpm;
   };
   wm_pick_tile(cs, cu, g);
-  if (cs == 1 && cu == 8) { groups(16, 3); return launch_wm<1, 8, 3>(g, x, dy, in_scale, in_shift, dw, dbias, st); }
+  if (cs == 1 && cu == 8) { groups(16, 3); return launch_wm<1, 8, 3>(g, x, dy, in_scale, in_shift, dw, dbias, st, dw_group); }
   // MT keeps the accumulators at <= 56 registers so that two CTAs share an SM without spills
-  if (cs == 8 && cu == 8) { groups(2, 12); return launch_wm<8, 8, 12>(g, x, dy, in_scale, in_shift, dw, dbias, st); }
-  if (cs == 8 && cu == 16) { groups(2, 7); return launch_wm<8, 16, 7>(g, x, dy, in_scale, in_shift, dw, dbias, st); }
-  if (cs == 16 && cu == 16) { groups(1, 7); return launch_wm<16, 16, 7>(g, x, dy, in_scale, in_shift, dw, dbias, st); }
-  if (cs == 16 && cu == 8) { groups(1, 14); return launch_wm<16, 8, 14>(g, x, dy, in_scale, in_shift, dw, dbias, st); }
+  if (cs == 8 && cu == 8) { groups(2, 12); return launch_wm<8, 8, 12>(g, x, dy, in_scale, in_shift, dw, dbias, st, dw_group); }
+  if (cs == 8 && cu == 16) { groups(2, 7); return launch_wm<8, 16, 7>(g, x, dy, in_scale, in_shift, dw, dbias, st, dw_group); }
+  if (cs == 16 && cu == 16) { groups(1, 7); return launch_wm<16, 16, 7>(g, x, dy, in_scale, in_shift, dw, dbias, st, dw_group); }
+  if (cs == 16 && cu == 8) { groups(1, 14); return launch_wm<16, 8, 14>(g, x, dy, in_scale, in_shift, dw, dbias, st, dw_group); }
   return 1;
 }
 

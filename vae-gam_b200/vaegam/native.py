@@ -105,6 +105,10 @@ SIGNATURES = {
     "vg_conv_fwd": (_I, [C.POINTER(VgConvDesc), _P, _P, _P, _P, _P, _P, _I, _P, _P]),
     "vg_conv_dgrad": (_I, [C.POINTER(VgConvDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "vg_conv_wgrad": (_I, [C.POINTER(VgConvDesc), _P, _P, _P, _P, _P, _P, _P]),
+    "vg_box_sums": (_I, [_P, _I, _I, C.POINTER(C.c_int32), _LL, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _P, _P]),
+    "vg_conv_wgrad_grouped": (_I, [C.POINTER(VgConvDesc), _P, _P, _P, _P]),
+    "vg_bn_fused_finalize": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _D, _P, _P, _P, _P, _P, _P]),
+    "vg_conv_dgrad_bn_apply": (_I, [C.POINTER(VgConvDesc), _P, _P, _P, _P, _P, _P, _P]),
     "vg_bn_stats": (_I, [_P, _I, _I, _LL, _I, _P, _P]),
     "vg_bn_finalize": (_I, [_P, _P, _P, _I, _I, _D, _P, _P, _P, _P, _P]),
     "vg_bn_bwd_apply": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _LL, _I, _D, _I, _I, _P, _P, _P, _P, _P]),
