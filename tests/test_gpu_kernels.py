@@ -370,7 +370,7 @@ def test_fused_bn_backward_junction(lib, in_):
     assert rel_err(dgamma.cpu(), gr.grad.cpu()) < 1e-2 and rel_err(dbeta.cpu(), br.grad.cpu()) < 1e-2
     got = from_cl(du.float())
     assert rel_err(got.cpu(), du_ref.cpu()) < 1.5e-2, rel_err(got.cpu(), du_ref.cpu())
-    assert rel_err(csum.cpu(), got.sum((0, 2, 3, 4)).cpu()) < 1e-3
+    assert rel_err(csum.cpu(), got.sum((0, 2, 3, 4)).cpu()) < 1e-2        # the stored values are rounded to bf16, the sum is not
 
 
 @pytest.mark.parametrize("name", list(LAYERS))

@@ -304,7 +304,10 @@ __global__ void bn_fused_finalize_kernel(const float* __restrict__ raw, const do
     double s1 = 0.0, s2 = 0.0;
     if (lane < 27) {
       const double r = (double)raw[((size_t)g * 27 + lane) * c + ch], d0 = box[(size_t)g * 28 + lane];
-      const double wv = (double)w[(size_t)ch * 27 + lane];          // ConvTranspose3d weight (cin, 1, 3, 3, 3)
+      // ConvTranspose3d weight (cin, 1, 3, 3, 3), ROUNDED to bf16 like the operand of the data-gradient MMAs: the
+      // sums must describe the data gradient that is actually computed (a systematic 2^-9 mismatch in m1 would
+      // show up, un-averaged, in every voxel — and in the producer's bias gradient)
+      const double wv = (double)__bfloat162float(__float2bfloat16(w[(size_t)ch * 27 + lane]));
       s1 = wv * d0;
       s2 = wv * ((double)istd[gc] * r - (double)mistd[gc] * d0);
       dwt += (float)((double)scale[gc] * r + (double)shift[gc] * d0);
