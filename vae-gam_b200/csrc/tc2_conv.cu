@@ -73,6 +73,10 @@ struct T2Plan {
   // the row frame (rows = HB * PW), a ring slot is two TMA boxes [8 ch][PW][HB + halo lines] — exactly the staged
   // operand layout, out-of-range voxels zero-filled by the TMA unit.  hb == 0: staging by the producer warps.
   int hb, box_h;
+  // saved-activation staging of the epilogue (bf16 aux with 8 channels whose rows are the plane's voxels in order:
+  // 1-channel gathers, pitch == output width): the 128-row x 16-byte chunks an accumulator unit needs are fetched
+  // one unit ahead with bulk asynchronous copies into a double buffer behind the weights.  0: loaded by the threads.
+  int auxs;
   int groups;                  // BatchNorm groups of the launch when the fold moves into the weights (TMA mode): a CTA serves ONE group
   T2Phase ph[T2_MAX_PH];
   T2Mma mma[T2_MAX_MMA];
@@ -94,6 +98,11 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm,
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// contiguous global -> shared bulk copy (UBLKCP); 16-byte aligned, size a multiple of 16; completion on the mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 constexpr int T2_MAX_CLS = 5;      // tap-validity classes per output dimension (k <= 5 would give more; TMA mode has k = 3)
 __host__ __device__ constexpr int t2_max_chunk(int cin, int es, int sd) {
   return sd == 2 ? 1 : (cin == 8 ? (es == 1 ? 2 : 4) : (cin == 16 ? (es == 1 ? 2 : 3) : (es == 1 ? 3 : 5)));
@@ -114,7 +123,7 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
   constexpr int NJ = 16 / COUT;                        // output planes per epilogue item (16 TMEM columns)
 
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t full_bar[T2_MAX_RING], empty_bar[T2_MAX_RING], accf_bar[2], acce_bar[2];
+  __shared__ __align__(8) uint64_t full_bar[T2_MAX_RING], empty_bar[T2_MAX_RING], accf_bar[2], acce_bar[2], auxf_bar[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ int lut[T2_MAX_PH][45];
   __shared__ float s_bias[16];
@@ -141,6 +150,7 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&accf_bar[b]), (uint32_t)min(pl.nrb, NMW));
       mbar_init(smem_u32(&acce_bar[b]), EPI_WARPS * 32);
+      mbar_init(smem_u32(&auxf_bar[b]), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
@@ -306,6 +316,40 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
     const int mid_bofs = (cls_mid[1] * (TMA ? s_ncls[2] : 0) + cls_mid[2]) * COUT;
     const int mid_d0 = TMA ? s_midrange[0] : 0, mid_d1 = TMA ? s_midrange[1] : 0;
     const uint32_t pw_mul = (uint32_t)((0x100000000ULL + (uint64_t)pl.PW - 1) / (uint64_t)pl.PW);   // exact r / PW for r * PW < 2^32
+    // ---- saved-activation staging (pl.auxs): thread 0 fetches the aux chunks of the NEXT accumulator unit with bulk
+    // asynchronous copies while the current unit is processed; chunk (row block, plane) = 128 rows x 16 bytes, contiguous
+    // in global memory because the rows are the plane's voxels in order.
+    constexpr bool AUXS_OK = CIN == 1 && COUT == 8 && !TMA;
+    const bool auxs = AUXS_OK && pl.auxs != 0;
+    const uint32_t aux_s0 = smem_u32(wts) + (uint32_t)pl.wbytes;
+    const uint8_t* const aux_sp = wts + pl.wbytes;
+    auto aux_issue = [&](int n_, int t_, int qdf, int qde, int bufi) {
+      const int plane_vox = g.outH * g.outW;
+      const __nv_bfloat16* src_n = reinterpret_cast<const __nv_bfloat16*>(a.aux) + (size_t)n_ * g.out_img;
+      uint32_t bytes = 0;
+      for (int rbb = 0; rbb < pl.nrb; ++rbb) {
+        const int r0 = t_ * pl.TR + rbb * 128;
+        const int rows = min(128, pl.RTOT - r0);
+        if (rows <= 0) continue;
+        for (int j = 0; j < pl.OB; ++j) if (qdf + j < qde) bytes += (uint32_t)rows * 16u;
+      }
+      const uint32_t bar = smem_u32(&auxf_bar[bufi]);
+      mbar_arrive_expect_tx(bar, bytes);
+      for (int rbb = 0; rbb < pl.nrb; ++rbb) {
+        const int r0 = t_ * pl.TR + rbb * 128;
+        const int rows = min(128, pl.RTOT - r0);
+        if (rows <= 0) continue;
+        for (int j = 0; j < pl.OB; ++j)
+          if (qdf + j < qde)
+            bulk_g2s(aux_s0 + (uint32_t)(((bufi * pl.nrb + rbb) * pl.OB + j) * 2048), src_n + ((size_t)(qdf + j) * plane_vox + r0) * 8,
+                     (uint32_t)rows * 16u, bar);
+      }
+    };
+    if (auxs && tid == 0 && col_first < col_count) {       // first unit of this CTA
+      const int dc = col_first / per_dc, t_ = (col_first - dc * per_dc) % pl.ntiles, n_ = col_img0 + (col_first - dc * per_dc) / pl.ntiles;
+      const int qd0_ = dc * pl.dchunk, qd1_ = min(pl.qDmax, qd0_ + pl.dchunk);
+      aux_issue(n_, t_, qd0_, min((int)pl.ph[0].qD, qd1_), 0);
+    }
     for (int col = col_first; col < col_count; col += col_step) {
       // d-chunk major: the chunks of an image differ in length (the last one is short), so all the long columns come
       // first and a CTA's round-robin share mixes long and short ones whatever the parity of the grid
@@ -336,6 +380,22 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
           const int au = acc_base + b * pl.nph + ph, buf = au & 1;
           const int qd_end = min((int)P.qD, qd1);
           const uint32_t ph_off = (uint32_t)P.rD * plane_out + ((uint32_t)P.rH * (uint32_t)g.outW + (uint32_t)P.rW) * COUT;
+          if (auxs && tid == 0) {                 // prefetch the aux chunks of the next unit (same column or the next one)
+            int n_ = n, t_ = t, qdf = qd0 + (b + 1) * pl.OB, qde = qd_end;
+            bool have = b + 1 < nblocks;
+            if (!have && col + col_step < col_count) {
+              const int c2 = col + col_step, dc2 = c2 / per_dc;
+              t_ = (c2 - dc2 * per_dc) % pl.ntiles; n_ = col_img0 + (c2 - dc2 * per_dc) / pl.ntiles;
+              qdf = dc2 * pl.dchunk;
+              qde = min((int)P.qD, min(pl.qDmax, qdf + pl.dchunk));
+              have = true;
+            }
+            if (have) {
+              const int au1 = au + 1;
+              mbar_wait(smem_u32(&acce_bar[au1 & 1]), (uint32_t)(((au1 >> 1) & 1) ^ 1));      // unit au - 1 drained that buffer
+              aux_issue(n_, t_, qdf, qde, au1 & 1);
+            }
+          }
           // row cache: valid for the row block `c_rb` of this (column, phase)
           int c_rb = -1, c_bofs = mid_bofs;
           bool c_ok = false;
@@ -362,7 +422,7 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
             I.off = (uint32_t)I.qd * plane_step + c_rowoff;
           };
           auto load_aux = [&](const Item& I, float (&ax)[NJ][COUT]) {
-            if (a.aux_mode == 0 || !I.row_ok) return;
+            if (a.aux_mode == 0 || !I.row_ok || auxs) return;
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
               if (I.qd + j >= qd_end) continue;
@@ -434,6 +494,13 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
                     }
                   }
                 }
+                if constexpr (AUXS_OK) {
+                  if (auxs) {                     // staged chunk (buffer, row block, plane of the block): this thread's row
+                    const uint4 q = *reinterpret_cast<const uint4*>(aux_sp + (size_t)(((buf * pl.nrb + I.rb) * pl.OB + I.k * NJ + j) * 2048) +
+                                                                     (size_t)etid * 16);
+                    unpack_bf16x8(q, av);
+                  }
+                }
                 if (a.aux_mode == 1) {
 #pragma unroll
                   for (int c = 0; c < COUT; ++c) y[c] = av[c] > 0.f ? y[c] : 0.f;
@@ -492,6 +559,7 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
           if (it < nitems) { setup(it, I0); load_aux(I0, ax0); }
           mbar_wait(smem_u32(&accf_bar[buf]), (uint32_t)((au >> 1) & 1));
           tc_fence_after();
+          if (auxs) mbar_wait(smem_u32(&auxf_bar[buf]), (uint32_t)((au >> 1) & 1));       // this unit's aux chunks have landed
           while (it < nitems) {
             if (it + ES < nitems) { setup(it + ES, I1); load_aux(I1, ax1); }
             process(I0, ax0);
@@ -874,8 +942,8 @@ static inline int t2_ceil_div(int a, int b) { return a >= 0 ? (a + b - 1) / b : 
 // tma: TMA-direct staging requested (bf16 input; see T2Plan::hb) — falls back to producer-warp staging (returns
 // true with pl.hb == 0) when the geometry is outside what the TMA path covers.
 static bool t2_build_plan(int cin, int cout, const Geom* gs, int ng, Geom& merged, T2Plan& pl, bool tma = false,
-                          bool affine = false) {
-  pl.hb = 0; pl.box_h = 0; pl.groups = 1;
+                          bool affine = false, bool auxs = false) {
+  pl.hb = 0; pl.box_h = 0; pl.groups = 1; pl.auxs = 0;
   if (ng < 1 || ng > T2_MAX_PH) return false;
   if (cin != 1 && cin != 8 && cin != 16) return false;
   if (cout != 1 && cout != 8 && cout != 16) return false;
@@ -1065,6 +1133,10 @@ static bool t2_build_plan(int cin, int cout, const Geom* gs, int ng, Geom& merge
   if (nrb_max > 4) nrb_max = 4;
   const int need = (pl.RTOT + 127) / 128;
   if (nrb_max > need) nrb_max = need;
+  // epilogue aux staging: rows must be the output plane's voxels in order (pitch == width, one phase, unit strides)
+  const bool use_auxs = auxs && cin == 1 && cout == 8 && ng == 1 && sd == 1 && merged.sout == 1 && pl.PW == merged.outW &&
+                        merged.qH == merged.outH && merged.qW == merged.outW;
+  if (use_auxs && nrb_max > 2) nrb_max = 2;                 // two units of nrb x OB chunks of 2 KB must fit beside the ring
   int best = 0, best_r = 0;
   double best_eff = 0.0;
   for (int nrb = nrb_max; nrb >= 1; --nrb) {
@@ -1072,10 +1144,11 @@ static bool t2_build_plan(int cin, int cout, const Geom* gs, int ng, Geom& merge
     const int sr = (tr + sm_h * pl.PW + (cin == 1 ? 0 : sm_w) + 7) & ~7;
     if (sr > max_sr) continue;
     const size_t slot = (size_t)2 * pl.nsg * sr * 16;
+    const size_t aux_bytes = use_auxs ? (size_t)2 * nrb * pl.OB * 2048 : 0;
     int r = pl.NPAIR + 3;
     if (r > T2_MAX_RING) r = T2_MAX_RING;
-    while (r > pl.NPAIR + 1 && (size_t)r * slot + pl.wbytes > (size_t)kT2SmemBudget) --r;
-    if ((size_t)r * slot + pl.wbytes > (size_t)kT2SmemBudget) continue;
+    while (r > pl.NPAIR + 1 && (size_t)r * slot + pl.wbytes + aux_bytes > (size_t)kT2SmemBudget) --r;
+    if ((size_t)r * slot + pl.wbytes + aux_bytes > (size_t)kT2SmemBudget) continue;
     const int nt = (pl.RTOT + tr - 1) / tr;
     // useful rows per staged row: tile quantisation and the h-halo that every tile re-stages
     const double eff = (double)pl.RTOT / ((double)nt * sr);
@@ -1086,6 +1159,7 @@ static bool t2_build_plan(int cin, int cout, const Geom* gs, int ng, Geom& merge
   pl.TR = 128 * best;
   pl.SR = (pl.TR + sm_h * pl.PW + (cin == 1 ? 0 : sm_w) + 7) & ~7;
   pl.R = best_r;
+  pl.auxs = use_auxs ? 1 : 0;
   for (int m = 0; m < nmma; ++m) pl.mma[m].a_shift = (uint32_t)(m_sg[m] * pl.SR + m_mh[m] * pl.PW + m_mw[m]);
   pl.ntiles = (pl.RTOT + pl.TR - 1) / pl.TR;
   int tc = 32;
@@ -1168,7 +1242,7 @@ static int make_tmap(const Geom& g, const T2Plan& pl, const void* base, CUtensor
 
 template <int CIN, int COUT, int SD, bool TMA = false>
 static int launch_tc2_t(const Geom& g, const GatherArgs& a, const T2Plan& pl, cudaStream_t st) {
-  const size_t smem = (size_t)pl.R * 2 * pl.nsg * pl.SR * 16 + pl.wbytes;
+  const size_t smem = (size_t)pl.R * 2 * pl.nsg * pl.SR * 16 + pl.wbytes + (pl.auxs ? (size_t)2 * pl.nrb * pl.OB * 2048 : 0);
   VG_CUDA(cudaFuncSetAttribute(tc2_kernel<CIN, COUT, SD, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long cols = (long long)g.N * pl.ntiles * pl.ndchunks;
   const int sms = vg_sm_count();
@@ -1194,7 +1268,8 @@ int launch_tc2_gather(int cin, int cout, const Geom* gs, int ng, const GatherArg
   T2Plan pl;
   Geom merged;
   const bool want_tma = a.in_bf16 && tma_enabled();
-  if (!t2_build_plan(cin, cout, gs, ng, merged, pl, want_tma, a.in_scale != nullptr)) { set_error("plane-folded tensor-core path: unsupported geometry"); return VG_EINVAL; }
+  const bool want_auxs = a.aux_bf16 && a.aux_mode != 0 && a.aux != nullptr && tma_wanted();
+  if (!t2_build_plan(cin, cout, gs, ng, merged, pl, want_tma, a.in_scale != nullptr, want_auxs)) { set_error("plane-folded tensor-core path: unsupported geometry"); return VG_EINVAL; }
   if (pl.hb > 0) {                                // TMA-direct staging of a bf16 input
     if (cin == 8 && cout == 1) return launch_tc2_t<8, 1, 1, true>(merged, a, pl, st);
     if (cin == 8 && cout == 8) return launch_tc2_t<8, 8, 1, true>(merged, a, pl, st);
