@@ -1268,7 +1268,10 @@ int launch_tc2_gather(int cin, int cout, const Geom* gs, int ng, const GatherArg
   T2Plan pl;
   Geom merged;
   const bool want_tma = a.in_bf16 && tma_enabled();
-  const bool want_auxs = a.aux_bf16 && a.aux_mode != 0 && a.aux != nullptr && tma_wanted();
+  // Opt-in (VAEGAM_AUX_STAGING=1): measured on B200 the smaller tile it needs (two row blocks, so that two units of
+  // chunks fit beside the ring) costs more than the prefetch wins — convt5's data gradient 0.65 ms vs 0.50 ms.
+  static const bool aux_staging = [] { const char* e = getenv("VAEGAM_AUX_STAGING"); return e && e[0] == '1'; }();
+  const bool want_auxs = aux_staging && a.aux_bf16 && a.aux_mode != 0 && a.aux != nullptr;
   if (!t2_build_plan(cin, cout, gs, ng, merged, pl, want_tma, a.in_scale != nullptr, want_auxs)) { set_error("plane-folded tensor-core path: unsupported geometry"); return VG_EINVAL; }
   if (pl.hb > 0) {                                // TMA-direct staging of a bf16 input
     if (cin == 8 && cout == 1) return launch_tc2_t<8, 1, 1, true>(merged, a, pl, st);
