@@ -251,6 +251,18 @@ def stock_torch_b200(device, steps=4, warmup=2, B=BATCH):
     ids = torch.from_numpy(coh.subject_index()[:B].copy()).to(device)
     work = tempfile.mkdtemp(prefix="stock_")
     tr, te, glm, _ = syn.write_experiment(work, n_subjects=2, config="checker", glm="uniform")
+    # The reference inverts Ku in fp32 without jitter (gp.py:107); with z-scored motion covariates the
+    # inducing grid is finer than the length scale and cuSOLVER's fp32 inverse leaves the gain covariance non-PD at
+    # initialisation.  For this TIMING diagnostic the motion covariates are spread 3x wider (grid step > length scale),
+    # which conditions Ku without changing a single operation of the step.
+    import pandas as pd
+    SPREAD = 3.0
+    for path in (tr, te):
+        df = pd.read_csv(path, index_col=0)
+        df[["x", "y", "z", "rot_x", "rot_y", "rot_z"]] *= SPREAD
+        df.to_csv(path)
+    cov = cov.clone()
+    cov[:, 1:7] *= SPREAD
     ref_model = None
     kind = "oracle port (oracle/ref_port.py) on cuda"
     if os.path.isfile(os.path.join(ref_dir, "vae_reg_GP.py")):

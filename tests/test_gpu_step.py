@@ -90,7 +90,9 @@ def test_step_matches_oracle_and_golden(case):
 # on the encoder's weight gradients (its activations feed z, on which all nine decoder passes depend); every
 # backward pass in bf16 costs < 1 %, the decoder's forward 2-3 %.  Hence the default "mixed" mode: encoder forward
 # in fp32, everything else bf16 on the tensor cores.
-GRAD_TOL = {("mixed", 4): 8e-2, ("mixed", 32): 4e-2, ("bf16", 4): 0.45, ("bf16", 32): 0.35}
+# Measured on B200 (worst parameter tensor): mixed 3.4e-2 (B=4) / 2.2e-2 (B=32) / 2.4e-2 (B=128, m=8);
+# bf16 everywhere 0.18 / 0.23 — which is why "mixed" is the default.
+GRAD_TOL = {("mixed", 4): 6e-2, ("mixed", 32): 3.5e-2, ("bf16", 4): 0.35, ("bf16", 32): 0.35}
 
 
 @pytest.mark.parametrize("arith", ["mixed", "bf16"])
@@ -122,7 +124,9 @@ def test_step_tensor_core_modes(case, arith):
     worst_map = {}
     for k in ref_imgs:
         diff = np.abs(imgs[k] - ref_imgs[k].detach().numpy())
-        lim = (2e-2, 0.3, 0.8) if k == "full_rec" else (6e-3, 0.1, 0.3)
+        # (mean, 99.9 % quantile, max) of the absolute deviation; measured: base 1.2e-3 / 1.1e-2 / 2.6e-2, covariate maps
+        # (scaled by gains of order 1..10) up to 3.4e-3 / 5.3e-2 / 0.14, full_rec 9.5e-3 / 0.11 / 0.31
+        lim = (2e-2, 0.2, 0.5) if k == "full_rec" else ((3e-3, 3e-2, 6e-2) if k == "base" else (6e-3, 0.1, 0.25))
         worst_map[k] = (float(diff.mean()), float(np.quantile(diff, 0.999)), float(diff.max()))
         assert diff.mean() < lim[0] and np.quantile(diff, 0.999) < lim[1] and diff.max() < lim[2], (k, worst_map[k])
     gmax = max(float(Pd[n].grad.norm()) for n, _ in model.named_parameters())
