@@ -570,6 +570,7 @@ def main():
     sync_all()
     e2e_ms = f0.elapsed_time(f1)   # device clock; every loss value has reached the host before f1's sync returns
     identical = params_identical(model, device, world)
+    graphed = any(gs.graph is not None for gs in model._graph_steps.values())     # before the sub-measurements drop the graphs
 
     # ---------------- max over ranks
     ms, e2e_ms = max_over_ranks([ms, e2e_ms], device, world)
@@ -679,7 +680,6 @@ def main():
         return
     total_vols = args.steps * B * world
     value = total_vols / (ms * 1e-3)
-    graphed = any(gs.graph is not None for gs in model._graph_steps.values())
     line = {
         "metric": "training volumes/sec (fwd+bwd+step)", "value": value, "unit": "volumes/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,

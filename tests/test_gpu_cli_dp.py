@@ -85,7 +85,7 @@ def test_reference_cli_runs_unchanged(tmp_path):
     assert one.shape == (41, 49, 35) and np.isfinite(one).all()
 
 
-def _dp_worker(rank, world, port, tmp, ret):
+def _dp_worker(rank, world, port, tmp, files, ret):
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     for p in (ROOT, PKG, os.path.join(ROOT, "tests")):
         if p not in sys.path:
@@ -97,7 +97,7 @@ def _dp_worker(rank, world, port, tmp, ret):
     rank, world, local = dp.init_from_env()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    tr, te, glm = (os.path.join(tmp, f) for f in ("train.csv", "test.csv", "glm.csv"))
+    tr, te, glm = files
     torch.manual_seed(1 + rank)                           # different initial values: the broadcast must fix that
     model = vae_reg_GP.VAE(save_dir=os.path.join(tmp, f"r{rank}"), glm_maps=glm, csv_files=[tr, te])
     model.writer = vae_reg_GP._NullWriter()
@@ -165,7 +165,7 @@ def test_dp_two_gpus_allreduced_gradient_is_the_mean_and_replicas_stay_identical
     ret = mgr.dict()
     ctx = mp.get_context("spawn")
     port = 29600 + os.getpid() % 300
-    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, str(tmp_path), ret)) for r in range(2)]
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, str(tmp_path), (tr, te, glm), ret)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:

@@ -103,6 +103,14 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// one 5-D box (channel, w, h, d, n) — the strided variant: element strides (1, 2, 2, 1, 1) pick one (h, w)-parity sub-grid
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3,
+                                            int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
 constexpr int T2_MAX_CLS = 5;      // tap-validity classes per output dimension (k <= 5 would give more; TMA mode has k = 3)
 __host__ __device__ constexpr int t2_max_chunk(int cin, int es, int sd) {
   return sd == 2 ? 1 : (cin == 8 ? (es == 1 ? 2 : 4) : (cin == 16 ? (es == 1 ? 2 : 3) : (es == 1 ? 3 : 5)));
@@ -112,7 +120,7 @@ template <int CIN, int COUT, int SD, bool TMA>
 __global__ void __launch_bounds__(T2_THREADS, 1)
 tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_constant__ T2Plan pl,
            const __grid_constant__ CUtensorMap tmap) {
-  static_assert(!TMA || (CIN == 8 && SD == 1), "TMA-direct staging: 8 bf16 channels = one 16-byte word per voxel, unit stride");
+  static_assert(!TMA || CIN == 8, "TMA-direct staging: 8 bf16 channels = one 16-byte word per voxel");
   // TMA mode has no producer warps: 12 epilogue warps (3 sets), warp 12 issues the TMA loads, warps 13..15 the MMAs
   constexpr int ES = TMA ? 3 : t2_epi_sets(CIN, COUT, SD);
   constexpr int MMA_WARP0 = TMA ? 13 : T2_MMA_WARP, NMW = 16 - MMA_WARP0;      // MMA issuer warps
@@ -600,7 +608,7 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
     if constexpr (TMA) {
       if (warp == EPI_WARPS) {
         const uint32_t ring_a = smem_u32(ring);
-        const uint32_t slot_tx = (uint32_t)(2 * pl.box_h * pl.PW * 16);     // two boxes of [8 ch][PW][box_h] bf16
+        const uint32_t slot_tx = (uint32_t)(2 * NSG * pl.box_h * pl.PW * 16);     // 2 * NSG boxes of [8 ch][PW][box_h] bf16
         for (int col = col_first; col < col_count; col += col_step) {
           // d-chunk major: the chunks of an image differ in length (the last one is short), so all the long columns come
       // first and a CTA's round-robin share mixes long and short ones whatever the parity of the grid
@@ -615,9 +623,17 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
               const uint32_t bar = smem_u32(&full_bar[slot]);
               mbar_arrive_expect_tx(bar, slot_tx);
 #pragma unroll
-              for (int hf = 0; hf < 2; ++hf)      // plane ip may lie outside the input: the whole box is then zero-filled
-                tma_load_4d(ring_a + (uint32_t)slot * (uint32_t)PAIRB + (uint32_t)hf * (uint32_t)SRB, &tmap, bar, 4 * pl.lo_w,
-                            t * pl.hb + pl.lo_h, qd0 + pl.lo_d + 2 * P + hf, n);
+              for (int hf = 0; hf < 2; ++hf) {    // plane ip may lie outside the input: the whole box is then zero-filled
+                if constexpr (SD == 1) {
+                  tma_load_4d(ring_a + (uint32_t)slot * (uint32_t)PAIRB + (uint32_t)hf * (uint32_t)SRB, &tmap, bar, 4 * pl.lo_w,
+                              t * pl.hb + pl.lo_h, qd0 + pl.lo_d + 2 * P + hf, n);
+                } else {                          // input stride 2: one strided box per (h, w)-parity sub-grid
+#pragma unroll
+                  for (int sg = 0; sg < NSG; ++sg)
+                    tma_load_5d(ring_a + (uint32_t)slot * (uint32_t)PAIRB + (uint32_t)(hf * NSG + sg) * (uint32_t)SRB, &tmap, bar, 0,
+                                pl.lo_w + (sg & 1), SD * t * pl.hb + pl.lo_h + (sg >> 1), SD * qd0 + pl.lo_d + 2 * P + hf, n);
+                }
+              }
             }
             __syncwarp();
           }
@@ -1063,8 +1079,8 @@ static bool t2_build_plan(int cin, int cout, const Geom* gs, int ng, Geom& merge
   pl.wbytes = (woff + 1023) & ~1023;
   if (pl.wbytes > 96 * 1024) return false;
 
-  if (tma && cin == 8 && sd == 1 && (ng == 1 || !affine) && pl.span_d <= 2 && merged.outD <= 64 && merged.outH <= 64 &&
-      merged.outW <= 64 && pl.PW <= 64) {
+  if (tma && cin == 8 && (sd == 1 || (ng == 1 && !affine && cout != 1)) && (ng == 1 || !affine) && (pl.span_d <= 2 || !affine) &&
+      merged.outD <= 64 && merged.outH <= 64 && merged.outW <= 64 && pl.PW <= 64) {
     // ---- TMA-direct staging: tile = hb whole lines of the row frame, a slot = two boxes [8][PW][hb + halo]
     int nrb_max = 512 / (2 * pl.ACCW);
     if (nrb_max > 4) nrb_max = 4;
@@ -1102,11 +1118,11 @@ static bool t2_build_plan(int cin, int cout, const Geom* gs, int ng, Geom& merge
       const int reach = 128 * nrb + sm_h * pl.PW + sm_w;   // rows the last row block's shifted windows touch
       if (sr < reach) sr = reach;
       sr = (sr + 7) & ~7;
-      const size_t slot = (size_t)2 * sr * 16;
+      const size_t slot = (size_t)2 * pl.nsg * sr * 16;
       int r = pl.NPAIR + 3;
       if (r > T2_MAX_RING) r = T2_MAX_RING;
       while (r > pl.NPAIR + 1 && (size_t)r * slot + pl.wbytes > (size_t)kT2SmemBudget) --r;
-      if ((size_t)r * slot + pl.wbytes > (size_t)kT2SmemBudget || box_h > 256) continue;
+      if ((size_t)r * slot + pl.wbytes > (size_t)kT2SmemBudget || sd * box_h > 256) continue;
       pl.hb = hb; pl.box_h = box_h; pl.nrb = nrb; pl.TR = 128 * nrb; pl.SR = sr; pl.R = r;
       pl.ntiles = nt;
       pl.groups = affine ? merged.N / merged.group_size : 1;
@@ -1227,7 +1243,22 @@ static EncodeTiledFn tma_encoder() {
   return fn;
 }
 static bool tma_enabled() { return tma_wanted() && tma_encoder() != nullptr; }
+static int make_tmap_strided(const Geom& g, const T2Plan& pl, const void* base, CUtensorMap& tm) {
+  // input stride 2: 5-D (channel, w, h, d, n) with element strides 2 along w and h; a box of 2*PW x 2*box_h traversed
+  // positions delivers the PW x box_h voxels of one parity sub-grid, densely packed
+  const cuuint64_t dims[5] = {8, (cuuint64_t)g.inW, (cuuint64_t)g.inH, (cuuint64_t)g.inD, (cuuint64_t)g.N};
+  const cuuint64_t strides[4] = {16, (cuuint64_t)g.inW * 16, (cuuint64_t)g.inW * g.inH * 16, (cuuint64_t)g.in_img * 2};
+  const cuuint32_t box[5] = {8, (cuuint32_t)pl.PW * 2, (cuuint32_t)pl.box_h * 2, 1, 1};
+  const cuuint32_t estr[5] = {1, 2, 2, 1, 1};
+  if (((uintptr_t)base & 15) || (strides[3] & 15)) { set_error("TMA staging: tensor not 16-byte aligned"); return VG_EINVAL; }
+  const CUresult rc = tma_encoder()(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (strided) failed (%d)", (int)rc); return VG_ECUDA; }
+  return VG_OK;
+}
 static int make_tmap(const Geom& g, const T2Plan& pl, const void* base, CUtensorMap& tm) {
+  if (pl.sd == 2) return make_tmap_strided(g, pl, base, tm);
   const cuuint64_t dims[4] = {(cuuint64_t)g.inW * 4, (cuuint64_t)g.inH, (cuuint64_t)g.inD, (cuuint64_t)g.N};
   const cuuint64_t strides[3] = {(cuuint64_t)g.inW * 16, (cuuint64_t)g.inW * g.inH * 16, (cuuint64_t)g.in_img * 2};
   const cuuint32_t box[4] = {(cuuint32_t)pl.PW * 4, (cuuint32_t)pl.box_h, 1, 1};
@@ -1274,6 +1305,8 @@ int launch_tc2_gather(int cin, int cout, const Geom* gs, int ng, const GatherArg
   const bool want_auxs = aux_staging && a.aux_bf16 && a.aux_mode != 0 && a.aux != nullptr;
   if (!t2_build_plan(cin, cout, gs, ng, merged, pl, want_tma, a.in_scale != nullptr, want_auxs)) { set_error("plane-folded tensor-core path: unsupported geometry"); return VG_EINVAL; }
   if (pl.hb > 0) {                                // TMA-direct staging of a bf16 input
+    if (pl.sd == 2 && cin == 8 && cout == 8) return launch_tc2_t<8, 8, 2, true>(merged, a, pl, st);
+    if (pl.sd == 2 && cin == 8 && cout == 16) return launch_tc2_t<8, 16, 2, true>(merged, a, pl, st);
     if (cin == 8 && cout == 1) return launch_tc2_t<8, 1, 1, true>(merged, a, pl, st);
     if (cin == 8 && cout == 8) return launch_tc2_t<8, 8, 1, true>(merged, a, pl, st);
     if (cin == 8 && cout == 16) return launch_tc2_t<8, 16, 1, true>(merged, a, pl, st);
