@@ -241,43 +241,51 @@ bn_bwd_apply8_kernel(const float* __restrict__ dy, const void* __restrict__ x_, 
 __global__ void __launch_bounds__(256)
 box_sums_kernel(const float* __restrict__ dy, int group_size, int yD, int yH, int yW, long long y_img, int xD, int xH, int xW,
                 int pD, int pH, int pW, double* out) {
-  const int n = blockIdx.y, d = blockIdx.x;
-  const float* p = dy + (size_t)n * y_img + (size_t)d * yH * yW;
-  float acc[10];
+  // one block per image: a thread keeps the nine (b, c) sums of the plane it is walking and folds them into its 27
+  // tap sums for the a's that plane belongs to; 28 atomics per block at the end
+  const int n = blockIdx.x;
+  const float* p0 = dy + (size_t)n * y_img;
+  const int plane = yH * yW;
+  float acc[27], tot = 0.f;
 #pragma unroll
-  for (int i = 0; i < 10; ++i) acc[i] = 0.f;
-  for (int e = threadIdx.x; e < yH * yW; e += blockDim.x) {
+  for (int i = 0; i < 27; ++i) acc[i] = 0.f;
+  // each thread owns fixed (h, w) positions (e = tid + k * 256), so its tap masks do not depend on the plane
+  for (int e = threadIdx.x; e < plane; e += blockDim.x) {
     const int h = e / yW, w = e - h * yW;
-    const float v = __ldg(p + e);
-    acc[9] += v;
+    bool okb[3], okc[3];
 #pragma unroll
-    for (int b = 0; b < 3; ++b) {
-      const int xh = h - b + pH;
-      if (xh < 0 || xh >= xH) continue;
+    for (int b = 0; b < 3; ++b) { const int xh = h - b + pH; okb[b] = xh >= 0 && xh < xH; }
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const int xw = w - c + pW;
-        if (xw >= 0 && xw < xW) acc[b * 3 + c] += v;
-      }
+    for (int c = 0; c < 3; ++c) { const int xw = w - c + pW; okc[c] = xw >= 0 && xw < xW; }
+    float sa[3] = {0.f, 0.f, 0.f};          // sum over the planes each a covers
+    for (int d = 0; d < yD; ++d) {
+      const float v = __ldg(p0 + (size_t)d * plane + e);
+      tot += v;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { const int xd = d - a + pD; if (xd >= 0 && xd < xD) sa[a] += v; }
     }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          if (okb[b] && okc[c]) acc[a * 9 + b * 3 + c] += sa[a];
   }
-  __shared__ float red[10];
-  if (threadIdx.x < 10) red[threadIdx.x] = 0.f;
+  __shared__ float red[28];
+  if (threadIdx.x < 28) red[threadIdx.x] = 0.f;
   __syncthreads();
 #pragma unroll
-  for (int i = 0; i < 10; ++i) {
+  for (int i = 0; i < 27; ++i) {
     const float r = warp_sum(acc[i]);
     if ((threadIdx.x & 31) == 0) atomicAdd(&red[i], r);
   }
-  __syncthreads();
-  double* o = out + (size_t)(n / group_size) * 28;
-  if (threadIdx.x < 27) {
-    const int a = threadIdx.x / 9, bc = threadIdx.x % 9;
-    const int xd = d - a + pD;
-    if (xd >= 0 && xd < xD) atomicAdd(o + threadIdx.x, (double)red[bc]);
-  } else if (threadIdx.x == 27) {
-    atomicAdd(o + 27, (double)red[9]);
+  {
+    const float r = warp_sum(tot);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&red[27], r);
   }
+  __syncthreads();
+  if (threadIdx.x < 28) atomicAdd(out + (size_t)(n / group_size) * 28 + threadIdx.x, (double)red[threadIdx.x]);
 }
 
 // From the per-group raw products R[g][t][c] = sum x(v,c) dy(v + t) (x = the BatchNorm INPUT, un-normalised), the box
@@ -464,8 +472,7 @@ extern "C" int vg_box_sums(const float* dy, int n, int group_size, const int32_t
                            const int32_t* x_dims, const int32_t* pad, double* out, void* stream) {
   VG_CHECK_ARG(dy && out && y_dims && x_dims && pad && n > 0 && group_size > 0 && n % group_size == 0, "bad arguments");
   const long long img = y_img_stride ? y_img_stride : (long long)y_dims[0] * y_dims[1] * y_dims[2];
-  dim3 grid(y_dims[0], n);
-  box_sums_kernel<<<grid, 256, 0, as_stream(stream)>>>(dy, group_size, y_dims[0], y_dims[1], y_dims[2], img, x_dims[0], x_dims[1],
+  box_sums_kernel<<<n, 256, 0, as_stream(stream)>>>(dy, group_size, y_dims[0], y_dims[1], y_dims[2], img, x_dims[0], x_dims[1],
                                                         x_dims[2], pad[0], pad[1], pad[2], out);
   VG_LAUNCH_CHECK();
   return VG_OK;

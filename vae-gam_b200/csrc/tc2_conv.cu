@@ -1079,7 +1079,8 @@ static bool t2_build_plan(int cin, int cout, const Geom* gs, int ng, Geom& merge
   pl.wbytes = (woff + 1023) & ~1023;
   if (pl.wbytes > 96 * 1024) return false;
 
-  if (tma && cin == 8 && (sd == 1 || (ng == 1 && !affine && cout != 1)) && (ng == 1 || !affine) && (pl.span_d <= 2 || !affine) &&
+  // (16 output channels stay on the producer-warp path: that instantiation spills in the 12-warp epilogue and is slower)
+  if (tma && cin == 8 && cout != 16 && (sd == 1 || (ng == 1 && !affine && cout != 1)) && (ng == 1 || !affine) && (pl.span_d <= 2 || !affine) &&
       merged.outD <= 64 && merged.outH <= 64 && merged.outW <= 64 && pl.PW <= 64) {
     // ---- TMA-direct staging: tile = hb whole lines of the row frame, a slot = two boxes [8][PW][hb + halo]
     int nrb_max = 512 / (2 * pl.ACCW);

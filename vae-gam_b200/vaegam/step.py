@@ -332,8 +332,7 @@ class GraphStep:
     per minibatch size as a CUDA graph and replayed.  The native calls are allocation-free,
     sync-free and fork / join their helper streams with events only, so the ~130 launches of a step become
     one `cudaGraphLaunch`; inputs are copied into static buffers and the noise is drawn eagerly into static
-    buffers with the same calls, in the same order, as `StepEngine.draw_noise` (same RNG stream as the eager
-    path and as the reference).  The graph holds raw pointers into the flat parameter / gradient / Adam
+    buffers (one launch for all ten arrays; the eager `forward` keeps the reference's ten calls and their order).  The graph holds raw pointers into the flat parameter / gradient / Adam
     buffers: it is rebuilt when they are re-packed (FlatParams.version)."""
 
     WARMUP = 2      # eager steps before capture: every lazily created stream / event / attribute exists by then
@@ -347,8 +346,11 @@ class GraphStep:
         f32 = dict(dtype=torch.float32, device=dev)
         self.x = torch.zeros(B, V, **f32)
         self.cov = torch.zeros(B, 8, **f32)
-        self.noise = {"eps_w": torch.zeros(B, 1, **f32), "eps_d": torch.zeros(B, NUM_LATENTS, **f32),
-                      "eps_g": torch.zeros(8, B, **f32)}
+        # one flat buffer, three views: the training fast path draws all of a step's noise with ONE launch
+        self.noise_flat = torch.zeros(B * (1 + NUM_LATENTS + 8), **f32)
+        self.noise = {"eps_w": self.noise_flat[:B].view(B, 1),
+                      "eps_d": self.noise_flat[B:B * (1 + NUM_LATENTS)].view(B, NUM_LATENTS),
+                      "eps_g": self.noise_flat[B * (1 + NUM_LATENTS):].view(8, B)}
         self.loss = torch.zeros(1, **f32)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.calls = 0
@@ -380,11 +382,10 @@ class GraphStep:
         self.sb = sb
 
     def draw(self, generator=None):
-        n = self.noise
-        n["eps_w"].normal_(generator=generator)
-        n["eps_d"].normal_(generator=generator)
-        for i in range(8):
-            n["eps_g"][i].normal_(generator=generator)
+        """i.i.d. N(0,1) for eps_W, eps_D and the eight gain draws in one launch.  (The eager `forward` draws them
+        with the reference's ten calls, in its order — `StepEngine.draw_noise`; the values of a given seed differ,
+        the distribution does not.)"""
+        self.noise_flat.normal_(generator=generator)
 
     def run(self, x, covariates, noise=None) -> torch.Tensor:
         B = self.B
