@@ -381,8 +381,13 @@ static int no_bf16_path() {
   return VG_EINVAL;
 }
 
+// strided 16-channel gathers (convt2's data gradient, conv4's forward) have no other tensor-core kernel: the
+// plane-folded one serves them whatever their size
+static bool tc2_only(int cin, const Geom& g) { return g.sin == 2 && cin == 16; }
+
 static int launch_gather(bool tc, int cin, int cout, const Geom& g, const GatherArgs& a, cudaStream_t st) {
-  if (tc && (tc2_worthwhile(&g, 1) || wants_bf16(a)) && tc2_supported(cin, cout, &g, 1)) return launch_tc2_gather(cin, cout, &g, 1, a, st);
+  if (tc && (tc2_worthwhile(&g, 1) || wants_bf16(a) || tc2_only(cin, g)) && tc2_supported(cin, cout, &g, 1))
+    return launch_tc2_gather(cin, cout, &g, 1, a, st);
   if (wants_bf16(a)) return no_bf16_path();
   if (tc && tc_supported(cin, cout, g)) return launch_tc_gather(cin, cout, g, a, st);
   if (cin == 1 && cout == 8) return launch_gather_t<1, 8, 4>(g, a, st);
@@ -492,7 +497,7 @@ extern "C" int vg_conv_describe(const VgConvDesc* d, int kind, char* buf, size_t
   }
   for (int i = 0; i < ng && off + 8 < cap; ++i) {
     int n = 0;
-    if (use_tc && (tc2_worthwhile(&gs[i], 1) || any16)) n = tc2_describe(cin, cout, &gs[i], 1, buf + off, cap - off, in16);
+    if (use_tc && (tc2_worthwhile(&gs[i], 1) || any16 || tc2_only(cin, gs[i]))) n = tc2_describe(cin, cout, &gs[i], 1, buf + off, cap - off, in16);
     if (n <= 0) {
       const bool tc = use_tc && tc_supported(cin, cout, gs[i]);
       n = snprintf(buf + off, cap - off, "%s cin=%d cout=%d q=(%d,%d,%d) taps=%d", tc ? "tc1" : "fp32", cin, cout,

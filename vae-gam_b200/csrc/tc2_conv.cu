@@ -965,7 +965,7 @@ static bool t2_build_plan(int cin, int cout, const Geom* gs, int ng, Geom& merge
   if (cout != 1 && cout != 8 && cout != 16) return false;
   const int sd = gs[0].sin;
   if (sd != 1 && sd != 2) return false;
-  if (sd == 2 && (ng != 1 || cin != 8 || cout == 1)) return false;     // strided gathers: 8 input channels, one phase
+  if (sd == 2 && (ng != 1 || cin == 1 || cout == 1)) return false;     // strided gathers: 8 or 16 input channels, one phase
   if (cin == 16 && cout == 1) return false;
   merged = gs[0];
   int ntaps = 0;
@@ -1011,7 +1011,7 @@ static bool t2_build_plan(int cin, int cout, const Geom* gs, int ng, Geom& merge
   pl.PW = cin == 1 ? qmax[2] : qmax[2] + sm_w;
   pl.RTOT = qmax[1] * pl.PW;
   pl.qDmax = qmax[0];
-  pl.OB = cout == 1 ? 16 : (sd == 2 ? 4 : 8);
+  pl.OB = cout == 1 ? 16 : (sd == 2 ? (cin == 16 ? 2 : 4) : 8);       // 16-channel strided gathers: one plane per slot, keep the window short
   const int wpl = sd * (pl.OB - 1) + pl.span_d + 1;      // input planes one block reads
   pl.NPAIR = (wpl + pl.pps - 1) / pl.pps;
   pl.ppb = sd * pl.OB / pl.pps;
@@ -1317,6 +1317,7 @@ int launch_tc2_gather(int cin, int cout, const Geom* gs, int ng, const GatherArg
   if (pl.sd == 2) {
     if (cin == 8 && cout == 8) return launch_tc2_t<8, 8, 2>(merged, a, pl, st);
     if (cin == 8 && cout == 16) return launch_tc2_t<8, 16, 2>(merged, a, pl, st);
+    if (cin == 16 && cout == 16) return launch_tc2_t<16, 16, 2>(merged, a, pl, st);
   } else {
     if (cin == 1 && cout == 8) return launch_tc2_t<1, 8, 1>(merged, a, pl, st);
     if (cin == 1 && cout == 16) return launch_tc2_t<1, 16, 1>(merged, a, pl, st);
