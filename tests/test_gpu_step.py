@@ -245,6 +245,46 @@ def test_bf16_mode_trains_like_fp32_mode(tmp_path):
     assert np.abs(a - b).max() <= 1e-2 * np.abs(a).max(), (a, b)
 
 
+@pytest.mark.parametrize("arith", ["fp32", "mixed"])
+def test_loss_curve_follows_the_reference(tmp_path, arith):
+    """Few-epoch loss curve of BASELINE configs[0] in miniature against the UNMODIFIED reference
+    (tests/golden/curve_config1.npz, made by tests/golden/make_curve.py on the CPU): 3 epochs x 4 unshuffled
+    minibatches of the control experiment through forward / backward / Adam with the reference's noise injected
+    step by step.  The reference's fp32 GP algebra puts its own losses ~3e-4 from the truth; the curve
+    must be followed within 2e-3 per step in the fp32 check mode and in the default tensor-core mode."""
+    import ast
+    import os
+    import vae_reg_GP
+    from oracle import ref_port as rp
+    from vaegam import synthetic as syn
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "curve_config1.npz"), allow_pickle=False)
+    r = ast.literal_eval(str(g["recipe"]))
+    tr, te, glm, coh = syn.write_experiment(str(tmp_path), n_subjects=r["n_subjects"], config=r["config"], glm=r["glm"])
+    torch.manual_seed(r["param_seed"])
+    m = vae_reg_GP.VAE(save_dir=str(tmp_path), glm_maps=glm, csv_files=[tr, te], num_inducing_pts=r["m"],
+                       gp_kl_scale=r["gp_kl_scale"], glm_reg_scale=r["glm_reg_scale"], neural_covariates=r["neural"])
+    m.arith = arith
+    dev = m.device
+    x_all, cov_all = coh.volumes().to(dev), torch.from_numpy(coh.covariates().copy()).to(dev)
+    ids_all = torch.from_numpy(coh.subject_index().copy()).to(dev)
+    n = x_all.shape[0]
+    k, worst = 0, 0.0
+    for ep in range(r["epochs"]):
+        tot = 0.0
+        for bi, lo in enumerate(range(0, n, r["batch"])):
+            sl = slice(lo, min(n, lo + r["batch"]))
+            noise = rp.draw_noise(sl.stop - sl.start, seed=1000 * ep + bi)
+            loss = float(m.train_batch(ids_all[sl], cov_all[sl], x_all[sl], _noise=noise).item())
+            m.check_status()
+            want = float(g["step_losses"][k])
+            worst = max(worst, abs(loss - want) / abs(want))
+            assert abs(loss - want) <= 2e-3 * abs(want), (arith, ep, bi, loss, want)
+            tot += loss
+            k += 1
+        assert abs(tot / n - float(g["epoch_losses"][ep])) <= 2e-3 * abs(float(g["epoch_losses"][ep]))
+    print(f"[loss curve {arith}] worst relative step deviation from the reference: {worst:.2e}")
+
+
 def test_drop_in_training_loop_decreases_loss(tmp_path):
     """Config-1-like run through the reference-facing API: loaders -> train_epoch (Adam) ->
     save_state/load_state -> reconstruct path."""

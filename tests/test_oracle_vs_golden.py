@@ -87,3 +87,33 @@ def test_numpy_restatement_matches_golden(case):
     assert abs(out["tot"] - float(g["tot"])) / abs(float(g["tot"])) < 2e-6
     assert np.abs(out["x_rec"][:, ::STRIDE[case]] - g["map_full_rec"]).max() < 5e-5
     assert np.abs(out["maps"][0][:, ::STRIDE[case]] - g["map_base"]).max() < 5e-5
+
+
+def test_oracle_port_follows_the_reference_loss_curve():
+    """tests/golden/curve_config1.npz: 12 training steps of the UNMODIFIED reference on the control experiment
+    (make_curve.py).  The fp32 oracle port, fed the same noise and run through the same Adam, must reproduce the
+    first epoch's step losses (the reference's own fp32 GP algebra limits the agreement to ~1e-3)."""
+    import ast
+    import os
+    import tempfile
+    import vae_reg_GP
+    from oracle import ref_port as rp
+    from vaegam import synthetic as syn
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "curve_config1.npz"), allow_pickle=False)
+    r = ast.literal_eval(str(g["recipe"]))
+    work = tempfile.mkdtemp(prefix="curve_")
+    tr, te, glm, coh = syn.write_experiment(work, n_subjects=r["n_subjects"], config=r["config"], glm=r["glm"])
+    torch.manual_seed(r["param_seed"])
+    m = vae_reg_GP.VAE(save_dir=work, glm_maps=glm, csv_files=[tr, te], num_inducing_pts=r["m"], gp_kl_scale=r["gp_kl_scale"],
+                       glm_reg_scale=r["glm_reg_scale"], neural_covariates=r["neural"], device_name="cpu")
+    P = rp.cast_params(rp.params_from_module(m), torch.float32, requires_grad=True)
+    x_all, cov_all = coh.volumes(), torch.from_numpy(coh.covariates().copy())
+    st = {}
+    n = x_all.shape[0]
+    for bi, lo in enumerate(range(0, n, r["batch"])):
+        sl = slice(lo, min(n, lo + r["batch"]))
+        noise = rp.draw_noise(sl.stop - sl.start, seed=bi)             # epoch 0: seed = 1000 * 0 + batch
+        got = rp.training_step_cpu(P, st, x_all[sl].float(), cov_all[sl], noise, gp_kl_scale=r["gp_kl_scale"],
+                                   glm_reg_scale=r["glm_reg_scale"], neural_covariates=r["neural"])
+        want = float(g["step_losses"][bi])
+        assert abs(got - want) <= 1e-3 * abs(want), (bi, got, want)
