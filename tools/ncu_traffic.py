@@ -18,15 +18,16 @@ def val(r, name):
                 "msecond": 1e3, "usecond": 1.0, "nsecond": 1e-3}.get(u, 1.0)
 
 
-OPS = [  # op, kernel regex, pick ("max": longest launch, "min": shortest)
-    ("convt5.fwd", r"tc2_kernel<8, 1, 1>", "max"), ("conv1.dgrad", r"tc2_kernel<8, 1, 1>", "min"),
-    ("convt5.dgrad", r"tc2_kernel<1, 8, 1>", "max"), ("conv1.fwd", r"tc2_kernel<1, 8, 1>", "min"),
-    ("convt4.fwd", r"tc2_kernel<8, 8, 1>", "max"), ("conv2.dgrad", r"tc2_kernel<8, 8, 1>", "min"),
-    ("convt4.dgrad", r"tc2_kernel<8, 8, 2>", "max"),
-    ("convt3.fwd", r"tc2_kernel<16, 8, 1>", "max"), ("convt3.dgrad", r"tc2_kernel<8, 16, 1>", "max"),
+OPS = [  # op, kernel regex, pick ("max": longest launch, "min": shortest) — round-2 instantiations <CIN, COUT, SD, TMA>
+    ("convt5.fwd", r"tc2_kernel<8, 1, 1, 1>", "max"), ("conv1.dgrad", r"tc2_kernel<8, 1, 1, 0>", "max"),
+    ("convt5.dgrad", r"tc2_kernel<1, 8, 1, 0>", "max"), ("conv1.fwd", r"gather_kernel<1, 8, 4>", "max"),
+    ("convt4.fwd", r"tc2_kernel<8, 8, 1, 1>", "max"), ("conv2.dgrad", r"tc2_kernel<8, 8, 1, 0>", "max"),
+    ("convt4.dgrad", r"tc2_kernel<8, 8, 2, 1>", "max"), ("convt2.dgrad", r"tc2_kernel<16, 16, 2, 0>", "max"),
+    ("convt3.fwd", r"tc2_kernel<16, 8, 1, 0>", "max"), ("convt3.dgrad", r"tc2_kernel<8, 16, 1, 0>", "max"),
     ("convt5.wgrad", r"wgrad_mma_kernel<1, 8, 3, 1>", "max"), ("convt4.wgrad", r"wgrad_mma_kernel<8, 8, 12, 1>", "max"),
-    ("convt3.wgrad", r"wgrad_mma_kernel<8, 16, 7, 1>", "max"),
-    ("bnt5.bn_bwd", r"bn_bwd_apply_kernel<8>", "max"), ("bnt3.bn_bwd", r"bn_bwd_apply_kernel<16>", "max"),
+    ("convt3.wgrad", r"wgrad_mma_kernel<8, 16, 7, 1>", "max"), ("convt2.wgrad", r"wgrad_mma_kernel<16, 16, 7, 1>", "max"),
+    ("conv2.fwd", r"gather_kernel<8, 8, 4>", "max"), ("conv3.fwd", r"gather_kernel<8, 16, 4>", "max"),
+    ("bnt3.bn_bwd", r"bn_bwd_apply_kernel<16>", "max"), ("convt5.box_sums", r"box_sums_kernel", "max"),
     ("recon_loss.fwd", r"recon_fwd_kernel", "max"), ("recon_loss.bwd", r"recon_bwd_kernel", "max"),
     ("fc2-fc43.fwd", r"mlp_fwd_kernel<1>", "max"), ("fc5-fc7.fwd", r"mlp_fwd_kernel<2>", "max"),
     ("fc2-fc43.bwd", r"mlp_bwd_kernel<1>", "max"), ("fc5-fc7.bwd", r"mlp_bwd_kernel<2>", "max"),

@@ -291,6 +291,17 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
 
   int pair_base = 0, acc_base = 0;              // running counters, identical in every role
 
+  // Register reallocation between the warpgroups (setmaxnreg): the epilogue warps are the ones that need registers
+  // (accumulator slice, look-ahead buffers of the saved activation, statistics), the TMA / MMA issuers need few.
+  // Budget: 64 K registers per SM = sum over the four warpgroups of 128 threads x their limit.
+  // (producer warps keep a register-staged plane pair: 8- and 16-channel inputs need ~100 registers there, the
+  // 1-channel gathers less — and their epilogue, convt5's data gradient, the most)
+  constexpr int REG_OTHER = TMA ? 56 : (ES == 1 ? 112 : (CIN == 1 ? 88 : 104));
+  constexpr int REG_EPI = TMA ? 152 : (ES == 1 ? 176 : (CIN == 1 ? 168 : 152));
+  static_assert(ES * REG_EPI + (4 - ES) * REG_OTHER <= 512, "register budget");
+  if (warp < EPI_WARPS) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REG_EPI));
+  else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REG_OTHER));
+
   if (warp < EPI_WARPS) {
     // ================================================================ epilogue warps
     const bool want_stats = a.stats != nullptr, want_bn = a.aux_mode == 2, bn_apply = a.aux_mode == 3;
@@ -460,7 +471,8 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
               }
             }
           };
-          auto process = [&](const Item& I, const float (&ax)[NJ][COUT]) {
+          // q8: optional raw bf16 words of the saved activation (deep-prefetch path, COUT == 8: one 16-byte word per plane)
+          auto process = [&](const Item& I, const float (&ax)[NJ][COUT], const uint4* q8 = nullptr) {
             const uint32_t tcol = tmem_base + ((uint32_t)((etid >> 5) * 32) << 16) +
                                   (uint32_t)((buf * pl.nrb + I.rb) * pl.ACCW + I.k * 16);
             uint32_t rr[16];
@@ -501,6 +513,9 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
                       av[2 * c] = bf16_lo(wv); av[2 * c + 1] = bf16_hi(wv);
                     }
                   }
+                }
+                if constexpr (COUT == 8) {
+                  if (q8) unpack_bf16x8(q8[j], av);
                 }
                 if constexpr (AUXS_OK) {
                   if (auxs) {                     // staged chunk (buffer, row block, plane of the block): this thread's row
@@ -564,11 +579,49 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
           Item I0, I1;
           float ax0[NJ][COUT], ax1[NJ][COUT];
           int it = eset;
+          bool deep_done = false;
+          if constexpr (CIN == 1 && COUT == 8 && !TMA) {      // convt5's data gradient: the one launch this matters for
+            // bf16 saved activation with 8 channels = ONE 16-byte word per plane: the registers of the two fp32
+            // look-ahead buffers hold THREE items of raw words instead, i.e. the loads of the next two items are in
+            // flight while one is processed (the epilogue was waiting on these loads, profiles/r2_tc2_source_hotspots.txt)
+            if (a.aux_bf16 && a.aux_mode != 0 && !auxs) {
+              deep_done = true;
+              Item J0, J1, J2;
+              uint4 q0[NJ], q1[NJ], q2[NJ];
+              const __nv_bfloat16* const aux16 = reinterpret_cast<const __nv_bfloat16*>(aux_n);
+              auto fetch = [&](int it_, Item& J, uint4 (&q)[NJ]) {
+                setup(it_, J);
+                if (!J.row_ok) return;
+#pragma unroll
+                for (int j = 0; j < NJ; ++j)
+                  if (J.qd + j < qd_end) q[j] = ldg_u4(aux16 + J.off + (uint32_t)j * plane_step);
+              };
+              if (it < nitems) fetch(it, J0, q0);
+              if (it + ES < nitems) fetch(it + ES, J1, q1);
+              mbar_wait(smem_u32(&accf_bar[buf]), (uint32_t)((au >> 1) & 1));
+              tc_fence_after();
+              while (it < nitems) {
+                if (it + 2 * ES < nitems) fetch(it + 2 * ES, J2, q2);
+                process(J0, ax0, q0);
+                it += ES;
+                if (it >= nitems) break;
+                if (it + 2 * ES < nitems) fetch(it + 2 * ES, J0, q0);
+                process(J1, ax0, q1);
+                it += ES;
+                if (it >= nitems) break;
+                if (it + 2 * ES < nitems) fetch(it + 2 * ES, J1, q1);
+                process(J2, ax0, q2);
+                it += ES;
+              }
+            }
+          }
+          if (!deep_done) {
           if (it < nitems) { setup(it, I0); load_aux(I0, ax0); }
           mbar_wait(smem_u32(&accf_bar[buf]), (uint32_t)((au >> 1) & 1));
           tc_fence_after();
           if (auxs) mbar_wait(smem_u32(&auxf_bar[buf]), (uint32_t)((au >> 1) & 1));       // this unit's aux chunks have landed
-          while (it < nitems) {
+          }
+          while (!deep_done && it < nitems) {
             if (it + ES < nitems) { setup(it + ES, I1); load_aux(I1, ax1); }
             process(I0, ax0);
             it += ES;
