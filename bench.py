@@ -80,6 +80,17 @@ def conv_extra_bytes(name, kind):
     return 4.0 * vi * cin if (kind == "dgrad" and name != "conv1") else 0.0
 
 
+def absorbed_layer_bytes(op, B):
+    """Layer-by-layer fp32 bytes (the accounting of SURVEY §8(d)(iii)) of the reference layers ONE launch of `op`
+    replaces, where that is more than the convolution pass itself.  convt5.dgrad also executes bnt5's BatchNorm +
+    ReLU backward in its epilogue: dgrad reads dy (1 ch) and writes dX (8 ch); the absorbed
+    BatchNorm backward would then read dX and the saved activation and write its own dX (3 x 8 ch)."""
+    if op == "convt5.dgrad":
+        cin, cout, taps, vo, vi = _CONV["convt5"]
+        return 9 * B * 4.0 * (vo * cout + vi * cin + 3 * vi * cin)
+    return None
+
+
 def op_work(op, B, extended=False):
     """Algorithmic (flops, bytes) of one recorded operation at minibatch B; None if not modelled."""
     layer, _, kind = op.partition(".")
@@ -657,6 +668,14 @@ def main():
                     "ms": top["ms_per_step"], "share_of_step": top["share"],
                     "tensor_frac": round(top["gflops"] / 1e3 / tf_peak, 5),
                     "tensor_pipe_pct_ncu": nf.get("tensor_pipe_pct") if nf else None}
+            ab = absorbed_layer_bytes(top["op"], B)
+            if ab:
+                ab_gbs = ab / (top["ms_per_step"] * 1e-3) / 1e9
+                roof["layers_absorbed"] = {
+                    "bytes": ab, "achieved": round(ab_gbs, 1), "frac": round(ab_gbs / hbm_peak, 4),
+                    "rule": "fp32 layer-by-layer bytes (8(d)(iii) accounting) of the two reference layers this launch executes: "
+                            "the convolution data gradient AND bnt5's BatchNorm+ReLU backward fused into its epilogue; "
+                            "not the headline frac, which stays the strict 8(d)(ii) figure of the convolution alone"}
         rl = [r for r in rows if r["op"].startswith("recon_loss")]
         kernels["fused_loss"] = [{"op": r["op"], "gbs": r.get("gbs"), "frac_hbm": round(r.get("gbs", 0) / hbm_peak, 4)} for r in rl]
         for bb in (128, 512):       # alone, inputs (0.36 / 1.4 GB) larger than L2: the stage's own roofline figure
