@@ -195,7 +195,11 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
   const int col_step = grouped ? (int)((gridDim.x - my_grp + pl.groups - 1) / pl.groups) : (int)gridDim.x;
   const int col_count = grouped ? g.group_size * cols_per_img : g.N * cols_per_img;
   const int col_img0 = grouped ? my_grp * g.group_size : 0;
-  const int per_dc = (grouped ? g.group_size : g.N) * pl.ntiles;      // columns per d-chunk index
+  const int col_imgs = grouped ? g.group_size : g.N;
+  const int per_dc = col_imgs * pl.ntiles;                            // columns per d-chunk index
+  // Columns inside a d-chunk are TILE major (all images of tile 0, then tile 1, ...): the last tile of the row frame may
+  // hold fewer live 128-row blocks (t2_live_rb) and is then cheaper, so a CTA's round-robin share has to mix the tiles.
+  auto live_rb = [&](int t) { return TMA ? pl.nrb : min(pl.nrb, (pl.RTOT - t * pl.TR + 127) >> 7); };
   const float* fold_scale = (TMA && a.in_scale) ? a.in_scale + (size_t)my_grp * CIN : nullptr;
   const float* fold_shift = (TMA && a.in_scale) ? a.in_shift + (size_t)my_grp * CIN : nullptr;
 
@@ -306,7 +310,7 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
     // ================================================================ epilogue warps
     const bool want_stats = a.stats != nullptr, want_bn = a.aux_mode == 2, bn_apply = a.aux_mode == 3;
     const int eset = warp >> 2, etid = tid & 127;            // TMEM lane = etid
-    const int ipr = pl.ACCW >> 4, nitems = pl.nrb * ipr;     // 16-column items per row block / per accumulator
+    const int ipr = pl.ACCW >> 4;                            // 16-column items per row block
     const int ipr_shift = 31 - __clz(ipr);                   // ACCW is 16, 32, 64 or 128: ipr is a power of two
     const uint32_t plane_out = (uint32_t)(g.outH * g.outW * COUT);   // offsets inside ONE image fit 32 bits
     const uint32_t plane_step = (uint32_t)g.sout * plane_out;
@@ -365,17 +369,18 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
       }
     };
     if (auxs && tid == 0 && col_first < col_count) {       // first unit of this CTA
-      const int dc = col_first / per_dc, t_ = (col_first - dc * per_dc) % pl.ntiles, n_ = col_img0 + (col_first - dc * per_dc) / pl.ntiles;
+      const int dc = col_first / per_dc, t_ = (col_first - dc * per_dc) / col_imgs, n_ = col_img0 + (col_first - dc * per_dc) % col_imgs;
       const int qd0_ = dc * pl.dchunk, qd1_ = min(pl.qDmax, qd0_ + pl.dchunk);
       aux_issue(n_, t_, qd0_, min((int)pl.ph[0].qD, qd1_), 0);
     }
     for (int col = col_first; col < col_count; col += col_step) {
       // d-chunk major: the chunks of an image differ in length (the last one is short), so all the long columns come
       // first and a CTA's round-robin share mixes long and short ones whatever the parity of the grid
-      const int dc = col / per_dc, t = (col - dc * per_dc) % pl.ntiles, n = col_img0 + (col - dc * per_dc) / pl.ntiles;
+      const int dc = col / per_dc, t = (col - dc * per_dc) / col_imgs, n = col_img0 + (col - dc * per_dc) % col_imgs;
       const int qd0 = dc * pl.dchunk, qd1 = min(pl.qDmax, qd0 + pl.dchunk);
       const int nblocks = (qd1 - qd0 + pl.OB - 1) / pl.OB;
       const int grp = n / g.group_size;
+      const int nitems = live_rb(t) * ipr;                   // items per accumulator: dead row blocks are never accumulated, never drained
       // image bases (64-bit once per column); bf16 tensors have the same element offsets at half the size
       float* const out_n = a.out ? (a.out_bf16 ? reinterpret_cast<float*>(reinterpret_cast<__nv_bfloat16*>(a.out) + (size_t)n * g.out_img)
                                                : a.out + (size_t)n * g.out_img) : nullptr;
@@ -404,7 +409,7 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
             bool have = b + 1 < nblocks;
             if (!have && col + col_step < col_count) {
               const int c2 = col + col_step, dc2 = c2 / per_dc;
-              t_ = (c2 - dc2 * per_dc) % pl.ntiles; n_ = col_img0 + (c2 - dc2 * per_dc) / pl.ntiles;
+              t_ = (c2 - dc2 * per_dc) / col_imgs; n_ = col_img0 + (c2 - dc2 * per_dc) % col_imgs;
               qdf = dc2 * pl.dchunk;
               qde = min((int)P.qD, min(pl.qDmax, qdf + pl.dchunk));
               have = true;
@@ -665,7 +670,7 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
         for (int col = col_first; col < col_count; col += col_step) {
           // d-chunk major: the chunks of an image differ in length (the last one is short), so all the long columns come
       // first and a CTA's round-robin share mixes long and short ones whatever the parity of the grid
-      const int dc = col / per_dc, t = (col - dc * per_dc) % pl.ntiles, n = col_img0 + (col - dc * per_dc) / pl.ntiles;
+      const int dc = col / per_dc, t = (col - dc * per_dc) / col_imgs, n = col_img0 + (col - dc * per_dc) % col_imgs;
           const int qd0 = dc * pl.dchunk, qd1 = min(pl.qDmax, qd0 + pl.dchunk);
           const int nblocks = (qd1 - qd0 + pl.OB - 1) / pl.OB;
           const int npairs = nblocks * H2 + (pl.NPAIR - H2);
@@ -703,7 +708,7 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
     for (int col = col_first; col < col_count; col += col_step) {
       // d-chunk major: the chunks of an image differ in length (the last one is short), so all the long columns come
       // first and a CTA's round-robin share mixes long and short ones whatever the parity of the grid
-      const int dc = col / per_dc, t = (col - dc * per_dc) % pl.ntiles, n = col_img0 + (col - dc * per_dc) / pl.ntiles;
+      const int dc = col / per_dc, t = (col - dc * per_dc) / col_imgs, n = col_img0 + (col - dc * per_dc) % col_imgs;
       const int qd0 = dc * pl.dchunk, qd1 = min(pl.qDmax, qd0 + pl.dchunk);
       const int nblocks = (qd1 - qd0 + pl.OB - 1) / pl.OB;
       const int npairs = nblocks * H2 + (pl.NPAIR - H2);
@@ -728,7 +733,7 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
           const int s = ptid + k * PT;
           goff[sg][k] = -1;
           if (sg == 0) wlim[k] = 0;
-          if (s < pl.SR) {
+          if (s < pl.SR - (pl.nrb - live_rb(t)) * 128) {      // rows the live row blocks' shifted windows reach
             const int rr = t * pl.TR + s;
             const int hh = rr / pl.PW, ww = rr - hh * pl.PW;
             const int ih = SD * hh + (sg >> 1) + pl.lo_h, iw = SD * ww + (sg & 1) + pl.lo_w;
@@ -951,6 +956,7 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
       const int dc = col / per_dc;
       const int qd0 = dc * pl.dchunk, qd1 = min(pl.qDmax, qd0 + pl.dchunk);
       const int nblocks = (qd1 - qd0 + pl.OB - 1) / pl.OB;
+      const int nrb_t = live_rb((col - dc * per_dc) / col_imgs);     // a warp without a live row block still waits and commits
       for (int b = 0; b < nblocks; ++b)
         for (int ph = 0; ph < pl.nph; ++ph) {
           const int au = acc_base + b * pl.nph + ph, buf = au & 1;
@@ -965,7 +971,7 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
             }
             if (elect_one()) {
               const int m1 = pl.ph[ph].pair_begin[p + 1];
-              for (int rb = rb0; rb < pl.nrb; rb += NMW) {
+              for (int rb = rb0; rb < nrb_t; rb += NMW) {
                 const uint32_t d_buf = tmem_base + (uint32_t)((buf * pl.nrb + rb) * pl.ACCW);
                 const uint32_t a_lo0 = ((ring16 + (uint32_t)rb * 128u + (uint32_t)slot * ((uint32_t)PAIRB >> 4)) & 0x3FFFu) | lbo_field;
 #pragma unroll 4
