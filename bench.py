@@ -624,7 +624,7 @@ def main():
     kernels, roof = {}, None
     if not args.no_profile and rank == 0:
         native.profile(True)
-        ksteps = 3
+        ksteps = 5
         for i in range(ksteps):          # local steps only: the other ranks are not in this pass
             idx = batch_idx(i)
             loss = model.forward(sidx[idx], covs[idx], vols[idx], 'train', train_mode=False)
@@ -634,12 +634,20 @@ def main():
         torch.cuda.synchronize()
         rec = native.profile_collect()
         native.profile(False)
-        total = sum(sum(v) for v in rec.values())
+        # per-step time of an operation = the MEDIAN over the profiled steps of that step's instances (an eager pass
+        # shares the box with the host: one stalled launch must not pass for a kernel's duration)
+        def step_median(v):
+            per = len(v) // ksteps
+            if per < 1 or per * ksteps != len(v):
+                return sum(v) / ksteps
+            return float(np.median([sum(v[i * per:(i + 1) * per]) for i in range(ksteps)]))
+        med = {op: step_median(v) for op, v in rec.items()}
+        total = sum(med.values())
         rows = []
         for op, v in rec.items():
-            per_step = sum(v) / ksteps
+            per_step = med[op]
             w = op_work(op, B)
-            row = {"op": op, "ms_per_step": round(per_step, 4), "share": round(sum(v) / total, 4)}
+            row = {"op": op, "ms_per_step": round(per_step, 4), "share": round(per_step / total, 4)}
             if w:
                 row["gflops"] = round(w[0] / (per_step * 1e-3) / 1e9, 1)
                 row["gbs"] = round(w[1] / (per_step * 1e-3) / 1e9, 1)
@@ -651,7 +659,7 @@ def main():
                         row["tensor_pipe_pct_ncu"] = nf["tensor_pipe_pct"]
             rows.append(row)
         rows.sort(key=lambda r: -r["ms_per_step"])
-        kernels = {"ops": rows, "profiled_ms_per_step": round(total / ksteps, 3)}
+        kernels = {"ops": rows, "profiled_ms_per_step": round(total, 3), "profiled_steps": ksteps, "statistic": "median over steps"}
         top = next((r for r in rows if "gbs" in r), None)
         if top:
             w = op_work(top["op"], B)
