@@ -87,30 +87,6 @@ struct T2Plan {
 // roles per (cin, cout): the side that moves more bytes gets more warps
 __host__ __device__ constexpr int t2_epi_sets(int cin, int cout, int sd) { return (sd == 2 || (cin == 8 && cout == 1)) ? 1 : 2; }
 
-// ---- TMA (cp.async.bulk.tensor) primitives
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// one 4-D box (line words, h, d, n) of the tensor map -> shared memory; completion is signalled on the mbarrier (bytes)
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-// contiguous global -> shared bulk copy (UBLKCP); 16-byte aligned, size a multiple of 16; completion on the mbarrier
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-// one 5-D box (channel, w, h, d, n) — the strided variant: element strides (1, 2, 2, 1, 1) pick one (h, w)-parity sub-grid
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3,
-                                            int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
 constexpr int T2_MAX_CLS = 5;      // tap-validity classes per output dimension (k <= 5 would give more; TMA mode has k = 3)
 __host__ __device__ constexpr int t2_max_chunk(int cin, int es, int sd) {
   return sd == 2 ? 1 : (cin == 8 ? (es == 1 ? 2 : 4) : (cin == 16 ? (es == 1 ? 2 : 3) : (es == 1 ? 3 : 5)));
@@ -1329,6 +1305,25 @@ static int make_tmap(const Geom& g, const T2Plan& pl, const void* base, CUtensor
                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (rc != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)rc); return VG_ECUDA; }
   return VG_OK;
+}
+
+bool tma_available() { return tma_enabled(); }
+bool make_tmap_voxels(const void* base, int C, int W, int H, int D, int N, long long img_stride_elems, int bw, int bh, int bd,
+                      CUtensorMap* tm) {
+  // (channel, w) is ONE dimension of 32-bit words (C / 2 per voxel), so a box row is bw whole voxels = a contiguous
+  // run of bw * C * 2 bytes (16-byte box rows are what makes a tensor copy slow)
+  const int wpv = C / 2;
+  if (!tma_enabled() || (C != 8 && C != 16) || bw < 1 || bh < 1 || bd < 1 || bw * wpv > 256 || bh > 256 || bd > 256) return false;
+  const cuuint64_t dims[4] = {(cuuint64_t)W * wpv, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+  const cuuint64_t strides[3] = {(cuuint64_t)W * C * 2, (cuuint64_t)W * H * C * 2, (cuuint64_t)img_stride_elems * 2};
+  const cuuint32_t box[4] = {(cuuint32_t)(bw * wpv), (cuuint32_t)bh, (cuuint32_t)bd, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  if (((uintptr_t)base & 15) || (strides[2] & 15)) return false;
+  memset(tm, 0, sizeof(*tm));
+  const CUresult rc = tma_encoder()(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, const_cast<void*>(base), dims, strides, box, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return rc == CUDA_SUCCESS;
 }
 
 template <int CIN, int COUT, int SD, bool TMA = false>

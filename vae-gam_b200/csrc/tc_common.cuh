@@ -1,5 +1,6 @@
 // tcgen05 / TMEM / mbarrier primitives shared by the tensor-core kernels (sm_100a inline PTX).
 #pragma once
+#include <cuda.h>          // CUtensorMap
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -98,6 +99,38 @@ __device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// ---- TMA (cp.async.bulk.tensor) primitives
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// one 4-D box (line words, h, d, n) of the tensor map -> shared memory; completion is signalled on the mbarrier (bytes)
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// contiguous global -> shared bulk copy (UBLKCP); 16-byte aligned, size a multiple of 16; completion on the mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// one 5-D box (channel, w, h, d, n) — the strided variant: element strides (1, 2, 2, 1, 1) pick one (h, w)-parity sub-grid
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3,
+                                            int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+// host side (tc2_conv.cu): tensor map of a channels-last bf16 tensor (N, D, H, W, C), C = 8 or 16, as a 4-D map
+// (w * C / 2 32-bit words, h, d, n) with a box of [bd][bh][bw] whole voxels — the kernel's w coordinate is in WORDS
+// (voxel * C / 2); false when TMA is switched off (VAEGAM_TMA=0), the driver entry point is missing, the box row
+// exceeds 256 words or the tensor is not 16-byte aligned.  Out-of-range box coordinates are zero-filled.
+bool tma_available();      // VAEGAM_TMA != 0 and cuTensorMapEncodeTiled resolved
+bool make_tmap_voxels(const void* base, int C, int W, int H, int D, int N, long long img_stride_elems, int bw, int bh, int bd,
+                      CUtensorMap* tm);
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);

@@ -13,6 +13,9 @@
 // tap shift and the stride are just per-lane row addresses.  CTAs are persistent over tiles;
 // accumulators are flushed once per CTA (shared-memory reduce, then one global atomic per weight).
 #include <cuda_bf16.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -34,6 +37,8 @@ struct WmGeom {
   int ntaps, tg, taps_per_group;
   uint32_t mul_tH, mul_tW, mul_sH, mul_sW;   // ceil(2^32 / d) for the staging index decomposition (0: d == 1)
   int x_bf16, y_bf16;    // x / dy stored as bf16 (8 or 16 channels): staged by a straight 16-byte copy when nothing is folded
+  int un_tma, sh_tma;    // that copy is ONE cp.async.bulk.tensor box per tile (tensor maps in the kernel parameters)
+  int nbuf;              // operand buffers in shared memory: 2 with TMA staging (the next tile's boxes travel during the MMAs)
 };
 
 __device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
@@ -42,6 +47,11 @@ __device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
 }
 __device__ __forceinline__ void ldsm_x2_t(uint32_t addr, uint32_t (&r)[2]) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
 }
 __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -62,9 +72,11 @@ template <int C, bool BIAS, int UV>
 __device__ __forceinline__ void stage_box_bf16(__nv_bfloat16* dst, const float* __restrict__ src, int oD, int oH, int oW,
                                                int bh, int bw, int nvox, uint32_t mul_h, uint32_t mul_w, int gD, int gH,
                                                int gW, const float* sc, const float* sh, const int (&own)[6],
-                                               float (&bs)[8], bool src16 = false) {
+                                               float (&bs)[8], bool src16 = false, __nv_bfloat16* dst1 = nullptr) {
   constexpr int PER = C >= 8 ? C / 8 : 1;        // 16-byte bf16 chunks per voxel
-  constexpr int U = C >= 8 ? UV : 4;             // elements in flight per thread (registers are shared with the accumulators)
+  // elements in flight per thread (registers are shared with the accumulators).  One channel: a box is ~14 elements per
+  // thread, all of them in flight at once — each further round is one more exposed global-load latency per tile
+  constexpr int U = C >= 8 ? UV : 16;
   const int nel = nvox * PER;
   for (int e0 = threadIdx.x; e0 < nel; e0 += U * blockDim.x) {
     float4 va[U], vb[U];
@@ -138,7 +150,9 @@ __device__ __forceinline__ void stage_box_bf16(__nv_bfloat16* dst, const float* 
           if (BIAS && state[u] == 3) bs[0] += t;
           if (sc) t = fmaf(t, sc[0], sh[0]);
         }
-        dst[e] = __float2bfloat16(t);
+        const __nv_bfloat16 tb = __float2bfloat16(t);
+        dst[e] = tb;
+        if (dst1 && e > 0) dst1[e - 1] = tb;       // second copy, one element ahead: odd pair addresses become aligned words
       }
     }
   }
@@ -174,8 +188,9 @@ template <int CS, int CU, int MT, int MODE>
 __global__ void __launch_bounds__(256, 2)
 wgrad_mma_kernel(const __grid_constant__ WmGeom g, const float* __restrict__ x, const float* __restrict__ dy,
                  const float* __restrict__ in_scale, const float* __restrict__ in_shift, float* dw, float* dbias,
-                 float* dw_group) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
+                 float* dw_group, const __grid_constant__ CUtensorMap tm_un, const __grid_constant__ CUtensorMap tm_sh) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t s_tma_bar[2];
   __shared__ int s_tapoff[48];
   __shared__ float s_bias[16];
   constexpr int NT = CU / 8;                       // n8 tiles
@@ -188,27 +203,62 @@ wgrad_mma_kernel(const __grid_constant__ WmGeom g, const float* __restrict__ x, 
   const int tap_hi = min(g.ntaps, tap_lo + g.taps_per_group);
   const int tile_vox = g.tD * g.tH * g.tW, box_vox = g.sD * g.sH * g.sW;
   const int nchunks = (tile_vox + 15) >> 4;
-  __nv_bfloat16* Ssh = reinterpret_cast<__nv_bfloat16*>(smem_raw);                       // shifted operand: box
-  const size_t sh_bytes = (((size_t)box_vox * CS * 2 + 64) + 15) & ~(size_t)15;           // + slack for clamped taps
-  __nv_bfloat16* Sun = reinterpret_cast<__nv_bfloat16*>(smem_raw + sh_bytes);             // un-shifted operand: tile (+ pad chunk)
+  const size_t sh_one = (((size_t)box_vox * CS * 2 + 64) + 127) & ~(size_t)127;           // + slack for clamped taps; TMA destinations are 128-byte aligned
+  // One shifted channel: a second copy of the box, one element ahead, so that the (voxel, voxel + 1) pair of an A
+  // fragment register is ONE aligned 32-bit word whatever the parity of the tap offset (pair_ok below).
+  const size_t sh_bytes = CS == 1 ? 2 * sh_one : sh_one;
+  const size_t un_bytes = ((size_t)nchunks * 16 * CU * 2 + 127) & ~(size_t)127;           // un-shifted operand: tile (+ pad chunk)
+  // Operand buffers [shifted box | un-shifted tile] x nbuf: with TMA staging the boxes of tile i + 1 travel while
+  // tile i is multiplied (two buffers, one mbarrier each).  Then the voxel-offset table and, with two buffers, the
+  // reduction scratch of flush() (with one buffer it reuses the operand memory).
+  const int nbuf = g.nbuf;
+  const size_t buf_stride = sh_bytes + un_bytes;
   // box offset of every tile voxel (the tile geometry is the same for all tiles): no divisions in the chunk loop
-  unsigned short* s_vo = reinterpret_cast<unsigned short*>(smem_raw + sh_bytes + (size_t)nchunks * 16 * CU * 2);
+  unsigned short* s_vo = reinterpret_cast<unsigned short*>(smem_raw + (size_t)nbuf * buf_stride);
+  float* const red_scratch = nbuf == 2 ? reinterpret_cast<float*>(smem_raw + (size_t)nbuf * buf_stride + (((size_t)nchunks * 32 + 127) & ~(size_t)127))
+                                       : reinterpret_cast<float*>(smem_raw);
   for (int v = threadIdx.x; v < nchunks * 16; v += blockDim.x) {
-    const int vv = min(v, tile_vox - 1);               // padded rows of the last chunk meet zero B rows
+    // padded rows of the last chunk meet zero B rows; they keep the parity of their index (pair loads need even offsets)
+    const int vv = v < tile_vox ? v : max(0, tile_vox - 2 + (v & 1) - (tile_vox & 1));
     const int l = vv % g.tW, rr = vv / g.tW;
     const int j = rr % g.tH, i = rr / g.tH;
     s_vo[v] = (unsigned short)(((i * g.s) * g.sH + j * g.s) * g.sW + l * g.s);
   }
   if (threadIdx.x < 16) s_bias[threadIdx.x] = 0.f;
+  const bool any_tma = g.un_tma || g.sh_tma;
+  if (any_tma && threadIdx.x == 0) {
+    mbar_init(smem_u32(&s_tma_bar[0]), 1);
+    mbar_init(smem_u32(&s_tma_bar[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  // zero the un-shifted rows of the last chunk's padding (tile_vox .. 16*nchunks) of every buffer: never overwritten
+  for (int b = 0; b < nbuf; ++b)
+    for (int e = threadIdx.x; e < (nchunks * 16 - tile_vox) * CU / 8; e += blockDim.x)
+      reinterpret_cast<uint4*>(smem_raw + (size_t)b * buf_stride + sh_bytes + (size_t)tile_vox * CU * 2)[e] = make_uint4(0u, 0u, 0u, 0u);
   float bsum[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) bsum[c] = 0.f;
-  const uint32_t ssh_addr = (uint32_t)__cvta_generic_to_shared(Ssh), sun_addr = (uint32_t)__cvta_generic_to_shared(Sun);
+  const uint32_t smem_addr0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
 
   if (threadIdx.x < 48) {
     const int t = min((int)threadIdx.x, g.ntaps - 1);
     const int ka = t / (g.kH * g.kW), kb = (t / g.kW) % g.kH, kc = t % g.kW;
     s_tapoff[threadIdx.x] = (ka * g.sH + kb) * g.sW + kc;
+  }
+
+  // CS == 1 fast path (see the A fragments below): byte offset of a tap's pair word, per m16 tile and row half
+  const bool pair_ok = CS == 1 && g.s == 1 && !(g.tW & 1) && !(g.sW & 1);
+  uint32_t pair_off[CS == 1 ? MT : 1][2];
+  if constexpr (CS == 1) {
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int t = min(tap_lo + mt * 16 + (lane >> 2) + hf * 8, max(tap_hi, 1) - 1);
+        const int ka = t / (g.kH * g.kW), kb = (t / g.kW) % g.kH, kc = t % g.kW;
+        const int off = (ka * g.sH + kb) * g.sW + kc;
+        pair_off[mt][hf] = (off & 1) ? (uint32_t)sh_one + 2u * (uint32_t)(off - 1) : 2u * (uint32_t)off;
+      }
   }
 
   float acc[MT][NT][4];
@@ -225,7 +275,7 @@ wgrad_mma_kernel(const __grid_constant__ WmGeom g, const float* __restrict__ x, 
   // reduce the warps' accumulators through shared memory (which holds no tile at that point), then one global
   // atomic per weight into `dst` laid out by (st_t, st_cs, st_cu)
   auto flush = [&](float* dst, int st_t, int st_cs, int st_cu) {
-    float* red = reinterpret_cast<float*>(smem_raw);            // [tap][shifted ch][un-shifted ch]
+    float* red = red_scratch;                                   // [tap][shifted ch][un-shifted ch]
     for (int e = threadIdx.x; e < nred; e += blockDim.x) red[e] = 0.f;
     __syncthreads();
     {
@@ -262,15 +312,47 @@ wgrad_mma_kernel(const __grid_constant__ WmGeom g, const float* __restrict__ x, 
   const long long t_end = grouped ? (t_begin + span < ntiles ? t_begin + span : ntiles) : ntiles;
   const long long t_step = grouped ? 1 : (long long)gridDim.x;
   int cur_grp = -1;
-  for (long long tile = t_begin; tile < t_end; tile += t_step) {
-    const int n = (int)(tile / tiles_per_img);
+  // operands that are already bf16 with nothing to fold / sum go straight to shared memory: one TMA box per tile
+  // (zero-filled outside the tensor) when the launch carries tensor maps, else one cp.async per voxel part
+  const bool x16 = g.x_bf16 != 0, y16 = g.y_bf16 != 0;
+  const bool x_async = x16 && !in_scale, y_async = y16 && !dbias;
+  const bool skip_un = g.un_tma && (MODE == 0 ? y_async : x_async);                 // travels by TMA
+  const bool skip_sh = CS >= 8 && g.sh_tma && (MODE == 0 ? x_async : y_async);
+  const bool tma_wait = skip_un || skip_sh;
+  auto tile_origin = [&](long long tile, int& n, int& td, int& th, int& tw) {
+    n = (int)(tile / tiles_per_img);
     int tr = (int)(tile - (long long)n * tiles_per_img);
-    const int tw = tr % g.nTw; tr /= g.nTw;
-    const int th = tr % g.nTh;
-    const int td = tr / g.nTh;
+    tw = tr % g.nTw; tr /= g.nTw;
+    th = tr % g.nTh;
+    td = tr / g.nTh;
+  };
+  auto tma_issue = [&](long long tile, int buf) {          // thread 0 only
+    int n, td, th, tw;
+    tile_origin(tile, n, td, th, tw);
     const int q0d = td * g.tD, q0h = th * g.tH, q0w = tw * g.tW;
+    const uint32_t bar = smem_u32(&s_tma_bar[buf]);
+    const uint32_t sh_a = smem_addr0 + (uint32_t)((size_t)buf * buf_stride), un_a = sh_a + (uint32_t)sh_bytes;
+    fence_async_smem();                        // earlier generic-proxy accesses of this buffer are ordered before the async writes
+    mbar_arrive_expect_tx(bar, (skip_un ? (uint32_t)tile_vox * CU * 2u : 0u) + (skip_sh ? (uint32_t)box_vox * CS * 2u : 0u));
+    // the maps' w coordinate counts 32-bit words: C / 2 per voxel
+    if (skip_un) tma_load_4d(un_a, &tm_un, bar, q0w * (CU / 2), q0h, q0d, n);
+    if (skip_sh) {
+      if (MODE == 0) tma_load_4d(sh_a, &tm_sh, bar, q0w * g.s * (CS / 2), q0h * g.s, q0d * g.s, n);
+      else tma_load_4d(sh_a, &tm_sh, bar, (q0w * g.s - g.pW) * (CS / 2), q0h * g.s - g.pH, q0d * g.s - g.pD, n);
+    }
+  };
+  if (tma_wait && nbuf == 2 && threadIdx.x == 0 && t_begin < t_end) tma_issue(t_begin, 0);
+  int tile_no = 0;
+  for (long long tile = t_begin; tile < t_end; tile += t_step, ++tile_no) {
+    int n, td, th, tw;
+    tile_origin(tile, n, td, th, tw);
+    const int q0d = td * g.tD, q0h = th * g.tH, q0w = tw * g.tW;
+    const int buf = nbuf == 2 ? (tile_no & 1) : 0;
+    __nv_bfloat16* const Ssh = reinterpret_cast<__nv_bfloat16*>(smem_raw + (size_t)buf * buf_stride);          // shifted operand: box
+    __nv_bfloat16* const Ssh1 = CS == 1 ? reinterpret_cast<__nv_bfloat16*>(smem_raw + (size_t)buf * buf_stride + sh_one) : nullptr;
+    __nv_bfloat16* const Sun = reinterpret_cast<__nv_bfloat16*>(smem_raw + (size_t)buf * buf_stride + sh_bytes);
+    const uint32_t ssh_addr = smem_addr0 + (uint32_t)((size_t)buf * buf_stride), sun_addr = ssh_addr + (uint32_t)sh_bytes;
     // bf16 tensors have the same element offsets at half the element size
-    const bool x16 = g.x_bf16 != 0, y16 = g.y_bf16 != 0;
     const float* xn = x16 ? reinterpret_cast<const float*>(reinterpret_cast<const __nv_bfloat16*>(x) + (size_t)n * g.x_img)
                           : x + (size_t)n * g.x_img;
     const float* yn = y16 ? reinterpret_cast<const float*>(reinterpret_cast<const __nv_bfloat16*>(dy) + (size_t)n * g.y_img)
@@ -283,21 +365,24 @@ wgrad_mma_kernel(const __grid_constant__ WmGeom g, const float* __restrict__ x, 
       if (cur_grp >= 0 && grp != cur_grp) flush(dw_group + (size_t)cur_grp * nred, CS * CU, CU, 1);
       cur_grp = grp;
     }
+    if (tma_wait && threadIdx.x == 0) {
+      if (nbuf == 2) { if (tile + t_step < t_end) tma_issue(tile + t_step, buf ^ 1); }       // the NEXT tile, into the other buffer
+      else tma_issue(tile, 0);
+    }
     // un-shifted tile: clipped to the base grid (voxels of the tile beyond it contribute zeros)
     const int none[6] = {0, 0, 0, 0, 0, 0};
-    // operands that are already bf16 with nothing to fold / sum go straight to shared memory (cp.async)
-    const bool x_async = x16 && !sc, y_async = y16 && !dbias;
     if (MODE == 0) {
       // dY is the un-shifted tile: tiles partition the output grid
       const int own[6] = {q0d, q0d + g.tD, q0h, q0h + g.tH, q0w, q0w + g.tW};
       if constexpr (CS >= 8) {
-        if (x_async) stage_box_async<CS>(Ssh, reinterpret_cast<const __nv_bfloat16*>(xn), q0d * g.s, q0h * g.s, q0w * g.s, g.sH, g.sW,
+        if (x_async && !skip_sh) stage_box_async<CS>(Ssh, reinterpret_cast<const __nv_bfloat16*>(xn), q0d * g.s, q0h * g.s, q0w * g.s, g.sH, g.sW,
                                          box_vox, g.mul_sH, g.mul_sW, g.xD, g.xH, g.xW);
       }
       if (!(CS >= 8 && x_async))
       stage_box_bf16<CS, false, UV>(Ssh, xn, q0d * g.s, q0h * g.s, q0w * g.s, g.sH, g.sW, box_vox, g.mul_sH, g.mul_sW, g.xD, g.xH,
-                                g.xW, sc, sh, none, bsum, x16);
-      if (y_async) stage_box_async<CU>(Sun, reinterpret_cast<const __nv_bfloat16*>(yn), q0d, q0h, q0w, g.tH, g.tW, tile_vox, g.mul_tH,
+                                g.xW, sc, sh, none, bsum, x16, Ssh1);
+      if (skip_un) {
+      } else if (y_async) stage_box_async<CU>(Sun, reinterpret_cast<const __nv_bfloat16*>(yn), q0d, q0h, q0w, g.tH, g.tW, tile_vox, g.mul_tH,
                                        g.mul_tW, g.yD, g.yH, g.yW);
       else if (dbias) stage_box_bf16<CU, true, UV>(Sun, yn, q0d, q0h, q0w, g.tH, g.tW, tile_vox, g.mul_tH, g.mul_tW, g.yD, g.yH, g.yW,
                                           nullptr, nullptr, own, bsum, y16);
@@ -309,25 +394,25 @@ wgrad_mma_kernel(const __grid_constant__ WmGeom g, const float* __restrict__ x, 
       const int own[6] = {td == 0 ? 0 : q0d * g.s - g.pD, td == g.nTd - 1 ? g.yD : (q0d + g.tD) * g.s - g.pD,
                           th == 0 ? 0 : q0h * g.s - g.pH, th == g.nTh - 1 ? g.yH : (q0h + g.tH) * g.s - g.pH,
                           tw == 0 ? 0 : q0w * g.s - g.pW, tw == g.nTw - 1 ? g.yW : (q0w + g.tW) * g.s - g.pW};
-      if (x_async) stage_box_async<CU>(Sun, reinterpret_cast<const __nv_bfloat16*>(xn), q0d, q0h, q0w, g.tH, g.tW, tile_vox, g.mul_tH,
+      if (skip_un) {
+      } else if (x_async) stage_box_async<CU>(Sun, reinterpret_cast<const __nv_bfloat16*>(xn), q0d, q0h, q0w, g.tH, g.tW, tile_vox, g.mul_tH,
                                        g.mul_tW, g.xD, g.xH, g.xW);
       else
       stage_box_bf16<CU, false, UV>(Sun, xn, q0d, q0h, q0w, g.tH, g.tW, tile_vox, g.mul_tH, g.mul_tW, g.xD, g.xH, g.xW, sc, sh,
                                 none, bsum, x16);
       if constexpr (CS >= 8) {
-        if (y_async) stage_box_async<CS>(Ssh, reinterpret_cast<const __nv_bfloat16*>(yn), q0d * g.s - g.pD, q0h * g.s - g.pH,
+        if (y_async && !skip_sh) stage_box_async<CS>(Ssh, reinterpret_cast<const __nv_bfloat16*>(yn), q0d * g.s - g.pD, q0h * g.s - g.pH,
                                          q0w * g.s - g.pW, g.sH, g.sW, box_vox, g.mul_sH, g.mul_sW, g.yD, g.yH, g.yW);
       }
       if (CS >= 8 && y_async) {
       } else if (dbias) stage_box_bf16<CS, true, UV>(Ssh, yn, q0d * g.s - g.pD, q0h * g.s - g.pH, q0w * g.s - g.pW, g.sH, g.sW, box_vox,
-                                          g.mul_sH, g.mul_sW, g.yD, g.yH, g.yW, nullptr, nullptr, own, bsum, y16);
+                                          g.mul_sH, g.mul_sW, g.yD, g.yH, g.yW, nullptr, nullptr, own, bsum, y16, Ssh1);
       else stage_box_bf16<CS, false, UV>(Ssh, yn, q0d * g.s - g.pD, q0h * g.s - g.pH, q0w * g.s - g.pW, g.sH, g.sW, box_vox,
-                                     g.mul_sH, g.mul_sW, g.yD, g.yH, g.yW, nullptr, nullptr, none, bsum, y16);
+                                     g.mul_sH, g.mul_sW, g.yD, g.yH, g.yW, nullptr, nullptr, none, bsum, y16, Ssh1);
     }
-    // zero the un-shifted rows of the last chunk's padding (tile_vox .. 16*nchunks)
-    for (int e = threadIdx.x; e < (nchunks * 16 - tile_vox) * CU / 8; e += blockDim.x)
-      reinterpret_cast<uint4*>(Sun + (size_t)tile_vox * CU)[e] = make_uint4(0u, 0u, 0u, 0u);
     cp_async_wait_all();
+    if (tma_wait)                                // every thread observes the completion: the boxes are visible to it
+      mbar_wait(smem_u32(&s_tma_bar[buf]), (uint32_t)((nbuf == 2 ? tile_no >> 1 : tile_no) & 1));
     __syncthreads();
     if (tap_lo >= tap_hi) continue;
 
@@ -369,12 +454,28 @@ wgrad_mma_kernel(const __grid_constant__ WmGeom g, const float* __restrict__ x, 
       } else {
         // one shifted channel: rows of the m16 tile are taps, fragments are gathered element-wise
         const int gq = lane >> 2, q4 = lane & 3;
+        if (pair_ok) {
+          // even tile and box widths, unit stride: voxels (2 q4, 2 q4 + 1) are neighbours along w at an even box offset,
+          // so a register is one 32-bit word of the copy the tap's parity selects
+          const uint32_t a0 = ssh_addr + 2u * (uint32_t)s_vo[c * 16 + 2 * q4], a2 = ssh_addr + 2u * (uint32_t)s_vo[c * 16 + 2 * q4 + 8];
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            if (tap_lo + mt * 16 >= tap_hi) break;
+            uint32_t af[4];
+            af[0] = lds_u32(a0 + pair_off[mt][0]); af[1] = lds_u32(a0 + pair_off[mt][1]);
+            af[2] = lds_u32(a2 + pair_off[mt][0]); af[3] = lds_u32(a2 + pair_off[mt][1]);
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) mma_bf16(acc[mt][nt], af, bf[nt][0], bf[nt][1]);
+          }
+          continue;
+        }
         int vo[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) vo[k] = s_vo[c * 16 + 2 * q4 + (k & 1) + (k >> 1) * 8];
         const unsigned short* S16 = reinterpret_cast<const unsigned short*>(Ssh);
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
+          if (tap_lo + mt * 16 >= tap_hi) break;
           const int ta = min(tap_lo + mt * 16 + gq, tap_hi - 1), tb = min(tap_lo + mt * 16 + gq + 8, tap_hi - 1);
           const int oa = s_tapoff[ta], ob = s_tapoff[tb];
           uint32_t af[4];
@@ -413,20 +514,37 @@ wgrad_mma_kernel(const __grid_constant__ WmGeom g, const float* __restrict__ x, 
   }
 }
 
+// shared-memory bytes of a launch (mirrors the kernel's layout)
+static size_t wm_smem_bytes(int cs, int cu, long long tile, long long box, int ntaps, int nbuf) {
+  const size_t sh_one = (((size_t)box * cs * 2 + 64) + 127) & ~(size_t)127;
+  const size_t sh_bytes = cs == 1 ? 2 * sh_one : sh_one;
+  const size_t nch = (size_t)((tile + 15) / 16);
+  const size_t un_bytes = (nch * 16 * cu * 2 + 127) & ~(size_t)127;
+  const size_t svo = (nch * 32 + 127) & ~(size_t)127;
+  const size_t red = (size_t)ntaps * cs * cu * sizeof(float);
+  size_t smem = (size_t)nbuf * (sh_bytes + un_bytes) + svo + (nbuf == 2 ? red : 0) + 64;
+  return smem > red ? smem : red;
+}
+
 static void wm_pick_tile(int cs, int cu, WmGeom& g) {
-  // q-voxel tile: staged bf16 bytes under ~72 KB (two CTAs per SM), prefer tiles whose staged
-  // box is small relative to the useful voxels (halo amortisation) and that tile the grid evenly
-  const long long budget = 72 * 1024;
+  // q-voxel tile: shared memory under ~72 KB (~110 KB with two operand buffers) so that two CTAs share an SM; prefer
+  // tiles whose staged box is small relative to the useful voxels (halo amortisation) and that tile the grid evenly
+  const long long budget = (g.nbuf == 2 ? 110 : 72) * 1024;
   int best[3] = {1, 1, 1};
   double best_score = -1.0;
   const int candD[] = {1, 2, 3, 4, 6, 8}, candH[] = {1, 2, 4, 6, 8, 12}, candW[] = {4, 7, 8, 14, 16, 17, 33, 35};
   for (int a : candD)
     for (int b : candH)
-      for (int c : candW) {
-        if (a > g.bD || b > g.bH || c > g.bW) continue;
+      for (int c0 : candW) {
+        int c = c0;
+        if (cs == 1 && g.s == 1) {               // one shifted channel: even widths only (pair loads of the A fragments);
+          if (c > g.bW) c = g.bW;                // the full row rounds UP to even, the extra voxel is outside the grid = zeros
+          c += c & 1;
+          if (a > g.bD || b > g.bH) continue;
+        } else if (a > g.bD || b > g.bH || c > g.bW) continue;
         const long long tile = (long long)a * b * c;
         const long long box = (long long)((a - 1) * g.s + g.kD) * ((b - 1) * g.s + g.kH) * ((c - 1) * g.s + g.kW);
-        const long long bytes = box * cs * 2 + ((tile + 15) / 16 * 16) * (cu * 2 + 2) + 256;
+        const long long bytes = (long long)wm_smem_bytes(cs, cu, tile, box, g.ntaps, g.nbuf) + 192;
         if (box > 65535) continue;
         if (bytes > budget) continue;
         const long long nT = (long long)((g.bD + a - 1) / a) * ((g.bH + b - 1) / b) * ((g.bW + c - 1) / c);
@@ -445,21 +563,45 @@ static void wm_pick_tile(int cs, int cu, WmGeom& g) {
 }
 
 template <int CS, int CU, int MT>
-static int launch_wm(const WmGeom& g, const float* x, const float* dy, const float* sc, const float* sh, float* dw,
+static int launch_wm(const WmGeom& g_in, const float* x, const float* dy, const float* sc, const float* sh, float* dw,
                      float* dbias, cudaStream_t st, float* dw_group = nullptr) {
+  WmGeom g = g_in;
   const long long tile = (long long)g.tD * g.tH * g.tW, box = (long long)g.sD * g.sH * g.sW;
-  size_t smem = ((size_t)box * CS * 2 + 64 + 15) / 16 * 16 + (size_t)((tile + 15) / 16 * 16) * (CU * 2 + 2) + 64;
-  const size_t red = (size_t)g.ntaps * CS * CU * sizeof(float);
-  if (red > smem) smem = red;
+  const size_t smem = wm_smem_bytes(CS, CU, tile, box, g.ntaps, g.nbuf);
+  // bf16 operands with nothing to fold or sum: one TMA box per tile (the kernel falls back to cp.async without a map)
+  alignas(64) CUtensorMap tm_un, tm_sh;
+  memset(&tm_un, 0, sizeof(tm_un));
+  memset(&tm_sh, 0, sizeof(tm_sh));
+  {
+    const bool x_plain = g.x_bf16 && !sc, y_plain = g.y_bf16 && !dbias;
+    const bool un_plain = g.mode == 0 ? y_plain : x_plain, sh_plain = CS >= 8 && (g.mode == 0 ? x_plain : y_plain);
+    const void* un_base = g.mode == 0 ? (const void*)dy : (const void*)x;
+    const void* sh_base = g.mode == 0 ? (const void*)x : (const void*)dy;
+    const int* ug = g.mode == 0 ? &g.yD : &g.xD;          // (D, H, W) of the un-shifted / shifted operand's grid
+    const int* sg = g.mode == 0 ? &g.xD : &g.yD;
+    const long long un_img = g.mode == 0 ? g.y_img : g.x_img, sh_img = g.mode == 0 ? g.x_img : g.y_img;
+    g.un_tma = un_plain && make_tmap_voxels(un_base, CU, ug[2], ug[1], ug[0], g.N, un_img, g.tW, g.tH, g.tD, &tm_un);
+    g.sh_tma = sh_plain && make_tmap_voxels(sh_base, CS, sg[2], sg[1], sg[0], g.N, sh_img, g.sW, g.sH, g.sD, &tm_sh);
+  }
   const long long ntiles = (long long)g.nTd * g.nTh * g.nTw * g.N;
   long long blocks = 2LL * vg_sm_count();
   if (blocks > ntiles) blocks = ntiles;
+  static const bool wm_debug = getenv("VAEGAM_WM_DEBUG") != nullptr;
+  if (wm_debug) {
+    int occ = -1;
+    if (g.mode == 0) { cudaFuncSetAttribute(wgrad_mma_kernel<CS, CU, MT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wgrad_mma_kernel<CS, CU, MT, 0>, 256, smem); }
+    else { cudaFuncSetAttribute(wgrad_mma_kernel<CS, CU, MT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wgrad_mma_kernel<CS, CU, MT, 1>, 256, smem); }
+    fprintf(stderr, "[wm] cs=%d cu=%d mode=%d tile=(%d,%d,%d) box=(%d,%d,%d) nT=(%d,%d,%d) smem=%zu nbuf=%d un_tma=%d sh_tma=%d occ=%d ntiles=%lld\n", CS, CU,
+            g.mode, g.tD, g.tH, g.tW, g.sD, g.sH, g.sW, g.nTd, g.nTh, g.nTw, smem, g.nbuf, g.un_tma, g.sh_tma, occ, ntiles);
+  }
   if (g.mode == 0) {
     VG_CUDA(cudaFuncSetAttribute(wgrad_mma_kernel<CS, CU, MT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    wgrad_mma_kernel<CS, CU, MT, 0><<<(unsigned)blocks, 256, smem, st>>>(g, x, dy, sc, sh, dw, dbias, dw_group);
+    wgrad_mma_kernel<CS, CU, MT, 0><<<(unsigned)blocks, 256, smem, st>>>(g, x, dy, sc, sh, dw, dbias, dw_group, tm_un, tm_sh);
   } else {
     VG_CUDA(cudaFuncSetAttribute(wgrad_mma_kernel<CS, CU, MT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    wgrad_mma_kernel<CS, CU, MT, 1><<<(unsigned)blocks, 256, smem, st>>>(g, x, dy, sc, sh, dw, dbias, dw_group);
+    wgrad_mma_kernel<CS, CU, MT, 1><<<(unsigned)blocks, 256, smem, st>>>(g, x, dy, sc, sh, dw, dbias, dw_group, tm_un, tm_sh);
   }
   VG_LAUNCH_CHECK();
   return VG_OK;
@@ -501,8 +643,16 @@ int wgrad_mma(const VgConvDesc* d, const void* x_, const void* dy_, const float*
     g.tg = tg;
     g.taps_per_group = ((tiles + tg - 1) / tg) * tpm;
   };
+  {
+    // plain bf16 operands travel by TMA, double-buffered; the tile is picked for that shared-memory budget
+    const bool x_plain = g.x_bf16 && !in_scale, y_plain = g.y_bf16 && !dbias;
+    const bool un_plain = g.mode == 0 ? y_plain : x_plain;
+    // two buffers only where they do not shrink the tile: with an 8/16-channel shifted box the halo dominates the
+    // bytes and a smaller tile costs more than the prefetch wins (convt4: 0.32 vs 0.24 ms)
+    g.nbuf = (tma_available() && un_plain && cs == 1) ? 2 : 1;
+  }
   wm_pick_tile(cs, cu, g);
-  if (cs == 1 && cu == 8) { groups(16, 3); return launch_wm<1, 8, 3>(g, x, dy, in_scale, in_shift, dw, dbias, st, dw_group); }
+  if (cs == 1 && cu == 8) { groups(16, 2); return launch_wm<1, 8, 2>(g, x, dy, in_scale, in_shift, dw, dbias, st, dw_group); }
   // MT keeps the accumulators at <= 56 registers so that two CTAs share an SM without spills
   if (cs == 8 && cu == 8) { groups(2, 12); return launch_wm<8, 8, 12>(g, x, dy, in_scale, in_shift, dw, dbias, st, dw_group); }
   if (cs == 8 && cu == 16) { groups(2, 7); return launch_wm<8, 16, 7>(g, x, dy, in_scale, in_shift, dw, dbias, st, dw_group); }
