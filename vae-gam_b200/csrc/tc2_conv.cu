@@ -581,17 +581,47 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
               if (it + ES < nitems) fetch(it + ES, J1, q1);
               mbar_wait(smem_u32(&accf_bar[buf]), (uint32_t)((au >> 1) & 1));
               tc_fence_after();
+              // The fused BatchNorm-backward apply writing bf16 (no bias, no activation, no statistics) is THE hot
+              // instance: a body without the runtime switches of the general epilogue, ~1/3 of its instructions
+              const bool lean = bn_apply && a.out_bf16 && out_n && !a.bias && !relu && !sigm && !want_stats;
+              auto process3 = [&](const Item& I, const uint4 (&q)[NJ]) {
+                const uint32_t tcol = tmem_base + ((uint32_t)((etid >> 5) * 32) << 16) +
+                                      (uint32_t)((buf * pl.nrb + I.rb) * pl.ACCW + I.k * 16);
+                uint32_t rr[16];
+                tmem_ld16(tcol, rr);
+                tmem_ld_wait();
+                tmem_zero16(tcol);
+                if (!I.row_ok) return;
+                __nv_bfloat16* const ob = reinterpret_cast<__nv_bfloat16*>(out_n);
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                  if (I.qd + j >= qd_end) continue;
+                  float av[8], y[8];
+                  unpack_bf16x8(q[j], av);
+#pragma unroll
+                  for (int c = 0; c < 8; ++c) {     // dx = (x > 0) * (A dy + B x + C); its sum = the producer's bias gradient
+                    const float v = fmaf(istd[c], __uint_as_float(rr[j * 8 + c]), fmaf(mistd[c], av[c], s2[c]));
+                    y[c] = av[c] > 0.f ? v : 0.f;
+                    s1[c] += y[c];
+                  }
+                  *reinterpret_cast<uint4*>(ob + I.off + (uint32_t)j * plane_step) = pack_bf16x8(y);
+                }
+              };
+              auto run = [&](const Item& I, const uint4 (&q)[NJ]) {
+                if (lean) process3(I, q);
+                else process(I, ax0, q);
+              };
               while (it < nitems) {
                 if (it + 2 * ES < nitems) fetch(it + 2 * ES, J2, q2);
-                process(J0, ax0, q0);
+                run(J0, q0);
                 it += ES;
                 if (it >= nitems) break;
                 if (it + 2 * ES < nitems) fetch(it + 2 * ES, J0, q0);
-                process(J1, ax0, q1);
+                run(J1, q1);
                 it += ES;
                 if (it >= nitems) break;
                 if (it + 2 * ES < nitems) fetch(it + 2 * ES, J1, q1);
-                process(J2, ax0, q2);
+                run(J2, q2);
                 it += ES;
               }
             }
