@@ -291,6 +291,9 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
     const uint32_t plane_out = (uint32_t)(g.outH * g.outW * COUT);   // offsets inside ONE image fit 32 bits
     const uint32_t plane_step = (uint32_t)g.sout * plane_out;
     const bool relu = a.act == VG_ACT_RELU, sigm = a.act == VG_ACT_SIGMOID;
+    // the epilogue's switches as one key (see `process`); combinations a channel count cannot have map to the run-time path
+    const int epi_key = (relu ? 1 : (sigm ? 2 : 0)) | ((a.aux_mode & 3) << 2) | (want_stats ? 0x10 : 0) |
+                        (a.out_bf16 ? 0x20 : 0) | (a.aux_bf16 ? 0x40 : 0);
     // Item = 16 accumulator columns (NJ output planes x COUT) of one 128-row block.  Everything that depends on
     // the ROW only (division by the pitch, validity, offset inside the plane, bias class) is computed once per
     // row block and reused by the items that share it.
@@ -453,7 +456,15 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
             }
           };
           // q8: optional raw bf16 words of the saved activation (deep-prefetch path, COUT == 8: one 16-byte word per plane)
-          auto process = [&](const Item& I, const float (&ax)[NJ][COUT], const uint4* q8 = nullptr) {
+          // KEY >= 0 (a literal at the inlined call sites of run_items below) fixes the epilogue's switches at compile
+          // time: bits 0-1 activation, 2-3 auxiliary mode, 4 statistics, 5 bf16 output, 6 bf16 saved activation — the hot
+          // variants; KEY < 0 reads them at run time
+          auto process = [&](const int KEY, const Item& I, const float (&ax)[NJ][COUT], const uint4* q8 = nullptr) {
+            const bool relu_ = KEY < 0 ? relu : (KEY & 3) == 1, sigm_ = KEY < 0 ? sigm : (KEY & 3) == 2;
+            const int auxm_ = KEY < 0 ? a.aux_mode : (KEY >> 2) & 3;
+            const bool stats_ = KEY < 0 ? want_stats : ((KEY >> 4) & 1) != 0;
+            const bool out16_ = KEY < 0 ? a.out_bf16 != 0 : ((KEY >> 5) & 1) != 0;
+            const bool aux16_ = KEY < 0 ? a.aux_bf16 != 0 : ((KEY >> 6) & 1) != 0;
             const uint32_t tcol = tmem_base + ((uint32_t)((etid >> 5) * 32) << 16) +
                                   (uint32_t)((buf * pl.nrb + I.rb) * pl.ACCW + I.k * 16);
             uint32_t rr[16];
@@ -478,16 +489,16 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
                 if constexpr (BREG) bc = bsrc ? bsrc[c] : b_mid[c];
                 else bc = bsrc[c];
                 float v = __uint_as_float(rr[j * COUT + c]) + bc;
-                if (relu) v = fmaxf(v, 0.f);
-                else if (sigm) v = 1.f / (1.f + __expf(-v));
+                if (relu_) v = fmaxf(v, 0.f);
+                else if (sigm_) v = 1.f / (1.f + __expf(-v));
                 y[c] = v;
               }
-              if (a.aux_mode != 0) {
+              if (auxm_ != 0) {
                 float av[COUT];
 #pragma unroll
                 for (int c = 0; c < COUT; ++c) av[c] = ax[j][c];
                 if constexpr (COUT % 8 == 0) {
-                  if (a.aux_bf16) {
+                  if (aux16_) {
 #pragma unroll
                     for (int c = 0; c < COUT / 2; ++c) {
                       const uint32_t wv = __float_as_uint(ax[j][c]);
@@ -505,10 +516,10 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
                     unpack_bf16x8(q, av);
                   }
                 }
-                if (a.aux_mode == 1) {
+                if (auxm_ == 1) {
 #pragma unroll
                   for (int c = 0; c < COUT; ++c) y[c] = av[c] > 0.f ? y[c] : 0.f;
-                } else if (a.aux_mode == 2) {
+                } else if (auxm_ == 2) {
 #pragma unroll
                   for (int c = 0; c < COUT; ++c) {
                     const float xh = fmaf(av[c], istd[c], -mistd[c]);
@@ -523,7 +534,7 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
                   }
                 }
               }
-              if (want_stats) {
+              if (stats_) {
 #pragma unroll
                 for (int c = 0; c < COUT; ++c) {
                   s1[c] += y[c];
@@ -532,7 +543,7 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
               }
               if (out_n) {
                 if constexpr (COUT % 8 == 0) {
-                  if (a.out_bf16) {
+                  if (out16_) {
                     __nv_bfloat16* pb = reinterpret_cast<__nv_bfloat16*>(out_n) + off;
 #pragma unroll
                     for (int i = 0; i < COUT / 8; ++i) {
@@ -609,7 +620,7 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
               };
               auto run = [&](const Item& I, const uint4 (&q)[NJ]) {
                 if (lean) process3(I, q);
-                else process(I, ax0, q);
+                else process(-1, I, ax0, q);
               };
               while (it < nitems) {
                 if (it + 2 * ES < nitems) fetch(it + 2 * ES, J2, q2);
@@ -632,14 +643,30 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
           tc_fence_after();
           if (auxs) mbar_wait(smem_u32(&auxf_bar[buf]), (uint32_t)((au >> 1) & 1));       // this unit's aux chunks have landed
           }
-          while (!deep_done && it < nitems) {
-            if (it + ES < nitems) { setup(it + ES, I1); load_aux(I1, ax1); }
-            process(I0, ax0);
-            it += ES;
-            if (it >= nitems) break;
-            if (it + ES < nitems) { setup(it + ES, I0); load_aux(I0, ax0); }
-            process(I1, ax1);
-            it += ES;
+          // the item loop, instantiated once per hot combination of the epilogue switches and once with run-time switches
+          auto run_items = [&](const int tag) {
+            while (it < nitems) {
+              if (it + ES < nitems) { setup(it + ES, I1); load_aux(I1, ax1); }
+              process(tag, I0, ax0);
+              it += ES;
+              if (it >= nitems) break;
+              if (it + ES < nitems) { setup(it + ES, I0); load_aux(I0, ax0); }
+              process(tag, I1, ax1);
+              it += ES;
+            }
+          };
+          if (!deep_done) {
+            switch (epi_key) {
+              case 0x31: run_items(0x31); break;      // ReLU + next-layer statistics, bf16 out
+              case 0x21: run_items(0x21); break;      // ReLU, bf16 out
+              case 0x00: run_items(0x00); break;      // plain fp32 out
+              case 0x02: run_items(0x02); break;      // sigmoid, fp32 out
+              case 0x64: run_items(0x64); break;      // ReLU mask from a bf16 activation, bf16 out
+              case 0x04: run_items(0x04); break;      // ReLU mask, fp32
+              case 0x08: run_items(0x08); break;      // BatchNorm-backward sums, fp32
+              case 0x48: run_items(0x48); break;      // BatchNorm-backward sums from a bf16 activation
+              default: run_items(-1); break;
+            }
           }
           tmem_st_wait();
           tc_fence_before();

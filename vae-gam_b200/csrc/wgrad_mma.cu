@@ -74,9 +74,8 @@ __device__ __forceinline__ void stage_box_bf16(__nv_bfloat16* dst, const float* 
                                                int gW, const float* sc, const float* sh, const int (&own)[6],
                                                float (&bs)[8], bool src16 = false, __nv_bfloat16* dst1 = nullptr) {
   constexpr int PER = C >= 8 ? C / 8 : 1;        // 16-byte bf16 chunks per voxel
-  // elements in flight per thread (registers are shared with the accumulators).  One channel: a box is ~14 elements per
-  // thread, all of them in flight at once — each further round is one more exposed global-load latency per tile
-  constexpr int U = C >= 8 ? UV : 16;
+  // elements in flight per thread (registers are shared with the accumulators)
+  constexpr int U = UV;
   const int nel = nvox * PER;
   for (int e0 = threadIdx.x; e0 < nel; e0 += U * blockDim.x) {
     float4 va[U], vb[U];
@@ -196,6 +195,9 @@ wgrad_mma_kernel(const __grid_constant__ WmGeom g, const float* __restrict__ x, 
   constexpr int NT = CU / 8;                       // n8 tiles
   constexpr int UV = MT * NT * 4 <= 16 ? 4 : 2;    // staged voxels in flight per thread: more when the accumulators are few
   constexpr int TPM = CS == 8 ? 2 : (CS == 16 ? 1 : 16);   // taps per m16 tile
+  // one shifted channel: a box is ~14 elements per thread; the transposed layer (convt5) keeps all of them in flight at
+  // once — each further round is one more exposed global-load latency per tile (the forward layer's variant would spill)
+  constexpr int USH = CS >= 8 ? UV : (MODE == 1 ? 16 : 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvw = (blockDim.x >> 5) / g.tg;        // warps sharing a tap group split the voxel chunks
   const int tgi = warp % g.tg, vwi = warp / g.tg;
@@ -379,7 +381,7 @@ wgrad_mma_kernel(const __grid_constant__ WmGeom g, const float* __restrict__ x, 
                                          box_vox, g.mul_sH, g.mul_sW, g.xD, g.xH, g.xW);
       }
       if (!(CS >= 8 && x_async))
-      stage_box_bf16<CS, false, UV>(Ssh, xn, q0d * g.s, q0h * g.s, q0w * g.s, g.sH, g.sW, box_vox, g.mul_sH, g.mul_sW, g.xD, g.xH,
+      stage_box_bf16<CS, false, USH>(Ssh, xn, q0d * g.s, q0h * g.s, q0w * g.s, g.sH, g.sW, box_vox, g.mul_sH, g.mul_sW, g.xD, g.xH,
                                 g.xW, sc, sh, none, bsum, x16, Ssh1);
       if (skip_un) {
       } else if (y_async) stage_box_async<CU>(Sun, reinterpret_cast<const __nv_bfloat16*>(yn), q0d, q0h, q0w, g.tH, g.tW, tile_vox, g.mul_tH,
@@ -405,9 +407,9 @@ wgrad_mma_kernel(const __grid_constant__ WmGeom g, const float* __restrict__ x, 
                                          q0w * g.s - g.pW, g.sH, g.sW, box_vox, g.mul_sH, g.mul_sW, g.yD, g.yH, g.yW);
       }
       if (CS >= 8 && y_async) {
-      } else if (dbias) stage_box_bf16<CS, true, UV>(Ssh, yn, q0d * g.s - g.pD, q0h * g.s - g.pH, q0w * g.s - g.pW, g.sH, g.sW, box_vox,
+      } else if (dbias) stage_box_bf16<CS, true, USH>(Ssh, yn, q0d * g.s - g.pD, q0h * g.s - g.pH, q0w * g.s - g.pW, g.sH, g.sW, box_vox,
                                           g.mul_sH, g.mul_sW, g.yD, g.yH, g.yW, nullptr, nullptr, own, bsum, y16, Ssh1);
-      else stage_box_bf16<CS, false, UV>(Ssh, yn, q0d * g.s - g.pD, q0h * g.s - g.pH, q0w * g.s - g.pW, g.sH, g.sW, box_vox,
+      else stage_box_bf16<CS, false, USH>(Ssh, yn, q0d * g.s - g.pD, q0h * g.s - g.pH, q0w * g.s - g.pW, g.sH, g.sW, box_vox,
                                      g.mul_sH, g.mul_sW, g.yD, g.yH, g.yW, nullptr, nullptr, none, bsum, y16, Ssh1);
     }
     cp_async_wait_all();
