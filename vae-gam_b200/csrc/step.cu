@@ -376,6 +376,8 @@ static int run_encoder(const VgStepIO* io, const EncWs& e, int B, int arith, cud
   }
   { VG_PROF("layout", st);
   VG_TRY(vg_nhwc_to_nchw(e.a5, e.a5f, B, 16, 192, st));   // h.view(-1, 3072) is channel-major
+  }
+  { VG_PROF("fc1.fwd", st);
   VG_TRY(vg_linear_fwd(e.a5f, PF(FC1), PF(FC1 + 1), e.h1, B, 200, 3072, VG_ACT_RELU, st));
   }
   { VG_PROF("fc2-fc43.fwd", st);
@@ -398,6 +400,8 @@ static int run_decoder(const VgStepIO* io, const DecWs& d, const float* zcat, in
   }
   { VG_PROF("layout", st);
   VG_TRY(vg_nchw_to_nhwc(d.f8, d.t0, nd, 16, 240, st));   // view(-1,16,6,8,5) -> channels-last
+  }
+  { VG_PROF("bnt1.bn_stats", st);
   VG_TRY(vg_bn_stats(d.t0, nd, group, 240, 16, d.bnt1.stats, st));
   }
   { VG_PROF("bnt1.bn_finalize", st);
@@ -634,7 +638,13 @@ static int step_bwd_impl(const VgStepConfig* cfg, const VgStepIO* io, void* work
   }
   { VG_PROF("layout", st);
   VG_TRY(vg_nhwc_to_nchw(w.d_t0, w.d_f8, nd, 16, 240, st));     // gradient w.r.t. fc8 pre-activation
-  VG_TRY(vg_linear_bwd(w.d_f8, nullptr, d.f7, PF(FC8), w.d_f7, GF(FC8), GF(FC8 + 1), nd, 3840, 200, st));
+  }
+  { cudaStream_t ws = fk.branch();                               // weight + bias gradient beside the data gradient
+  VG_PROF("fc8.wgrad", ws);
+  VG_TRY(vg_linear_bwd(w.d_f8, nullptr, d.f7, PF(FC8), nullptr, GF(FC8), GF(FC8 + 1), nd, 3840, 200, ws));
+  }
+  { VG_PROF("fc8.dgrad", st);
+  VG_TRY(vg_linear_bwd(w.d_f8, nullptr, d.f7, PF(FC8), w.d_f7, nullptr, nullptr, nd, 3840, 200, st));
   }
   { VG_PROF("fc5-fc7.bwd", st);
   const VgMlp m = dec_stem_mlp(io, d, w.zcat, nd, w.d_zcat, w.d_f7);
@@ -655,8 +665,12 @@ static int step_bwd_impl(const VgStepConfig* cfg, const VgStepIO* io, void* work
   const VgMlp m = enc_head_mlp(io, e, B, w.d_h1, w.dheads);
   VG_TRY(vg_mlp_bwd(&m, st));
   }
-  { VG_PROF("fc1.bwd", st);
-  VG_TRY(vg_linear_bwd(w.d_h1, e.h1, e.a5f, PF(FC1), w.d_a5f, GF(FC1), GF(FC1 + 1), B, 200, 3072, st));
+  { cudaStream_t ws = fk.branch();
+  VG_PROF("fc1.wgrad", ws);
+  VG_TRY(vg_linear_bwd(w.d_h1, e.h1, e.a5f, PF(FC1), nullptr, GF(FC1), GF(FC1 + 1), B, 200, 3072, ws));
+  }
+  { VG_PROF("fc1.dgrad", st);
+  VG_TRY(vg_linear_bwd(w.d_h1, e.h1, e.a5f, PF(FC1), w.d_a5f, nullptr, nullptr, B, 200, 3072, st));
   }
   }
   if (phases & 4u) {
