@@ -552,6 +552,16 @@ static int step_bwd_impl(const VgStepConfig* cfg, const VgStepIO* io, void* work
   VG_LAUNCH_CHECK();
   VgGainParams gp; VgGainGrads gg;
   fill_gain_params(cfg, io, gp, &gg);
+  if (ar == VG_ARITH_BF16) {
+    // fused bnt5 junction (below): the box sums of the reconstruction gradient need nothing but that gradient, so they
+    // run on the helper stream beside convt5's grouped weight gradient; the finalize kernel joins the two
+    cudaStream_t bs = fk.branch();
+    VG_PROF("convt5.box_sums", bs);
+    const int32_t ydims[3] = {kConvT[4].out[0], kConvT[4].out[1], kConvT[4].out[2]};
+    const int32_t xdims[3] = {kConvT[4].in[0], kConvT[4].in[1], kConvT[4].in[2]};
+    const int32_t pads[3] = {0, 0, 0};
+    VG_TRY(vg_box_sums(w.dpre5, nd, B, ydims, VP, xdims, pads, w.j5_box, bs));
+  }
   { cudaStream_t gs = fk.branch();
   VG_PROF("gain.bwd", gs);
   VG_TRY(vg_gain_bwd(&gp, &gg, io->covariates, io->eps_g, io->taps, w.dg, (double)cfg->gp_kl_scale, B, cfg->m,
@@ -570,12 +580,9 @@ static int step_bwd_impl(const VgStepConfig* cfg, const VgStepIO* io, void* work
     // Fused bnt5 junction: the BatchNorm-backward statistics come from the weight-gradient products (which do not
     // depend on the data gradient), so the data gradient's epilogue applies BatchNorm backward + ReLU mask directly
     // and writes the final gradient once, as bf16 — no raw fp32 gradient, no separate pass over the largest tensor.
-    const int32_t ydims[3] = {kConvT[4].out[0], kConvT[4].out[1], kConvT[4].out[2]};
-    const int32_t xdims[3] = {kConvT[4].in[0], kConvT[4].in[1], kConvT[4].in[2]};
-    const int32_t pads[3] = {0, 0, 0};
     { VG_PROF("convt5.wgrad", st);
-    VG_TRY(vg_box_sums(w.dpre5, nd, B, ydims, VP, xdims, pads, w.j5_box, st));
     VG_TRY(vg_conv_wgrad_grouped(&c5, d.t4, w.dpre5, w.j5_raw, st));
+    VG_TRY(fk.join());                            // the box sums (and the gain backward queued behind them)
     VG_TRY(vg_bn_fused_finalize(w.j5_raw, w.j5_box, PF(CONVT5), d.bnt5.scale, d.bnt5.shift, d.bnt5.istd, d.bnt5.mistd, NDEC, 8,
                                 (double)B * vol(kConvT[3].out), GF(CONVT5), GF(CONVT5 + 1), GF(BNT5), GF(BNT5 + 1), w.j5_coef, st));
     }
