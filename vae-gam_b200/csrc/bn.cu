@@ -32,10 +32,21 @@ bn_stats_kernel(const float* __restrict__ x, long long spatial, int group_size, 
       s2[2] = fmaf(v.z, v.z, s2[2]); s2[3] = fmaf(v.w, v.w, s2[3]);
     }
     const int c0 = (int)((((long long)blockIdx.x * blockDim.x + tid) * 4) % C);
+    // lanes that differ by a multiple of C / 4 hold the same four channels: reduce them in the warp first, so a warp
+    // issues C / 4 shared-memory atomics per sum instead of 32 (they serialise: this was 25 us for a 4 MB tensor)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      atomicAdd(&sred[2 * (c0 + j)], (double)s1[j]);
-      atomicAdd(&sred[2 * (c0 + j) + 1], (double)s2[j]);
+    for (int o = 16; o >= C / 4; o >>= 1)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], o);
+        s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], o);
+      }
+    if ((tid & 31) < C / 4) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        atomicAdd(&sred[2 * (c0 + j)], (double)s1[j]);
+        atomicAdd(&sred[2 * (c0 + j) + 1], (double)s2[j]);
+      }
     }
   } else {  // C == 1
     const long long stride = (long long)gridDim.x * blockDim.x;

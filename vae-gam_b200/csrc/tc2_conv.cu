@@ -88,7 +88,12 @@ struct T2Plan {
 __host__ __device__ constexpr int t2_epi_sets(int cin, int cout, int sd) { return (sd == 2 || (cin == 8 && cout == 1)) ? 1 : 2; }
 
 constexpr int T2_MAX_CLS = 5;      // tap-validity classes per output dimension (k <= 5 would give more; TMA mode has k = 3)
+// producer warps per (cin, epilogue sets): one input channel moves few bytes per row but waits for them — six producer
+// warps (two MMA issuer warps then share the four row blocks) with shorter per-thread chunk lists.  (A second pair of
+// look-ahead in the producers' registers measured slower: 0.38-0.41 vs 0.34 ms.)
+__host__ __device__ constexpr int t2_prod_warps(int cin, int es) { return cin == 1 ? 6 : 12 - 4 * es; }
 __host__ __device__ constexpr int t2_max_chunk(int cin, int es, int sd) {
+  if (cin == 1) return 4;
   return sd == 2 ? 1 : (cin == 8 ? (es == 1 ? 2 : 4) : (cin == 16 ? (es == 1 ? 2 : 3) : (es == 1 ? 3 : 5)));
 }
 
@@ -99,9 +104,9 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
   static_assert(!TMA || CIN == 8, "TMA-direct staging: 8 bf16 channels = one 16-byte word per voxel");
   // TMA mode has no producer warps: 12 epilogue warps (3 sets), warp 12 issues the TMA loads, warps 13..15 the MMAs
   constexpr int ES = TMA ? 3 : t2_epi_sets(CIN, COUT, SD);
-  constexpr int MMA_WARP0 = TMA ? 13 : T2_MMA_WARP, NMW = 16 - MMA_WARP0;      // MMA issuer warps
   constexpr int NSG = SD == 2 ? 4 : 1;
-  constexpr int EPI_WARPS = 4 * ES, PROD_WARPS = 12 - EPI_WARPS, PT = PROD_WARPS * 32;
+  constexpr int EPI_WARPS = 4 * ES, PROD_WARPS = TMA ? 0 : t2_prod_warps(CIN, ES), PT = PROD_WARPS * 32;
+  constexpr int MMA_WARP0 = TMA ? 13 : EPI_WARPS + PROD_WARPS, NMW = 16 - MMA_WARP0;      // MMA issuer warps
   constexpr int MAXC = t2_max_chunk(CIN, ES, SD);
   constexpr bool PIPE = SD == 1 && CIN != 16 && ((CIN == 1) || (ES == 1));   // register double-buffering of the staged pair
   constexpr int NJ = 16 / COUT;                        // output planes per epilogue item (16 TMEM columns)
@@ -733,7 +738,7 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
         }
       }
     }
-  } else if (!TMA && warp < T2_MMA_WARP) {
+  } else if (!TMA && warp < MMA_WARP0) {
     // ================================================================ producer warps
     const int ptid = tid - EPI_WARPS * 32;
     const bool affine = a.in_scale != nullptr;
@@ -853,6 +858,7 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
           fence_async_smem();
           mbar_arrive(smem_u32(&full_bar[slot]));
         };
+        {
         Buf v0, v1;
         load_pair(0, v0);
         for (int P = 0; P < npairs; P += 2) {
@@ -862,6 +868,7 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
             if (P + 2 < npairs) load_pair(P + 2, v0);
             store_pair(P + 1, v1);
           }
+        }
         }
       } else {
         // generic path: one [K half][sub-grid] array at a time, its chunks in flight together
@@ -1237,7 +1244,7 @@ static bool t2_build_plan(int cin, int cout, const Geom* gs, int ng, Geom& merge
   }
   // rows per tile: as many 128-row blocks as TMEM (2 buffers), the producers' reach and shared memory allow
   const int es = t2_epi_sets(cin, cout, sd);
-  const int max_sr = t2_max_chunk(cin, es, sd) * (12 - 4 * es) * 32;
+  const int max_sr = t2_max_chunk(cin, es, sd) * t2_prod_warps(cin, es) * 32;
   int nrb_max = 512 / (2 * pl.ACCW);
   if (nrb_max > 4) nrb_max = 4;
   const int need = (pl.RTOT + 127) / 128;
