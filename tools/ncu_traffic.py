@@ -24,7 +24,7 @@ OPS = [  # op, kernel regex, pick ("max": longest launch, "min": shortest) — r
     ("convt4.fwd", r"tc2_kernel<8, 8, 1, 1>", "max"), ("conv2.dgrad", r"tc2_kernel<8, 8, 1, 0>", "max"),
     ("convt4.dgrad", r"tc2_kernel<8, 8, 2, 1>", "max"), ("convt2.dgrad", r"tc2_kernel<16, 16, 2, 0>", "max"),
     ("convt3.fwd", r"tc2_kernel<16, 8, 1, 0>", "max"), ("convt3.dgrad", r"tc2_kernel<8, 16, 1, 0>", "max"),
-    ("convt5.wgrad", r"wgrad_mma_kernel<1, 8, 3, 1>", "max"), ("convt4.wgrad", r"wgrad_mma_kernel<8, 8, 12, 1>", "max"),
+    ("convt5.wgrad", r"wgrad_mma_kernel<1, 8, 2, 1>", "max"), ("convt4.wgrad", r"wgrad_mma_kernel<8, 8, 12, 1>", "max"),
     ("convt3.wgrad", r"wgrad_mma_kernel<8, 16, 7, 1>", "max"), ("convt2.wgrad", r"wgrad_mma_kernel<16, 16, 7, 1>", "max"),
     ("conv2.fwd", r"gather_kernel<8, 8, 4>", "max"), ("conv3.fwd", r"gather_kernel<8, 16, 4>", "max"),
     ("bnt3.bn_bwd", r"bn_bwd_apply_kernel<16>", "max"), ("convt5.box_sums", r"box_sums_kernel", "max"),
