@@ -28,6 +28,7 @@
 // Pipelines: full/empty mbarriers per ring slot (producers <-> MMA via tcgen05.commit), and
 // full/empty per accumulator buffer (MMA <-> epilogue), accumulators double-buffered in TMEM.
 #include <cuda.h>          // CUtensorMap (the encoder itself is fetched through cudaGetDriverEntryPoint: no libcuda link)
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -40,7 +41,7 @@
 namespace vg {
 
 constexpr int T2_THREADS = 16 * 32, T2_MMA_WARP = 12;   // warps 12..15: one MMA issuer per 128-row block
-constexpr int T2_MAX_MMA = 96, T2_MAX_BLK = 96, T2_MAX_PAIR = 10, T2_MAX_RING = 16, T2_MAX_PH = 8;
+constexpr int T2_MAX_MMA = 224, T2_MAX_BLK = 224, T2_MAX_PAIR = 10, T2_MAX_RING = 16, T2_MAX_PH = 8;
 
 // One tcgen05.mma of the list, pre-digested on the host so that the issuing lane only adds bases
 // (the table sits in the kernel parameters = constant bank, read straight into uniform registers).
@@ -664,6 +665,7 @@ tc2_kernel(const __grid_constant__ Geom g, const GatherArgs a, const __grid_cons
             switch (epi_key) {
               case 0x31: run_items(0x31); break;      // ReLU + next-layer statistics, bf16 out
               case 0x21: run_items(0x21); break;      // ReLU, bf16 out
+              case 0x11: run_items(0x11); break;      // ReLU + next-layer statistics, fp32 out (convt2)
               case 0x00: run_items(0x00); break;      // plain fp32 out
               case 0x02: run_items(0x02); break;      // sigmoid, fp32 out
               case 0x64: run_items(0x64); break;      // ReLU mask from a bf16 activation, bf16 out
@@ -1056,27 +1058,30 @@ static inline int t2_ceil_div(int a, int b) { return a >= 0 ? (a + b - 1) / b : 
 
 // tma: TMA-direct staging requested (bf16 input; see T2Plan::hb) — falls back to producer-warp staging (returns
 // true with pl.hb == 0) when the geometry is outside what the TMA path covers.
+// VAEGAM_T2_DEBUG=1: which check of the planner rejected a geometry (stderr)
+#define T2_FAIL(id) do { static const bool dbg = getenv("VAEGAM_T2_DEBUG") != nullptr; \
+    if (dbg) fprintf(stderr, "[t2 plan] cin=%d cout=%d phases=%d rejected at check %d (line %d)\n", cin, cout, ng, id, __LINE__); } while (0)
 static bool t2_build_plan(int cin, int cout, const Geom* gs, int ng, Geom& merged, T2Plan& pl, bool tma = false,
                           bool affine = false, bool auxs = false) {
   pl.hb = 0; pl.box_h = 0; pl.groups = 1; pl.auxs = 0;
-  if (ng < 1 || ng > T2_MAX_PH) return false;
-  if (cin != 1 && cin != 8 && cin != 16) return false;
-  if (cout != 1 && cout != 8 && cout != 16) return false;
+  if (ng < 1 || ng > T2_MAX_PH) { T2_FAIL(1); return false; }
+  if (cin != 1 && cin != 8 && cin != 16) { T2_FAIL(2); return false; }
+  if (cout != 1 && cout != 8 && cout != 16) { T2_FAIL(3); return false; }
   const int sd = gs[0].sin;
-  if (sd != 1 && sd != 2) return false;
-  if (sd == 2 && (ng != 1 || cin == 1 || cout == 1)) return false;     // strided gathers: 8 or 16 input channels, one phase
-  if (cin == 16 && cout == 1) return false;
+  if (sd != 1 && sd != 2) { T2_FAIL(4); return false; }
+  if (sd == 2 && (ng != 1 || cin == 1 || cout == 1)) { T2_FAIL(5); return false; }     // strided gathers: 8 or 16 input channels, one phase
+  if (cin == 16 && cout == 1) { T2_FAIL(6); return false; }
   merged = gs[0];
   int ntaps = 0;
   int lo[3] = {127, 127, 127}, hi[3] = {-127, -127, -127};
   int qmax[3] = {0, 0, 0};
   for (int p = 0; p < ng; ++p) {
     const Geom& g = gs[p];
-    if (g.sin != sd || g.ntaps < 1 || g.sout != gs[0].sout) return false;
-    if (g.inD != gs[0].inD || g.inH != gs[0].inH || g.inW != gs[0].inW) return false;
-    if (g.qD > 32767 || g.qH > 32767 || g.qW > 32767) return false;
+    if (g.sin != sd || g.ntaps < 1 || g.sout != gs[0].sout) { T2_FAIL(7); return false; }
+    if (g.inD != gs[0].inD || g.inH != gs[0].inH || g.inW != gs[0].inW) { T2_FAIL(8); return false; }
+    if (g.qD > 32767 || g.qH > 32767 || g.qW > 32767) { T2_FAIL(9); return false; }
     for (int t = 0; t < g.ntaps; ++t) {
-      if (ntaps >= kMaxTaps) return false;
+      if (ntaps >= kMaxTaps) { T2_FAIL(10); return false; }
       merged.taps[ntaps] = g.taps[t];
       merged.taps[ntaps].pad_ = (int8_t)p;
       ++ntaps;
@@ -1096,7 +1101,7 @@ static bool t2_build_plan(int cin, int cout, const Geom* gs, int ng, Geom& merge
   pl.nsg = sd == 2 ? 4 : 1;
   pl.lo_d = lo[0]; pl.lo_h = lo[1]; pl.lo_w = lo[2];
   pl.span_d = hi[0] - lo[0]; pl.span_h = hi[1] - lo[1]; pl.span_w = hi[2] - lo[2];
-  if (pl.span_d > 4 || pl.span_h > 2 || pl.span_w > 2) return false;
+  if (pl.span_d > 4 || pl.span_h > 2 || pl.span_w > 2) { T2_FAIL(11); return false; }
   int lut[T2_MAX_PH][45];
   for (int p = 0; p < ng; ++p)
     for (int i = 0; i < 45; ++i) lut[p][i] = -1;
@@ -1115,7 +1120,7 @@ static bool t2_build_plan(int cin, int cout, const Geom* gs, int ng, Geom& merge
   pl.NPAIR = (wpl + pl.pps - 1) / pl.pps;
   pl.ppb = sd * pl.OB / pl.pps;
   pl.ACCW = pl.OB * cout;
-  if (pl.NPAIR > T2_MAX_PAIR || pl.ppb > pl.NPAIR) return false;
+  if (pl.NPAIR > T2_MAX_PAIR || pl.ppb > pl.NPAIR) { T2_FAIL(12); return false; }
 
   // MMA list + weight blocks (deduplicated: interior slots share one shift-invariant block)
   struct Key { int ph, rel, nj, dh, dw, off16; };
@@ -1124,7 +1129,7 @@ static bool t2_build_plan(int cin, int cout, const Geom* gs, int ng, Geom& merge
   int nblk = 0, nmma = 0, woff = 0;
   for (int ph = 0; ph < ng; ++ph)
     for (int p = 0; p <= pl.NPAIR; ++p) {
-      if (nmma > 255) return false;
+      if (nmma > 255) { T2_FAIL(13); return false; }
       pl.ph[ph].pair_begin[p] = (uint8_t)nmma;
       if (p == pl.NPAIR) break;
       const int i_lo = pl.pps * p, i_hi = i_lo + pl.pps - 1;
@@ -1156,7 +1161,7 @@ static bool t2_build_plan(int cin, int cout, const Geom* gs, int ng, Geom& merge
               if (keys[k].ph == ph && keys[k].rel == i_lo - sd * j0 && keys[k].nj == nj && keys[k].dh == kh && keys[k].dw == kw)
                 found = k;
             if (found < 0) {
-              if (nblk >= T2_MAX_BLK) return false;
+              if (nblk >= T2_MAX_BLK) { T2_FAIL(14); return false; }
               found = nblk++;
               keys[found] = Key{ph, i_lo - sd * j0, nj, kh, kw, woff >> 4};
               pl.blk[found].i0 = (int8_t)i_lo; pl.blk[found].j0 = (int8_t)j0; pl.blk[found].nj = (int8_t)nj;
@@ -1164,7 +1169,7 @@ static bool t2_build_plan(int cin, int cout, const Geom* gs, int ng, Geom& merge
               pl.blk_off16[found] = (uint16_t)(woff >> 4);
               woff += nj * cout * 32;
             }
-            if (nmma >= T2_MAX_MMA) return false;
+            if (nmma >= T2_MAX_MMA) { T2_FAIL(15); return false; }
             T2Mma& m = pl.mma[nmma];
             m_sg[nmma] = sg; m_mh[nmma] = mh; m_mw[nmma] = cin == 1 ? 0 : mw;
             ++nmma;
@@ -1176,7 +1181,7 @@ static bool t2_build_plan(int cin, int cout, const Geom* gs, int ng, Geom& merge
   pl.nmma = nmma;
   pl.nblk = nblk;
   pl.wbytes = (woff + 1023) & ~1023;
-  if (pl.wbytes > 96 * 1024) return false;
+  if (pl.wbytes > 96 * 1024) { T2_FAIL(16); return false; }
 
   // (16 output channels stay on the producer-warp path: that instantiation spills in the 12-warp epilogue and is slower)
   if (tma && cin == 8 && cout != 16 && (sd == 1 || (ng == 1 && !affine && cout != 1)) && (ng == 1 || !affine) && (pl.span_d <= 2 || !affine) &&
@@ -1229,7 +1234,7 @@ static bool t2_build_plan(int cin, int cout, const Geom* gs, int ng, Geom& merge
       for (int m = 0; m < nmma; ++m) pl.mma[m].a_shift = (uint32_t)(m_sg[m] * pl.SR + m_mh[m] * pl.PW + m_mw[m]);
       int tc = 32;
       while (tc < 2 * pl.nrb * pl.ACCW) tc <<= 1;
-      if (tc > 512) return false;
+      if (tc > 512) { T2_FAIL(17); return false; }
       pl.tmem_cols = tc;
       const int nblocks_all = (pl.qDmax + pl.OB - 1) / pl.OB;
       const long long cols = (long long)merged.N * pl.ntiles;
@@ -1270,7 +1275,7 @@ static bool t2_build_plan(int cin, int cout, const Geom* gs, int ng, Geom& merge
     const double eff = (double)pl.RTOT / ((double)nt * sr);
     if (eff > best_eff * 1.15) { best_eff = eff; best = nrb; best_r = r; }
   }
-  if (best < 1) return false;
+  if (best < 1) { T2_FAIL(18); return false; }
   pl.nrb = best;
   pl.TR = 128 * best;
   pl.SR = (pl.TR + sm_h * pl.PW + (cin == 1 ? 0 : sm_w) + 7) & ~7;
@@ -1280,7 +1285,7 @@ static bool t2_build_plan(int cin, int cout, const Geom* gs, int ng, Geom& merge
   pl.ntiles = (pl.RTOT + pl.TR - 1) / pl.TR;
   int tc = 32;
   while (tc < 2 * pl.nrb * pl.ACCW) tc <<= 1;
-  if (tc > 512) return false;
+  if (tc > 512) { T2_FAIL(19); return false; }
   pl.tmem_cols = tc;
 
   // split columns along d until the persistent grid has at least ~2 columns per SM
