@@ -566,3 +566,23 @@ def test_no_cpu_fallback():
     model, x, cov, ids = build_case(rc, device_name="cpu")
     with pytest.raises(native.NativeError):
         model.forward(ids, cov, x, 'train', train_mode=False)
+
+
+@pytest.mark.gpu
+def test_glm_beta_maps_on_device_match_numpy_lstsq():
+    """the least-squares GLM maps of get_beta_map_regularizer.py:94-107, accumulated block-wise on the
+    GPU (volumes stay where the resident loader keeps them), against numpy's closed form on the host."""
+    from vaegam import glm_maps
+    rng = np.random.default_rng(5)
+    n, v = 96, 4096
+    gamma = rng.normal(size=(n, 7))
+    beta_true = rng.normal(size=(7, v))
+    y = gamma @ beta_true + 0.01 * rng.normal(size=(n, v))
+    sex = rng.normal(size=v)
+    want = np.concatenate([np.linalg.inv(gamma.T @ gamma) @ gamma.T @ y, sex[None]], 0)
+    want = (want / want.max(axis=1, keepdims=True)).T                          # utils.scale_beta_maps: divide by the maximum
+    dev = torch.device("cuda", 0)
+    blocks = [(torch.from_numpy(y[i:i + 32]).float().to(dev), torch.from_numpy(gamma[i:i + 32]).float()) for i in range(0, n, 32)]
+    got = glm_maps.lsq_beta_maps(blocks, torch.from_numpy(sex).to(dev))
+    assert got.shape == (v, 8)
+    np.testing.assert_allclose(got, want, rtol=2e-4, atol=2e-5)
