@@ -48,7 +48,9 @@ __device__ __forceinline__ void store_vec(float* __restrict__ p, const float (&v
   }
 }
 
-template <int CIN, int COUT, int VT>
+// ROW: unit input stride and the taps are a complete 3x3x3 cube sorted by (dd, dh, dw) — a thread then loads each
+// (dd, dh) input row segment ONCE (VT + 2 voxels) and applies the three dw taps to it, instead of VT loads per tap.
+template <int CIN, int COUT, int VT, bool ROW = false>
 __global__ void __launch_bounds__(256)
 gather_kernel(const __grid_constant__ Geom g, const GatherArgs a) {
   extern __shared__ float sw[];  // [ntaps][CIN][COUT]
@@ -93,6 +95,51 @@ gather_kernel(const __grid_constant__ Geom g, const GatherArgs a) {
       }
     }
     const float* in_n = a.in + (size_t)n * g.in_img;
+    if constexpr (ROW) {
+      const int lo_d = g.taps[0].dd, lo_h = g.taps[0].dh, lo_w = g.taps[0].dw;       // tap t = (a * 3 + b) * 3 + c
+      for (int ab = 0; ab < 9; ++ab) {
+        const int id = qd + lo_d + ab / 3, ih = qh + lo_h + ab % 3;
+        if (id < 0 || id >= g.inD || ih < 0 || ih >= g.inH) continue;
+        const float* rowp = in_n + ((size_t)id * g.inH + ih) * g.inW * CIN;
+        float xr[VT + 2][CIN];
+#pragma unroll
+        for (int v = 0; v < VT + 2; ++v) {
+          const int iw = qw0 + v + lo_w;
+          if (iw >= 0 && iw < g.inW) {
+            load_vec<CIN>(rowp + (size_t)iw * CIN, xr[v]);
+            if (affine) {
+#pragma unroll
+              for (int c = 0; c < CIN; ++c) xr[v][c] = fmaf(xr[v][c], sc[c], sh[c]);
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < CIN; ++c) xr[v][c] = 0.f;
+          }
+        }
+#pragma unroll
+        for (int c3 = 0; c3 < 3; ++c3) {
+          const float* wt = sw + (ab * 3 + c3) * (CIN * COUT);
+#pragma unroll
+          for (int ci = 0; ci < CIN; ++ci) {
+            float wr[COUT];
+            if constexpr (COUT % 4 == 0) {
+#pragma unroll
+              for (int i = 0; i < COUT / 4; ++i) {
+                float4 q4 = reinterpret_cast<const float4*>(wt + ci * COUT)[i];
+                wr[4 * i] = q4.x; wr[4 * i + 1] = q4.y; wr[4 * i + 2] = q4.z; wr[4 * i + 3] = q4.w;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < COUT; ++i) wr[i] = wt[ci * COUT + i];
+            }
+#pragma unroll
+            for (int v = 0; v < VT; ++v)
+#pragma unroll
+              for (int co = 0; co < COUT; ++co) acc[v][co] = fmaf(xr[v + c3][ci], wr[co], acc[v][co]);
+          }
+        }
+      }
+    } else
     for (int t = 0; t < g.ntaps; ++t) {
       const Tap tp = g.taps[t];
       const int id = qd * g.sin + tp.dd;
@@ -324,7 +371,7 @@ static int build_geoms(const VgConvDesc* d, int kind, Geom* out /* up to 8 */) {
   return ng;
 }
 
-template <int CIN, int COUT, int VT>
+template <int CIN, int COUT, int VT, bool ROW = false>
 static int launch_gather_t(const Geom& g, const GatherArgs& a, cudaStream_t st) {
   const int nWc = (g.qW + VT - 1) / VT;
   const long long items = (long long)g.qD * g.qH * nWc;
@@ -332,9 +379,26 @@ static int launch_gather_t(const Geom& g, const GatherArgs& a, cudaStream_t st) 
   if (threads < 32) threads = 32;
   dim3 grid(cdiv(items, threads), g.N);
   const size_t smem = (size_t)g.ntaps * CIN * COUT * sizeof(float);
-  gather_kernel<CIN, COUT, VT><<<grid, threads, smem, st>>>(g, a);
+  gather_kernel<CIN, COUT, VT, ROW><<<grid, threads, smem, st>>>(g, a);
   VG_LAUNCH_CHECK();
   return VG_OK;
+}
+
+// unit input stride and a complete 3x3x3 tap cube: `sorted` = g with its taps ordered by (dd, dh, dw) (row-reuse kernel)
+static bool full_cube(const Geom& g, Geom& sorted) {
+  if (g.sin != 1 || g.ntaps != 27) return false;
+  sorted = g;
+  for (int i = 1; i < 27; ++i) {
+    Tap t = sorted.taps[i];
+    int j = i - 1;
+    auto key = [](const Tap& x) { return (x.dd + 64) * 16384 + (x.dh + 64) * 128 + (x.dw + 64); };
+    while (j >= 0 && key(sorted.taps[j]) > key(t)) { sorted.taps[j + 1] = sorted.taps[j]; --j; }
+    sorted.taps[j + 1] = t;
+  }
+  const Tap c0 = sorted.taps[0];
+  for (int t = 0; t < 27; ++t)
+    if (sorted.taps[t].dd != c0.dd + t / 9 || sorted.taps[t].dh != c0.dh + (t / 3) % 3 || sorted.taps[t].dw != c0.dw + t % 3) return false;
+  return true;
 }
 
 // Process default of the arithmetic mode (0 fp32 CUDA cores, 1 bf16 tcgen05, 2 mixed: bf16 tcgen05 with the
@@ -390,6 +454,12 @@ static int launch_gather(bool tc, int cin, int cout, const Geom& g, const Gather
     return launch_tc2_gather(cin, cout, &g, 1, a, st);
   if (wants_bf16(a)) return no_bf16_path();
   if (tc && tc_supported(cin, cout, g)) return launch_tc_gather(cin, cout, g, a, st);
+  {
+    Geom gs;                            // stride-1 3x3x3 layers with few input channels: each input row loaded once per thread
+    if ((cin == 1 && cout == 8) || (cin == 8 && cout == 16)) {
+      if (full_cube(g, gs)) return cin == 1 ? launch_gather_t<1, 8, 6, true>(gs, a, st) : launch_gather_t<8, 16, 4, true>(gs, a, st);
+    }
+  }
   if (cin == 1 && cout == 8) return launch_gather_t<1, 8, 4>(g, a, st);
   if (cin == 8 && cout == 1) return launch_gather_t<8, 1, 4>(g, a, st);
   if (cin == 8 && cout == 8) return launch_gather_t<8, 8, 4>(g, a, st);
