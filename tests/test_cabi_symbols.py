@@ -121,3 +121,36 @@ def test_fused_mlp_validation_without_gpu(built_lib):
     m.layer[0].w, m.layer[0].n, m.layer[0].k, m.layer[0].in_, m.layer[0].out = 16, 10, 300, 0, 1
     assert lib.vg_mlp_fwd(ctypes.byref(m), None) == n.VG_EINVAL                       # k > 224
     assert b"224" in lib.vg_last_error()
+
+
+def test_conv_planner_dispatch_is_host_only_and_stable():
+    """vg_conv_describe is host code (no device work): which kernel serves the decoder's layer passes in the tensor-core
+    arithmetic, checked without a GPU.  Guards the planner's table sizes (convt2's forward needs 153 MMA entries for its
+    8 parity phases) and the TMA / live-row-block geometry of the largest layers."""
+    import ctypes as C
+
+    from vaegam import native
+    lib = native.load()
+
+    def describe(kind, *a, **k):
+        d = native.conv_desc(*a, **k)
+        buf = C.create_string_buffer(8192)
+        n = lib.vg_conv_describe(C.byref(d), kind, buf, len(buf))
+        return n, buf.value.decode()
+
+    bf = native.ARITH_BF16
+    # convt2 (16 -> 16, stride 2, asymmetric padding): forward = ONE plane-folded launch over the 8 parity phases
+    n, s = describe(0, True, 16, 16, (3, 3, 3), 2, (8, 10, 7), 288, 32, pad=(1, 0, 1), opad=(1, 0, 1), arith=bf)
+    assert n == 1 and s.startswith("tc2 ") and "phases=8" in s, s
+    # convt5's data gradient: 1 -> 8 channels, 1551 rows per plane in 512-row tiles (the last one holds 15 live rows)
+    n, s = describe(1, True, 8, 1, (3, 3, 3), 1, (39, 47, 33), 288, 32, arith=bf, bf16_mask=native.BF16_X)
+    assert n == 1 and "cin=1 cout=8" in s and "RTOT=1551" in s and "TR=512" in s and "ntiles=4" in s, s
+    # convt5 / convt4 forward read bf16 activations: TMA-direct staging (tma_hb > 0)
+    for args, kw in (((True, 8, 1, (3, 3, 3), 1, (39, 47, 33), 288, 32), dict(bf16_mask=native.BF16_X)),
+                     ((True, 8, 8, (5, 3, 3), 2, (18, 22, 15), 288, 32), dict(bf16_mask=native.BF16_X | native.BF16_Y))):
+        n, s = describe(0, *args, arith=bf, **kw)
+        hb = int(s.split("tma_hb=")[1].split()[0])
+        assert n == 1 and s.startswith("tc2 ") and hb > 0, s
+    # fp32 arithmetic never reaches a tensor-core kernel
+    n, s = describe(0, True, 8, 1, (3, 3, 3), 1, (39, 47, 33), 288, 32, arith=native.ARITH_FP32)
+    assert "fp32" in s and "tc" not in s.replace("fp32", ""), s
